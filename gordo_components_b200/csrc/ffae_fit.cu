@@ -1,0 +1,427 @@
+// K2: fit of the Dense autoencoder stacks -- one persistent CTA per job trains the whole fit.
+//
+// Replaces scikeras KerasRegressor.fit -> keras Model.fit (gordo/machine/model/models.py:284) for
+// the networks of factories/feedforward_autoencoder.py:65-104:
+//   loss = mean((net(x)-y)^2) + sum_l l1[l]*sum|a_l|,  Adam(lr, b1, b2, eps) [keras defaults 1e-3/.9/.999/1e-7],
+//   every epoch visits a permutation of the job's rows in batches of batch_size (last partial batch kept).
+//
+// A fit is a chain of epochs*ceil(n/batch) dependent optimizer steps of ~3 MFLOP each, so it is latency bound,
+// not roofline bound: the design keeps everything a step needs on chip.  The slot's weights live in shared
+// memory (padded [Kp][Np] image) for the entire fit, every layer's activations of the current mini-batch stay in
+// shared memory for the backward pass, the next mini-batch is gathered with cp.async while the current one is
+// processed, and the Adam moments (opaque state, same padded layout) stream through L2.  Machines (and CV folds,
+// which are just more jobs) are independent, so the grid is simply one CTA per job.
+#include <cuda_pipeline.h>
+#include "gb_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int NWARPS = THREADS / 32;
+constexpr int BR = 32;  // rows of a mini-batch chunk: one row per lane
+
+struct FitArgs {
+  gb_ffnet net;
+  gb::FFImage im;
+  gb_fit_hparams hp;
+  int apitch[GB_MAX_LAYERS + 1];  // pitch of activation buffer l (l = 0: x staging)
+  int aofs[GB_MAX_LAYERS + 1];    // offset of activation buffer l (l >= 1) in smem floats
+  int xofs[2], yofs[2], dofs[2];
+  int ypitch, dpitch;
+  int wfloats, smem_floats;
+  int n_in, n_out, max_rows;
+  long pstride, sstride;
+  float* params;
+  float* adam_m;
+  float* adam_v;
+  const gb_job* jobs;
+  const float *x, *y;
+  const int32_t* perm;
+  float *out_loss, *out_acc;
+};
+
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+  return h;
+}
+
+// keyed bijection on [0, n): 4-round Feistel network on the enclosing power of four, cycle-walked into range
+__device__ __forceinline__ uint32_t permute_index(uint32_t i, uint32_t n, uint32_t key) {
+  if (n <= 2) return (n == 2) ? (i ^ (key & 1u)) : 0u;
+  int bits = 32 - __clz(n - 1);
+  if (bits & 1) ++bits;
+  const int half = bits >> 1;
+  const uint32_t mask = (1u << half) - 1u;
+  do {
+    uint32_t l = i >> half, r = i & mask;
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {
+      const uint32_t t = l ^ (mix32(r * 0x9e3779b9U + key + round * 0x85ebca6bU) & mask);
+      l = r;
+      r = t;
+    }
+    i = (l << half) | r;
+  } while (i >= n);
+  return i;
+}
+
+__device__ __forceinline__ void adam_update(float& w, float g, float& m, float& v, float alpha, float omb1, float omb2,
+                                            float eps) {
+  m += (g - m) * omb1;
+  v += (g * g - v) * omb2;
+  w -= alpha * m / (sqrtf(v) + eps);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float s_red[3][NWARPS];
+  __shared__ float s_alpha;
+
+  const int job_id = blockIdx.x;
+  const gb_job job = a.jobs[job_id];
+  const int n = job.n_rows;
+  if (n <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = a.net.n_layers, n_in = a.n_in, n_out = a.n_out;
+  const int B = a.hp.batch_size;
+  float* sW = smem;
+  float* P = a.params + (long)job.slot * a.pstride;
+  float* Mg = a.adam_m + (long)job.slot * a.sstride;
+  float* Vg = a.adam_v + (long)job.slot * a.sstride;
+
+  // ---- weights -> padded smem image; zero every staging buffer ------------------------------------
+  for (int i = tid; i < a.smem_floats; i += THREADS) smem[i] = 0.f;
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const int K = a.net.dims[l], N = a.net.dims[l + 1], Np = a.im.np[l];
+    const float* Wg = P + a.im.pofs[l];
+    float* dst = sW + a.im.wofs[l];
+    for (int idx = tid; idx < K * N; idx += THREADS) {
+      const int k = idx / N, nn = idx - k * N;
+      dst[k * Np + nn] = Wg[idx];
+    }
+    for (int nn = tid; nn < N; nn += THREADS) sW[a.im.bofs[l] + nn] = Wg[K * N + nn];
+  }
+
+  const float* xbase = a.x + job.x_row * (long)n_in;
+  const float* ybase = a.y + job.x_row * (long)n_out;
+  const int steps = (n + B - 1) / B;
+  const uint32_t key_base = mix32((uint32_t)a.hp.seed ^ mix32((uint32_t)(a.hp.seed >> 32) + 0x632be5abU * (uint32_t)(job.slot + 1)));
+
+  auto row_index = [&](int e, int i) -> int {
+    if (a.hp.shuffle == 0) return i;
+    if (a.hp.shuffle == 2) return a.perm[((long)job_id * a.hp.epochs + e) * a.max_rows + i];
+    return (int)permute_index((uint32_t)i, (uint32_t)n, mix32(key_base + (uint32_t)e * 0x9e3779b9U));
+  };
+  auto gather = [&](int buf, int e, int s) {
+    const int nb = min(B, n - s * B);
+    float* xs = smem + a.xofs[buf];
+    float* ys = smem + a.yofs[buf];
+    for (int r = warp; r < nb; r += NWARPS) {
+      const int src = row_index(e, s * B + r);
+      const float* xr = xbase + (long)src * n_in;
+      const float* yr = ybase + (long)src * n_out;
+      if ((n_in & 3) == 0) {
+        for (int c = lane * 4; c < n_in; c += 128) __pipeline_memcpy_async(xs + r * a.apitch[0] + c, xr + c, 16);
+      } else {
+        for (int c = lane; c < n_in; c += 32) __pipeline_memcpy_async(xs + r * a.apitch[0] + c, xr + c, 4);
+      }
+      if ((n_out & 3) == 0) {
+        for (int c = lane * 4; c < n_out; c += 128) __pipeline_memcpy_async(ys + r * a.ypitch + c, yr + c, 16);
+      } else {
+        for (int c = lane; c < n_out; c += 32) __pipeline_memcpy_async(ys + r * a.ypitch + c, yr + c, 4);
+      }
+    }
+    __pipeline_commit();
+  };
+
+  const float omb1 = 1.f - a.hp.beta1, omb2 = 1.f - a.hp.beta2, eps = a.hp.eps;
+  int t_step = a.hp.step0;
+  int cur = 0;
+  __syncthreads();
+  gather(0, 0, 0);
+
+  for (int e = 0; e < a.hp.epochs; ++e) {
+    float acc_sq = 0.f, acc_reg = 0.f, acc_hit = 0.f;
+    for (int s = 0; s < steps; ++s) {
+      const int nb = min(B, n - s * B);
+      // ---- prefetch the next mini-batch, then wait for the current one ------------------------
+      int ne = e, ns = s + 1;
+      if (ns == steps) { ns = 0; ++ne; }
+      const bool more = ne < a.hp.epochs;
+      if (more) gather(cur ^ 1, ne, ns);
+      if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+      ++t_step;
+      if (tid == 0) {
+        const double t = (double)t_step;
+        s_alpha = (float)((double)a.hp.lr * sqrt(1.0 - pow((double)a.hp.beta2, t)) / (1.0 - pow((double)a.hp.beta1, t)));
+      }
+      __syncthreads();
+
+      // ---- forward ---------------------------------------------------------------------------
+      for (int l = 0; l < L; ++l) {
+        const int Kp = a.im.kp[l], Np = a.im.np[l], N = a.net.dims[l + 1], act = a.net.act[l];
+        const float* in = (l == 0) ? smem + a.xofs[cur] : smem + a.aofs[l];
+        float* out = smem + a.aofs[l + 1];
+        const int ip = a.apitch[l], op = a.apitch[l + 1];
+        const float* Wl = sW + a.im.wofs[l];
+        const float* bl = sW + a.im.bofs[l];
+        const float l1c = a.net.l1[l] * (a.hp.l1_div_batch ? 1.f : (float)nb);
+        for (int task = warp; task < (Np >> 2); task += NWARPS) {
+          const int n0 = task << 2;
+          float4 acc = *reinterpret_cast<const float4*>(bl + n0);
+          const float* arow = in + lane * ip;
+          const float* wcol = Wl + n0;
+          for (int k = 0; k < Kp; k += 4) {
+            const float4 av = *reinterpret_cast<const float4*>(arow + k);
+            const float4 w0 = *reinterpret_cast<const float4*>(wcol + (k + 0) * Np);
+            const float4 w1 = *reinterpret_cast<const float4*>(wcol + (k + 1) * Np);
+            const float4 w2 = *reinterpret_cast<const float4*>(wcol + (k + 2) * Np);
+            const float4 w3 = *reinterpret_cast<const float4*>(wcol + (k + 3) * Np);
+            acc.x = fmaf(av.x, w0.x, acc.x); acc.y = fmaf(av.x, w0.y, acc.y); acc.z = fmaf(av.x, w0.z, acc.z); acc.w = fmaf(av.x, w0.w, acc.w);
+            acc.x = fmaf(av.y, w1.x, acc.x); acc.y = fmaf(av.y, w1.y, acc.y); acc.z = fmaf(av.y, w1.z, acc.z); acc.w = fmaf(av.y, w1.w, acc.w);
+            acc.x = fmaf(av.z, w2.x, acc.x); acc.y = fmaf(av.z, w2.y, acc.y); acc.z = fmaf(av.z, w2.z, acc.z); acc.w = fmaf(av.z, w2.w, acc.w);
+            acc.x = fmaf(av.w, w3.x, acc.x); acc.y = fmaf(av.w, w3.y, acc.y); acc.z = fmaf(av.w, w3.z, acc.z); acc.w = fmaf(av.w, w3.w, acc.w);
+          }
+          float4 o;
+          o.x = (n0 + 0 < N) ? gb::apply_act(act, acc.x) : 0.f;
+          o.y = (n0 + 1 < N) ? gb::apply_act(act, acc.y) : 0.f;
+          o.z = (n0 + 2 < N) ? gb::apply_act(act, acc.z) : 0.f;
+          o.w = (n0 + 3 < N) ? gb::apply_act(act, acc.w) : 0.f;
+          *reinterpret_cast<float4*>(out + lane * op + n0) = o;
+          if (l1c != 0.f && lane < nb) acc_reg += l1c * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(o.w));
+        }
+        __syncthreads();
+      }
+
+      // ---- loss, dL/dyhat, accuracy -------------------------------------------------------------
+      {
+        const float* yh = smem + a.aofs[L];
+        const int yp = a.apitch[L];
+        const float* yt = smem + a.yofs[cur];
+        float* G = smem + a.dofs[0];
+        const int NpL = a.im.np[L - 1];
+        const float gscale = 2.f / ((float)nb * (float)n_out);
+        for (int r = warp; r < BR; r += NWARPS) {
+          for (int j = lane; j < NpL; j += 32) {
+            float g = 0.f;
+            if (r < nb && j < n_out) {
+              const float d = yh[r * yp + j] - yt[r * a.ypitch + j];
+              acc_sq += d * d;
+              g = gscale * d;
+            }
+            G[r * a.dpitch + j] = g;
+          }
+        }
+        if (warp == NWARPS - 1 && lane < nb) {  // keras "accuracy" on 2-D float targets: argmax match (binary if width 1)
+          if (n_out == 1) {
+            acc_hit += ((yh[lane * yp] > 0.5f ? 1.f : 0.f) == yt[lane * a.ypitch]) ? 1.f : 0.f;
+          } else {
+            int bp = 0, bt = 0;
+            float vp = yh[lane * yp], vt = yt[lane * a.ypitch];
+            for (int j = 1; j < n_out; ++j) {
+              const float p = yh[lane * yp + j], q = yt[lane * a.ypitch + j];
+              if (p > vp) { vp = p; bp = j; }
+              if (q > vt) { vt = q; bt = j; }
+            }
+            acc_hit += (bp == bt) ? 1.f : 0.f;
+          }
+        }
+      }
+      __syncthreads();
+      const float alpha = s_alpha;
+
+      // ---- backward + Adam --------------------------------------------------------------------------
+      int dcur = 0;
+      for (int l = L - 1; l >= 0; --l) {
+        const int Kp = a.im.kp[l], Np = a.im.np[l], N = a.net.dims[l + 1], act = a.net.act[l];
+        float* D = smem + a.dofs[dcur];
+        float* Dn = smem + a.dofs[dcur ^ 1];
+        const float* aout = smem + a.aofs[l + 1];
+        const int op = a.apitch[l + 1];
+        const float* ain = (l == 0) ? smem + a.xofs[cur] : smem + a.aofs[l];
+        const int ip = a.apitch[l];
+        float* Wl = sW + a.im.wofs[l];
+        // A: dz = (G + l1*sign(a)) * act'(a)
+        {
+          const float c = a.net.l1[l] / (a.hp.l1_div_batch ? (float)nb : 1.f);
+          for (int r = warp; r < BR; r += NWARPS) {
+            for (int j = lane; j < Np; j += 32) {
+              float dz = 0.f;
+              if (r < nb && j < N) {
+                const float ao = aout[r * op + j];
+                float g = D[r * a.dpitch + j];
+                if (c != 0.f) g += c * ((ao > 0.f) ? 1.f : ((ao < 0.f) ? -1.f : 0.f));
+                dz = g * gb::act_grad_from_output(act, ao);
+              }
+              D[r * a.dpitch + j] = dz;
+            }
+          }
+        }
+        __syncthreads();
+        // B: dL/da_in = dz . W^T
+        if (l > 0) {
+          for (int task = warp; task < (Kp >> 2); task += NWARPS) {
+            const int k0 = task << 2;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* drow = D + lane * a.dpitch;
+            for (int nn = 0; nn < Np; nn += 4) {
+              const float4 d = *reinterpret_cast<const float4*>(drow + nn);
+              const float4 w0 = *reinterpret_cast<const float4*>(Wl + (k0 + 0) * Np + nn);
+              const float4 w1 = *reinterpret_cast<const float4*>(Wl + (k0 + 1) * Np + nn);
+              const float4 w2 = *reinterpret_cast<const float4*>(Wl + (k0 + 2) * Np + nn);
+              const float4 w3 = *reinterpret_cast<const float4*>(Wl + (k0 + 3) * Np + nn);
+              acc.x = fmaf(d.x, w0.x, acc.x); acc.x = fmaf(d.y, w0.y, acc.x); acc.x = fmaf(d.z, w0.z, acc.x); acc.x = fmaf(d.w, w0.w, acc.x);
+              acc.y = fmaf(d.x, w1.x, acc.y); acc.y = fmaf(d.y, w1.y, acc.y); acc.y = fmaf(d.z, w1.z, acc.y); acc.y = fmaf(d.w, w1.w, acc.y);
+              acc.z = fmaf(d.x, w2.x, acc.z); acc.z = fmaf(d.y, w2.y, acc.z); acc.z = fmaf(d.z, w2.z, acc.z); acc.z = fmaf(d.w, w2.w, acc.z);
+              acc.w = fmaf(d.x, w3.x, acc.w); acc.w = fmaf(d.y, w3.y, acc.w); acc.w = fmaf(d.z, w3.z, acc.w); acc.w = fmaf(d.w, w3.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(Dn + lane * a.dpitch + k0) = acc;
+          }
+        }
+        __syncthreads();
+        // C: dW = a_in^T . dz (4x4 block per thread), db, Adam -- weights updated in place in smem
+        {
+          const int kblocks = Kp >> 2, nblocks = kblocks * (Np >> 2);
+          float* Ml = Mg + a.im.wofs[l];
+          float* Vl = Vg + a.im.wofs[l];
+          for (int bid = tid; bid < nblocks; bid += THREADS) {
+            const int kb = bid % kblocks, n0 = (bid / kblocks) << 2, k0 = kb << 2;
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
+#pragma unroll 4
+            for (int r = 0; r < BR; ++r) {
+              const float4 av = *reinterpret_cast<const float4*>(ain + r * ip + k0);
+              const float4 d = *reinterpret_cast<const float4*>(D + r * a.dpitch + n0);
+              g0.x = fmaf(av.x, d.x, g0.x); g0.y = fmaf(av.x, d.y, g0.y); g0.z = fmaf(av.x, d.z, g0.z); g0.w = fmaf(av.x, d.w, g0.w);
+              g1.x = fmaf(av.y, d.x, g1.x); g1.y = fmaf(av.y, d.y, g1.y); g1.z = fmaf(av.y, d.z, g1.z); g1.w = fmaf(av.y, d.w, g1.w);
+              g2.x = fmaf(av.z, d.x, g2.x); g2.y = fmaf(av.z, d.y, g2.y); g2.z = fmaf(av.z, d.z, g2.z); g2.w = fmaf(av.z, d.w, g2.w);
+              g3.x = fmaf(av.w, d.x, g3.x); g3.y = fmaf(av.w, d.y, g3.y); g3.z = fmaf(av.w, d.z, g3.z); g3.w = fmaf(av.w, d.w, g3.w);
+            }
+            const float4 gs[4] = {g0, g1, g2, g3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int off = (k0 + i) * Np + n0;
+              float4 w = *reinterpret_cast<float4*>(Wl + off);
+              float4 m = *reinterpret_cast<float4*>(Ml + off);
+              float4 v = *reinterpret_cast<float4*>(Vl + off);
+              adam_update(w.x, gs[i].x, m.x, v.x, alpha, omb1, omb2, eps);
+              adam_update(w.y, gs[i].y, m.y, v.y, alpha, omb1, omb2, eps);
+              adam_update(w.z, gs[i].z, m.z, v.z, alpha, omb1, omb2, eps);
+              adam_update(w.w, gs[i].w, m.w, v.w, alpha, omb1, omb2, eps);
+              *reinterpret_cast<float4*>(Wl + off) = w;
+              *reinterpret_cast<float4*>(Ml + off) = m;
+              *reinterpret_cast<float4*>(Vl + off) = v;
+            }
+          }
+          for (int j = THREADS - 1 - tid; j < Np; j += THREADS) {
+            float g = 0.f;
+            for (int r = 0; r < BR; ++r) g += D[r * a.dpitch + j];
+            const int off = a.im.bofs[l] + j;
+            float w = sW[off], m = Mg[off], v = Vg[off];
+            adam_update(w, g, m, v, alpha, omb1, omb2, eps);
+            sW[off] = w; Mg[off] = m; Vg[off] = v;
+          }
+        }
+        dcur ^= 1;
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+    // ---- epoch statistics (keras History: sample-weighted mean of the per-batch total loss) -------------
+    float v0 = acc_sq, v1 = acc_reg, v2 = acc_hit;
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    }
+    if (lane == 0) { s_red[0][warp] = v0; s_red[1][warp] = v1; s_red[2][warp] = v2; }
+    __syncthreads();
+    if (tid == 0) {
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+      for (int w = 0; w < NWARPS; ++w) { q0 += s_red[0][w]; q1 += s_red[1][w]; q2 += s_red[2][w]; }
+      a.out_loss[(long)job_id * a.hp.epochs + e] = (q0 / (float)n_out + q1) / (float)n;
+      if (a.out_acc) a.out_acc[(long)job_id * a.hp.epochs + e] = q2 / (float)n;
+    }
+    __syncthreads();
+  }
+
+  // ---- trained weights back to the canonical layout ------------------------------------------------------
+  for (int l = 0; l < L; ++l) {
+    const int K = a.net.dims[l], N = a.net.dims[l + 1], Np = a.im.np[l];
+    float* Wg = P + a.im.pofs[l];
+    const float* src = sW + a.im.wofs[l];
+    for (int idx = tid; idx < K * N; idx += THREADS) {
+      const int k = idx / N, nn = idx - k * N;
+      Wg[idx] = src[k * Np + nn];
+    }
+    for (int nn = tid; nn < N; nn += THREADS) Wg[K * N + nn] = sW[a.im.bofs[l] + nn];
+  }
+}
+
+int odd_pitch(int width) {
+  int p4 = (width + 3) / 4;
+  if ((p4 & 1) == 0) ++p4;
+  return p4 * 4;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gb_ffae_fit_state_stride(const gb_ffnet* net) {
+  if (gb::validate_ffnet(net) != GB_OK) return 0;
+  return (size_t)gb::round_up(gb::make_ff_image(net, 4).total, 4);
+}
+
+int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v, const gb_job* jobs, int32_t n_jobs,
+                int32_t max_rows, const float* x, const float* y, const int32_t* perm, const gb_fit_hparams* hp,
+                float* out_loss, float* out_acc, void* stream) {
+  int rc = gb::validate_ffnet(net);
+  if (rc != GB_OK) return rc;
+  GB_REQUIRE(params && adam_m && adam_v && jobs && x && y && hp && out_loss, GB_E_ARG,
+             "params/adam_m/adam_v/jobs/x/y/hp/out_loss must be non-NULL");
+  GB_REQUIRE(hp->epochs >= 1, GB_E_ARG, "epochs=%d must be >= 1", hp->epochs);
+  GB_REQUIRE(hp->batch_size >= 1 && hp->batch_size <= BR, GB_E_SHAPE,
+             "batch_size=%d: this kernel keeps one mini-batch row per lane (1..%d)", hp->batch_size, BR);
+  GB_REQUIRE(hp->shuffle >= 0 && hp->shuffle <= 2, GB_E_ARG, "shuffle=%d unknown", hp->shuffle);
+  GB_REQUIRE(hp->shuffle != 2 || perm, GB_E_ARG, "shuffle=2 needs perm");
+  GB_REQUIRE(gb::aligned16(params) && gb::aligned16(adam_m) && gb::aligned16(adam_v) && gb::aligned16(x) &&
+                 gb::aligned16(y),
+             GB_E_ALIGN, "params/adam/x/y must be 16-byte aligned");
+  if (n_jobs == 0 || max_rows == 0) return GB_OK;
+
+  FitArgs a{};
+  a.net = *net;
+  a.im = gb::make_ff_image(net, 4);
+  a.hp = *hp;
+  const int L = net->n_layers;
+  a.n_in = net->dims[0];
+  a.n_out = net->dims[L];
+  a.max_rows = max_rows;
+  a.pstride = (long)gb_ffnet_param_stride(net);
+  a.sstride = (long)gb_ffae_fit_state_stride(net);
+  int ofs = gb::round_up(a.im.total, 4);
+  a.wfloats = ofs;
+  a.apitch[0] = odd_pitch(a.im.kp[0]);
+  for (int l = 1; l <= L; ++l) {
+    a.apitch[l] = odd_pitch(a.im.np[l - 1]);
+    a.aofs[l] = ofs;
+    ofs += BR * a.apitch[l];
+  }
+  for (int b = 0; b < 2; ++b) { a.xofs[b] = ofs; ofs += BR * a.apitch[0]; }
+  a.ypitch = odd_pitch(gb::round_up(a.n_out, 4));
+  for (int b = 0; b < 2; ++b) { a.yofs[b] = ofs; ofs += BR * a.ypitch; }
+  a.dpitch = odd_pitch(a.im.max_np);
+  for (int b = 0; b < 2; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
+  a.smem_floats = ofs;
+  const size_t smem = (size_t)ofs * sizeof(float);
+  GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory for a resident fit", smem);
+  a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.jobs = jobs; a.x = x; a.y = y; a.perm = perm;
+  a.out_loss = out_loss; a.out_acc = out_acc;
+  GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ffae_fit_kernel<<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
+  GB_CUDA_CHECK(cudaGetLastError());
+  return GB_OK;
+}
+
+}  // extern "C"

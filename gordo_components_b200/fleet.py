@@ -1,0 +1,155 @@
+"""
+Fleet API: score (and shard) many machines at once.
+
+``anomaly_many`` is the call a fleet user makes: host arrays in, host arrays out, with the host<->device copies
+pipelined against the fused kernel on a few CUDA streams.  ``partition``/``assign_machines``/``gather_summaries`` are
+the whole multi-GPU story: machines are independent (the reference runs one Kubernetes pod per machine,
+gordo/workflow/workflow_generator/resources/argo-workflow.yml.template:1544-1557), so ranks own disjoint contiguous
+blocks of machines and the only communication is the broadcast of the assignment and the gather of per-machine
+summaries -- there is no exchange step inside fit, predict or anomaly.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import engine
+
+PER_TAG = ("model-output", "tag-anomaly-scaled", "tag-anomaly-unscaled", "anomaly-confidence")
+PER_ROW = ("total-anomaly-scaled", "total-anomaly-unscaled", "total-anomaly-confidence")
+
+
+# ------------------------------------------------------------------------------------------------ sharding
+def partition(n_machines: int, world: int) -> List[range]:
+    """Contiguous, balanced blocks: the first (n % world) ranks get one extra machine."""
+    base, extra = divmod(n_machines, world)
+    out, start = [], 0
+    for r in range(world):
+        size = base + (1 if r < extra else 0)
+        out.append(range(start, start + size))
+        start += size
+    return out
+
+
+def assign_machines(n_machines: int, world: int, rank: int, dist=None) -> np.ndarray:
+    """Rank 0 computes the partition and broadcasts it (NCCL/gloo object broadcast); returns this rank's machine ids."""
+    if dist is None or world == 1:
+        return np.arange(n_machines)
+    payload = [[list(r) for r in partition(n_machines, world)] if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    return np.asarray(payload[0][rank], dtype=np.int64)
+
+
+def gather_summaries(local, world: int, dist=None):
+    """all_gather of one fixed-size summary tensor per rank (e.g. max total-anomaly-confidence per machine)."""
+    if dist is None or world == 1:
+        return local
+    torch = engine._torch()
+    buf = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, local.contiguous())
+    return buf
+
+
+def random_glorot_params(eng: "engine.FFEngine", n_slots: int, generator):
+    """Synthetic fleet: glorot-uniform kernels, small uniform biases, generated on the device (bench/test plumbing)."""
+    torch = engine._torch()
+    params = torch.zeros((n_slots, eng.param_stride), dtype=torch.float32, device=eng.device)
+    ofs = 0
+    for i, o in zip(eng.dims[:-1], eng.dims[1:]):
+        lim = float(np.sqrt(6.0 / (i + o)))
+        params[:, ofs:ofs + i * o] = (torch.rand((n_slots, i * o), generator=generator, device=eng.device) * 2 - 1) * lim
+        ofs += i * o
+        params[:, ofs:ofs + o] = (torch.rand((n_slots, o), generator=generator, device=eng.device) * 2 - 1) * 0.1
+        ofs += o
+    return params
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer scoring
+class HostPipeline:
+    """Pinned host buffers + per-stream device staging for ``anomaly_many``; reusable across calls of the same shape."""
+
+    def __init__(self, eng: "engine.FFEngine", n_machines: int, rows: int, chunk_machines: int = 50, n_streams: int = 3,
+                 want: Sequence[str] = PER_TAG + PER_ROW):
+        torch = engine._torch()
+        self.eng, self.M, self.R = eng, n_machines, rows
+        self.chunk = max(1, min(chunk_machines, n_machines))
+        self.want = tuple(want)
+        dev = eng.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        cr = self.chunk * rows
+        self.stage = []
+        for _ in self.streams:
+            st = {"x": torch.empty((cr, eng.n_in), dtype=torch.float32, device=dev), "y": torch.empty((cr, eng.n_out), dtype=torch.float32, device=dev), "out": {}}
+            for k in self.want:
+                st["out"][k] = torch.empty((cr, eng.n_out) if k in PER_TAG else (cr,), dtype=torch.float32, device=dev)
+            self.stage.append(st)
+        total = n_machines * rows
+        self.host_out = {k: torch.empty((total, eng.n_out) if k in PER_TAG else (total,), dtype=torch.float32).pin_memory() for k in self.want}
+        self.chunks = []
+        for c0 in range(0, n_machines, self.chunk):
+            m = min(self.chunk, n_machines - c0)
+            jobs = engine.make_jobs(np.arange(c0, c0 + m), rows, np.arange(m, dtype=np.int64) * rows)
+            self.chunks.append((c0, m, engine.jobs_to_device(jobs, dev)))
+        self.h2d_bytes = total * (eng.n_in + eng.n_out) * 4
+        self.d2h_bytes = sum(v.numel() * 4 for v in self.host_out.values())
+
+    def run(self, params, x_host, y_host, scale, feat_thr, agg_thr, variant: int = 0) -> Dict[str, "object"]:
+        """x_host / y_host: pinned float32 host tensors [M*R, T].  Returns pinned host tensors (valid after the sync below)."""
+        torch = engine._torch()
+        R = self.R
+        for i, (c0, m, jobs) in enumerate(self.chunks):
+            s = self.streams[i % len(self.streams)]
+            st = self.stage[i % len(self.streams)]
+            rows = slice(c0 * R, (c0 + m) * R)
+            with torch.cuda.stream(s):
+                st["x"][: m * R].copy_(x_host[rows], non_blocking=True)
+                st["y"][: m * R].copy_(y_host[rows], non_blocking=True)
+                self.eng.infer_score(params, jobs, m, R, st["x"], st["y"], scale, feat_thr, agg_thr, out_rows=self.chunk * R,
+                                     want=self.want, variant=variant, out=st["out"])
+                for k in self.want:
+                    self.host_out[k][rows].copy_(st["out"][k][: m * R], non_blocking=True)
+        for s in self.streams:
+            s.synchronize()
+        return self.host_out
+
+
+def anomaly_many(eng: "engine.FFEngine", params, x_host, y_host, scale, feat_thr=None, agg_thr=None, rows: Optional[int] = None,
+                 pipeline: Optional[HostPipeline] = None, variant: int = 0):
+    """
+    Fleet form of ``DiffBasedAnomalyDetector.anomaly``: machine m owns rows [m*rows, (m+1)*rows) of the host arrays and
+    slot m of ``params`` / ``scale`` / thresholds.  Returns a dict of host arrays named like the anomaly frame's blocks.
+    """
+    torch = engine._torch()
+    xh = x_host if hasattr(x_host, "is_pinned") else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
+    yh = y_host if hasattr(y_host, "is_pinned") else torch.from_numpy(np.ascontiguousarray(y_host, dtype=np.float32))
+    n_machines = params.shape[0]
+    rows = rows or xh.shape[0] // n_machines
+    want = [k for k in PER_TAG + PER_ROW if not ((feat_thr is None and k == "anomaly-confidence") or (agg_thr is None and k == "total-anomaly-confidence"))]
+    pipe = pipeline or HostPipeline(eng, n_machines, rows, want=want)
+    if not xh.is_pinned():
+        xh = xh.pin_memory()
+    if not yh.is_pinned():
+        yh = yh.pin_memory()
+    return pipe.run(params, xh, yh, scale, feat_thr, agg_thr, variant)
+
+
+def time_e2e(eng, params, jobs_h, x_dev, y_dev, scale, feat_thr, agg_thr, steps: int = 3, variant: int = 0):
+    """End-to-end windows/s of ``anomaly_many``: pinned host inputs, H2D + kernel + D2H of every output inside the timed region."""
+    torch = engine._torch()
+    M = len(jobs_h)
+    R = int(jobs_h["n_rows"][0])
+    xh = torch.empty(x_dev.shape, dtype=torch.float32).pin_memory()
+    yh = torch.empty(y_dev.shape, dtype=torch.float32).pin_memory()
+    xh.copy_(x_dev)
+    yh.copy_(y_dev)
+    pipe = HostPipeline(eng, M, R)
+    anomaly_many(eng, params, xh, yh, scale, feat_thr, agg_thr, rows=R, pipeline=pipe, variant=variant)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        anomaly_many(eng, params, xh, yh, scale, feat_thr, agg_thr, rows=R, pipeline=pipe, variant=variant)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"ms_per_step": dt * 1e3, "h2d_bytes": pipe.h2d_bytes, "d2h_bytes": pipe.d2h_bytes}

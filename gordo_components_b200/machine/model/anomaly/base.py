@@ -1,0 +1,15 @@
+"""Anomaly detector protocol (mirror of gordo/machine/model/anomaly/base.py:11-23)."""
+import abc
+from datetime import timedelta
+from typing import Optional
+
+import pandas as pd
+from sklearn.base import BaseEstimator
+
+from ..base import GordoBase
+
+
+class AnomalyDetectorBase(BaseEstimator, GordoBase, metaclass=abc.ABCMeta):
+    @abc.abstractmethod
+    def anomaly(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None) -> pd.DataFrame:
+        """Frame of model output and anomaly scores for ``X`` against ``y``."""

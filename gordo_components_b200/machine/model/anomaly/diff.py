@@ -1,0 +1,319 @@
+"""
+Diff-based anomaly detection with the public contract of
+gordo/machine/model/anomaly/diff.py:21-458 (DiffBasedAnomalyDetector) -- constructor arguments,
+``get_params`` contents, ``cross_validate`` / ``anomaly`` outputs, threshold attributes, metadata keys and
+exceptions -- with every number computed on the GPU:
+
+* ``anomaly``         one fused launch: network forward + abs diffs + row means + confidences (gb_ffae_infer_score),
+                      or gb_anomaly_score when the base estimator is not one of ours;
+* ``cross_validate``  fold scoring as above followed by the rolling-min/max threshold reduction (gb_thresholds);
+* ``fit``             base estimator fit (gb_ffae_fit) and the MinMax scaler statistics (gb_minmax_fit).
+
+Because ``S(yhat) - S(y) = (yhat - y) * scale`` for any per-feature affine scaler, the kernels need only the
+scaler's per-tag multiplier; a non-affine ``scaler`` is rejected with ValueError rather than approximated.
+"""
+from __future__ import annotations
+
+from datetime import timedelta
+from typing import Dict, Optional, Sequence, Union
+
+import numpy as np
+import pandas as pd
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.exceptions import NotFittedError
+from sklearn.model_selection import TimeSeriesSplit
+from sklearn.model_selection import cross_validate as sk_cross_validate
+from sklearn.pipeline import Pipeline
+from sklearn.preprocessing import MinMaxScaler
+from sklearn.utils import shuffle as sk_shuffle
+
+from .. import utils as model_utils
+from ..base import GordoBase
+from ..models import KerasAutoEncoder, KerasBaseEstimator, KerasLSTMBaseEstimator
+from .base import AnomalyDetectorBase
+
+_SCORE_ALL = ("tag-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-scaled", "total-anomaly-unscaled",
+              "anomaly-confidence", "total-anomaly-confidence")
+
+
+def _values(a) -> np.ndarray:
+    return np.asarray(getattr(a, "values", a))
+
+
+def _scaler_multiplier(scaler, n_features: int) -> np.ndarray:
+    """Per-feature slope of a fitted affine scaler; ValueError if the transform is not affine per feature."""
+    probe = np.vstack([np.zeros(n_features), np.ones(n_features), np.full(n_features, 2.0)])
+    t = np.asarray(scaler.transform(probe), dtype=np.float64)
+    slope = t[1] - t[0]
+    if not np.allclose(t[2] - t[1], slope, rtol=1e-9, atol=1e-12):
+        raise ValueError(f"scaler {scaler!r} is not a per-feature affine transform; the fused anomaly kernels cannot use it")
+    return slope.astype(np.float32)
+
+
+class DiffBasedAnomalyDetector(AnomalyDetectorBase):
+    def __init__(
+        self,
+        base_estimator: BaseEstimator = KerasAutoEncoder(kind="feedforward_hourglass"),
+        scaler: TransformerMixin = MinMaxScaler(),
+        require_thresholds: bool = True,
+        shuffle: bool = False,
+        window: Optional[int] = None,
+        smoothing_method: Optional[str] = None,
+    ):
+        """
+        Wraps ``base_estimator``; after training it, fits ``scaler`` on the target purely for the error arithmetic
+        (the estimator itself sees unscaled ``y``).  Thresholds come from ``cross_validate`` (rolling minimum over 6
+        samples of the validation errors, maximised; the last fold wins).  ``require_thresholds`` makes ``anomaly``
+        raise AttributeError when they are missing.  ``shuffle`` shuffles rows in ``fit``.  ``window`` +
+        ``smoothing_method`` ('smm' | 'sma' | 'ewma', default 'smm' when only a window is given) add smoothed scores.
+        """
+        self.base_estimator = base_estimator
+        self.scaler = scaler
+        self.require_thresholds = require_thresholds
+        self.shuffle = shuffle
+        self.window = window
+        self.smoothing_method = smoothing_method
+        if self.window is not None and self.smoothing_method is None:
+            self.smoothing_method = "smm"
+
+    def __getattr__(self, item):
+        # anything the detector does not own is looked up on the wrapped estimator (this is how .predict exists)
+        if item in self.__dict__:
+            return getattr(self, item)
+        if item == "base_estimator":
+            raise AttributeError(item)
+        return getattr(self.base_estimator, item)
+
+    # ------------------------------------------------------------------ bookkeeping
+    def get_params(self, deep=True):
+        params = {"base_estimator": self.base_estimator, "scaler": self.scaler, "shuffle": self.shuffle}
+        if self.window is not None:
+            params["window"] = self.window
+            params["smoothing_method"] = self.smoothing_method
+        return params
+
+    def score(self, X, y, sample_weight=None) -> float:
+        return self.base_estimator.score(X, y)
+
+    def get_metadata(self):
+        metadata = dict()
+        if hasattr(self, "feature_thresholds_"):
+            metadata["feature-thresholds"] = self.feature_thresholds_.tolist()
+        if hasattr(self, "aggregate_threshold_"):
+            metadata["aggregate-threshold"] = self.aggregate_threshold_
+        if hasattr(self, "feature_thresholds_per_fold_"):
+            metadata["feature-thresholds-per-fold"] = self.feature_thresholds_per_fold_.to_dict()
+        if hasattr(self, "aggregate_thresholds_per_fold_"):
+            metadata["aggregate-thresholds-per-fold"] = self.aggregate_thresholds_per_fold_
+        if hasattr(self, "window"):
+            metadata["window"] = self.window
+        if hasattr(self, "smoothing_method"):
+            metadata["smoothing-method"] = self.smoothing_method
+        if hasattr(self, "smooth_feature_thresholds_") and self.smooth_aggregate_threshold_ is not None:
+            metadata["smooth-feature-thresholds"] = self.smooth_feature_thresholds_.tolist()
+        if hasattr(self, "smooth_aggregate_threshold_") and self.smooth_aggregate_threshold_ is not None:
+            metadata["smooth-aggregate-threshold"] = self.smooth_aggregate_threshold_
+        if hasattr(self, "smooth_feature_thresholds_per_fold_"):
+            metadata["smooth-feature-thresholds-per-fold"] = self.smooth_feature_thresholds_per_fold_.to_dict()
+        if hasattr(self, "smooth_aggregate_thresholds_per_fold_"):
+            metadata["smooth-aggregate-thresholds-per-fold"] = self.smooth_aggregate_thresholds_per_fold_
+        if isinstance(self.base_estimator, GordoBase):
+            metadata.update(self.base_estimator.get_metadata())
+        else:
+            metadata.update({"scaler": str(self.scaler), "base_estimator": str(self.base_estimator), "shuffle": self.shuffle})
+        return metadata
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X, y):
+        if self.shuffle:
+            Xs, ys = sk_shuffle(X, y, random_state=0)
+            self.base_estimator.fit(Xs, ys)
+        else:
+            self.base_estimator.fit(X, y)
+        self._fit_scaler(y)
+        return self
+
+    def _fit_scaler(self, y):
+        """Scaler statistics of the targets.  A default MinMaxScaler is fitted by the gb_minmax_fit kernel."""
+        sc = self.scaler
+        plain_minmax = type(sc) is MinMaxScaler and tuple(sc.feature_range) == (0, 1) and not getattr(sc, "clip", False)
+        if not plain_minmax:
+            sc.fit(y)  # user supplied transformer: its own code owns its statistics
+            return
+        from .... import engine
+
+        yv = _values(y)
+        dev = engine.cuda_device()
+        yd = engine.to_device_f32(yv, dev)
+        n, t = yd.shape
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+        scale, offset = engine.minmax_fit(jobs, 1, n, yd, t, 1, dev)
+        scale = scale[0].cpu().numpy().astype(np.float64)
+        offset = offset[0].cpu().numpy().astype(np.float64)
+        sc.scale_, sc.min_ = scale, offset
+        sc.data_min_ = -offset / scale
+        sc.data_range_ = 1.0 / scale  # (a constant feature reports 1 here where sklearn reports 0; transform is identical)
+        sc.data_max_ = sc.data_min_ + sc.data_range_
+        sc.n_features_in_ = t
+        sc.n_samples_seen_ = n
+        if hasattr(y, "columns"):
+            sc.feature_names_in_ = np.asarray([str(c) for c in y.columns], dtype=object)
+        elif hasattr(sc, "feature_names_in_"):
+            del sc.feature_names_in_
+
+    # ------------------------------------------------------------------ scoring core (all GPU)
+    def _fused_target(self):
+        """(pre-transformers, our feed-forward AE) when the forward pass can be fused with the scoring, else None."""
+        est = self.base_estimator
+        if isinstance(est, KerasAutoEncoder):
+            return [], est
+        if isinstance(est, Pipeline) and len(est.steps) and isinstance(est.steps[-1][1], KerasAutoEncoder):
+            return [step for _, step in est.steps[:-1]], est.steps[-1][1]
+        return None
+
+    def _score(self, estimator_owner, X, y_true, scaler, feat_thr=None, agg_thr=None, want: Sequence[str] = _SCORE_ALL) -> Dict[str, np.ndarray]:
+        """
+        Model output and the requested anomaly columns as host arrays.  ``estimator_owner`` is the detector whose
+        base estimator predicts (``self`` or a CV fold clone); ``y_true`` may be longer than the prediction and is
+        tail-aligned to it (LSTM offset).
+        """
+        from .... import engine
+
+        dev = engine.cuda_device()
+        yv = _values(y_true)
+        n_out = yv.shape[1]
+        mult = _scaler_multiplier(scaler, n_out)
+        torch = engine._torch()
+        scale_d = torch.from_numpy(mult.reshape(1, -1)).to(dev)
+        ft_d = torch.from_numpy(np.asarray(feat_thr, dtype=np.float32).reshape(1, -1)).to(dev) if feat_thr is not None else None
+        at_d = torch.tensor([float(agg_thr)], dtype=torch.float32, device=dev) if agg_thr is not None else None
+        fused = estimator_owner._fused_target()
+        if fused is not None and fused[1].model is not None:
+            pre, ae = fused
+            Xt = X
+            for step in pre:
+                Xt = step.transform(Xt)
+            Xv = _values(Xt)
+            eng = ae._engine()
+            n = len(Xv)
+            xd, yd = engine.to_device_f32(Xv, dev), engine.to_device_f32(yv, dev)
+            jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+            res = eng.infer_score(ae._device_params(), jobs, 1, n, xd, yd, scale_d, ft_d, at_d, want=want)
+        else:
+            pred = np.asarray(estimator_owner.predict(X) if hasattr(estimator_owner, "predict") else estimator_owner.transform(X))
+            n = len(pred)
+            pd_ = engine.to_device_f32(pred, dev)
+            yd = engine.to_device_f32(yv[-n:] if n else yv[:0], dev)
+            jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+            res = engine.anomaly_score(jobs, 1, n, pd_, yd, n_out, scale_d, ft_d, at_d, want=want) if n else {}
+            res["model-output"] = pred
+        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)) for k, v in res.items()}
+
+    # ------------------------------------------------------------------ cross validation -> thresholds
+    def cross_validate(self, *, X, y, cv=TimeSeriesSplit(n_splits=3), **kwargs):
+        """
+        sklearn cross validation of the detector (same return dict), after which the thresholds are derived from
+        each fold's validation errors; the final thresholds are the last fold's.
+        """
+        from .... import engine
+
+        kwargs.update(dict(return_estimator=True, cv=cv))
+        cv_output = sk_cross_validate(self, X=X, y=y, **kwargs)
+
+        columns = list(y.columns) if hasattr(y, "columns") else list(range(_values(y).shape[1]))
+        per_fold, agg_per_fold = {}, {}
+        smooth_per_fold, smooth_agg_per_fold = {}, {}
+        feat = agg = sfeat = sagg = None
+        dev = engine.cuda_device()
+        torch = engine._torch()
+        for i, ((_, test_idxs), fold) in enumerate(zip(kwargs["cv"].split(X, y), cv_output["estimator"])):
+            X_test = X.iloc[test_idxs] if isinstance(X, pd.DataFrame) else X[test_idxs]
+            y_test = y.iloc[test_idxs] if isinstance(y, pd.DataFrame) else y[test_idxs]
+            try:
+                fold.scaler.transform(_values(y_test)[:1])
+            except (NotFittedError, ValueError):
+                fold.scaler.fit(y_test)
+            res = self._score(fold, X_test, y_test, fold.scaler, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
+            n = len(res["model-output"])
+            tu = torch.from_numpy(np.ascontiguousarray(res["tag-anomaly-unscaled"], dtype=np.float32)).to(dev)
+            ts = torch.from_numpy(np.ascontiguousarray(res["total-anomaly-scaled"], dtype=np.float32)).to(dev)
+            jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+            f, a = engine.thresholds(jobs, 1, n, tu, ts, tu.shape[1], 1, 6, dev)
+            feat = pd.Series(f[0].cpu().numpy().astype(np.float64), index=columns, name=f"fold-{i}")
+            agg = float(a[0])
+            per_fold[f"fold-{i}"] = feat
+            agg_per_fold[f"fold-{i}"] = agg
+            if self.window is not None:
+                f, a = engine.thresholds(jobs, 1, n, tu, ts, tu.shape[1], 1, int(self.window), dev)
+                sfeat = pd.Series(f[0].cpu().numpy().astype(np.float64), index=columns, name=f"fold-{i}")
+                sagg = float(a[0])
+                smooth_per_fold[f"fold-{i}"] = sfeat
+                smooth_agg_per_fold[f"fold-{i}"] = sagg
+
+        self.feature_thresholds_per_fold_ = pd.DataFrame(list(per_fold.values())) if per_fold else pd.DataFrame()
+        self.aggregate_thresholds_per_fold_ = agg_per_fold
+        self.smooth_feature_thresholds_per_fold_ = pd.DataFrame(list(smooth_per_fold.values())) if smooth_per_fold else pd.DataFrame()
+        self.smooth_aggregate_thresholds_per_fold_ = smooth_agg_per_fold
+        self.feature_thresholds_ = feat
+        self.aggregate_threshold_ = agg
+        self.smooth_aggregate_threshold_ = sagg
+        self.smooth_feature_thresholds_ = sfeat
+        return cv_output
+
+    # ------------------------------------------------------------------ anomaly frame
+    def _smoothing(self, metric: Union[pd.DataFrame, pd.Series]):
+        # K6 -- GPU smoothing kernels are the next row; until they land the optional smooth-*
+        # columns are refused rather than computed on the host.
+        raise NotImplementedError(
+            "smoothing (window/smoothing_method) has no B200 kernel yet; construct the detector with window=None"
+        )
+
+    def anomaly(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None) -> pd.DataFrame:
+        """
+        Frame with ``start, end, model-input, model-output, tag-anomaly-scaled, total-anomaly-scaled,
+        tag-anomaly-unscaled, total-anomaly-unscaled`` [+ ``anomaly-confidence, total-anomaly-confidence`` when
+        thresholds exist]; rows follow the model output (shorter than X for LSTM models).
+        """
+        if not hasattr(X, "values"):
+            raise ValueError("Unable to find X.values property")
+        if self.require_thresholds and not any(hasattr(self, a) for a in ("feature_thresholds_", "aggregate_threshold_")):
+            raise AttributeError(
+                f"`require_thresholds={self.require_thresholds}` however `.cross_validate` needs to be called in order "
+                f"to calculate these thresholds before calling `.anomaly`"
+            )
+        if self.window is not None and self.smoothing_method is not None:
+            self._smoothing(None)
+        feat_thr = self.feature_thresholds_.values if getattr(self, "feature_thresholds_", None) is not None else None
+        agg_thr = self.aggregate_threshold_ if getattr(self, "aggregate_threshold_", None) is not None else None
+        res = self._score(self, X, y, self.scaler, feat_thr, agg_thr)
+
+        out = res["model-output"]
+        data = model_utils.make_base_dataframe(
+            tags=X.columns, model_input=X.values, model_output=out, target_tag_list=y.columns,
+            index=getattr(X, "index", None), frequency=frequency,
+        )
+        targets = list(data["model-output"].columns)
+        blocks, cols = [], []
+
+        def add(name, per_tag):
+            if name not in res:
+                return
+            v = np.asarray(res[name], dtype=np.float64)
+            if per_tag:
+                blocks.append(v)
+                cols.extend((name, t) for t in targets)
+            else:
+                blocks.append(v.reshape(-1, 1))
+                cols.append((name, ""))
+
+        add("tag-anomaly-scaled", True)
+        add("total-anomaly-scaled", False)
+        add("tag-anomaly-unscaled", True)
+        add("total-anomaly-unscaled", False)
+        if feat_thr is not None:
+            add("anomaly-confidence", True)
+        if agg_thr is not None:
+            add("total-anomaly-confidence", False)
+        extra = pd.DataFrame(np.concatenate(blocks, axis=1) if blocks else np.empty((len(data), 0)), index=data.index,
+                             columns=pd.MultiIndex.from_tuples(cols))
+        return pd.concat([data, extra], axis=1)

@@ -1,0 +1,469 @@
+"""
+sklearn-style model wrappers with the public surface of gordo/machine/model/models.py
+(KerasBaseEstimator :36-357, KerasAutoEncoder :360-398, KerasLSTMBaseEstimator :463-698,
+KerasLSTMForecast :701-704, KerasLSTMAutoEncoder :707-710, create_keras_timeseriesgenerator :713-793)
+-- same class names, constructor arguments, methods, return types and exceptions -- whose fit and
+predict run as CUDA kernels on a B200 through ``gordo_components_b200.engine``.
+
+The class names keep their "Keras" prefix on purpose: gordo model definitions, the factory registry
+(``register_model_builder.factories["KerasAutoEncoder"]``) and stored metadata key on them.  There is no
+Keras, TensorFlow or scikeras underneath, and no CPU fallback.
+"""
+from __future__ import annotations
+
+import abc
+import importlib
+import logging
+import math
+from copy import copy, deepcopy
+from importlib.util import find_spec
+from typing import Any, Callable, Dict, Optional, Tuple, Union
+
+import numpy as np
+import pandas as pd
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.exceptions import NotFittedError
+from sklearn.metrics import explained_variance_score
+
+from .base import GordoBase
+from .factories import *  # noqa: F401,F403  -- executes the @register_model_builder decorators
+from .factories.specs import FFNetSpec, LSTMNetSpec
+from .register import register_model_builder
+
+logger = logging.getLogger(__name__)
+
+
+class History:
+    """What keras leaves in ``model.history``: per-epoch metric lists, the fit params and the epoch index."""
+
+    def __init__(self, history=None, params=None, epoch=None):
+        self.history = history or {}
+        self.params = params or {}
+        self.epoch = epoch or []
+
+
+class FittedNet:
+    """A trained network: its specification plus host copies of the weights (what gets pickled)."""
+
+    def __init__(self, spec, weights):
+        self.spec = spec
+        self.weights = weights
+        self.history: Optional[History] = None
+
+    @property
+    def layers(self):
+        return self.spec.units
+
+    def get_weights(self):
+        return self.weights
+
+
+def _glorot_uniform(fan_in: int, fan_out: int) -> np.ndarray:
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return np.random.uniform(-limit, limit, size=(fan_in, fan_out)).astype(np.float32)
+
+
+def _orthogonal(rows: int, cols: int) -> np.ndarray:
+    a = np.random.standard_normal((max(rows, cols), min(rows, cols)))
+    q, r = np.linalg.qr(a)
+    q = q * np.sign(np.diag(r))
+    if rows < cols:
+        q = q.T
+    return q[:rows, :cols].astype(np.float32)
+
+
+def _as_2d_values(a):
+    a = getattr(a, "values", a)
+    return np.asarray(a)
+
+
+class KerasBaseEstimator(BaseEstimator, GordoBase):
+    # keyword arguments of the model definition that steer fitting rather than the architecture
+    supported_fit_args = [
+        "batch_size", "epochs", "verbose", "callbacks", "validation_split", "shuffle", "class_weight", "initial_epoch",
+        "steps_per_epoch", "validation_batch_size", "max_queue_size", "workers", "use_multiprocessing",
+    ]
+
+    def __init__(self, kind: Union[str, Callable], **kwargs) -> None:
+        """
+        ``kind`` names a registered factory for this class (``feedforward_hourglass`` ...), a dotted path to a
+        factory function, or is the factory function itself (it must take ``n_features``).  Every other keyword
+        goes to the factory and/or steers ``fit`` (``epochs``, ``batch_size``, ``validation_split``, ``shuffle``).
+        """
+        self.kind = self.load_kind(kind)
+        self.kwargs: Dict[str, Any] = kwargs
+        self._history: Optional[History] = None
+        self.model: Optional[FittedNet] = None
+
+    # ------------------------------------------------------------------ definition <-> object
+    @staticmethod
+    def parse_module_path(module_path) -> Tuple[Optional[str], str]:
+        parts = module_path.split(".")
+        return (None, parts[0]) if len(parts) == 1 else (".".join(parts[:-1]), parts[-1])
+
+    def load_kind(self, kind):
+        if callable(kind):
+            register_model_builder(type=self.__class__.__name__)(kind)
+            return kind.__name__
+        module_name, name = self.parse_module_path(kind)
+        if module_name is None:
+            if name not in register_model_builder.factories.get(self.__class__.__name__, {}):
+                raise ValueError(f"kind: {kind} is not an available model for type: {self.__class__.__name__}!")
+        else:
+            try:
+                found = find_spec(module_name) is not None
+            except ModuleNotFoundError:
+                found = False
+            if not found:
+                raise ValueError(f"kind: {kind}, unable to find module: '{module_name}'")
+        return kind
+
+    @classmethod
+    def extract_supported_fit_args(cls, kwargs):
+        return {k: kwargs[k] for k in cls.supported_fit_args if k in kwargs}
+
+    @classmethod
+    def from_definition(cls, definition: dict):
+        """Hook used by gordo.serializer.from_definition (gordo/serializer/from_definition.py:190-191)."""
+        definition = copy(definition)
+        kind = definition.pop("kind")
+        return cls(kind, **definition)
+
+    def into_definition(self) -> dict:
+        """Hook used by gordo.serializer.into_definition (gordo/serializer/into_definition.py:92-93)."""
+        definition = copy(self.kwargs)
+        definition["kind"] = self.kind
+        return definition
+
+    @property
+    def sk_params(self):
+        return self.kwargs
+
+    def get_params(self, **params):
+        out = {"kind": self.kind}
+        out.update(self.kwargs)
+        return out
+
+    def set_params(self, **params):
+        if "kind" in params:
+            self.kind = self.load_kind(params.pop("kind"))
+        self.kwargs.update(params)
+        return self
+
+    def __sklearn_clone__(self):
+        return self.__class__(self.kind, **deepcopy(self.kwargs))
+
+    # ------------------------------------------------------------------ pickling: plain numpy state, no device handles
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_dev_cache", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    # ------------------------------------------------------------------ shapes
+    @staticmethod
+    def get_n_features_out(y) -> Union[int, tuple]:
+        if len(y.shape) == 1:
+            raise ValueError("Unsupported number of the output dataset dimensions %d" % len(y.shape))
+        return y.shape[1] if len(y.shape) == 2 else y.shape[1:]
+
+    @staticmethod
+    def get_n_features(X) -> Union[int, tuple]:
+        if len(X.shape) == 1:
+            raise ValueError("Unsupported number of the output dataset dimensions %d" % len(X.shape))
+        return X.shape[1] if len(X.shape) == 2 else X.shape[2]
+
+    # ------------------------------------------------------------------ model construction
+    def _factory(self):
+        module_name, name = self.parse_module_path(self.kind)
+        if module_name is None:
+            return register_model_builder.factories[self.__class__.__name__][self.kind]
+        module = importlib.import_module(module_name)
+        if not hasattr(module, name):
+            raise ValueError("kind: %s, unable to find class %s in module '%s'" % (self.kind, name, module_name))
+        return getattr(module, name)
+
+    def _build_spec(self):
+        spec = self._factory()(**self.sk_params)
+        if not isinstance(spec, (FFNetSpec, LSTMNetSpec)):
+            raise ValueError(
+                f"factory {self.kind!r} returned {type(spec).__name__}; B200 factories must return an FFNetSpec or LSTMNetSpec"
+            )
+        return spec
+
+    def _initial_weights(self, spec):
+        """Keras initialisers [3P]: Dense/LSTM kernels glorot_uniform, recurrent kernels orthogonal, biases zero (forget gate 1)."""
+        if isinstance(spec, FFNetSpec):
+            return [(_glorot_uniform(i, o), np.zeros(o, np.float32)) for i, o in zip(spec.dims[:-1], spec.dims[1:])]
+        layers, i = [], spec.n_features
+        for u in spec.lstm_units:
+            b = np.zeros(4 * u, np.float32)
+            b[u : 2 * u] = 1.0
+            layers.append((_glorot_uniform(i, 4 * u), _orthogonal(u, 4 * u), b))
+            i = u
+        return layers, (_glorot_uniform(i, spec.n_features_out), np.zeros(spec.n_features_out, np.float32))
+
+    def _prepare_model(self):
+        spec = self._build_spec()
+        self.model = FittedNet(spec, self._initial_weights(spec))
+
+    def set_weights(self, weights):
+        """Install trained weights (Keras order: per Dense layer (kernel [in,out], bias [out]))."""
+        if self.model is None:
+            if "n_features" not in self.kwargs:
+                raise NotFittedError("set_weights needs n_features: pass it in kwargs or call fit first")
+            self._prepare_model()
+        self.model.weights = weights
+        self.__dict__.pop("_dev_cache", None)
+        return self
+
+    # ------------------------------------------------------------------ device plumbing
+    def _engine(self):
+        from ... import engine
+
+        return engine.ff_engine_for(self.model.spec)
+
+    def _device_params(self):
+        cache = self.__dict__.get("_dev_cache")
+        if cache is None or cache[0] is not self.model.weights:
+            eng = self._engine()
+            cache = (self.model.weights, eng.pack_params([self.model.weights]))
+            self.__dict__["_dev_cache"] = cache
+        return cache[1]
+
+    # ------------------------------------------------------------------ fit / predict
+    def fit(self, X, y, **kwargs):
+        """
+        Train on ``X`` -> ``y`` (numpy arrays or DataFrames).  Keyword arguments override the fit arguments given
+        at construction (``epochs``, ``batch_size``, ``shuffle``, ``validation_split``).
+        """
+        from ... import engine
+
+        if isinstance(y, np.ndarray) and y.ndim == 1:
+            y = y.reshape(-1, 1)
+        self.kwargs.update({"n_features": self.get_n_features(X), "n_features_out": self.get_n_features_out(y)})
+        X, y = _as_2d_values(X), _as_2d_values(y)
+        if self.model is None:
+            self._prepare_model()
+        spec = self.model.spec
+        if spec.dims[0] != X.shape[1] or spec.dims[-1] != y.shape[1]:
+            raise ValueError(f"model was built for {spec.dims[0]}->{spec.dims[-1]} features, got X {X.shape} y {y.shape}")
+        fit_args = {**self.extract_supported_fit_args(self.kwargs), **kwargs}
+        epochs = int(fit_args.get("epochs", 1))
+        batch_size = int(fit_args.get("batch_size") or 32)
+        shuffle = bool(fit_args.get("shuffle", True))
+        vsplit = float(fit_args.get("validation_split") or 0.0)
+        if fit_args.get("callbacks"):
+            logger.warning("callbacks %s are not supported by the B200 fit kernel and are ignored", fit_args["callbacks"])
+        n_train = len(X)
+        if 0.0 < vsplit < 1.0:  # keras holds out the *tail* before shuffling
+            n_train = int(math.floor(len(X) * (1.0 - vsplit)))
+        if n_train < 1:
+            raise ValueError("no training rows")
+
+        eng = engine.ff_engine_for(spec)
+        dev = eng.device
+        xd, yd = engine.to_device_f32(X, dev), engine.to_device_f32(y, dev)
+        params = eng.pack_params([self.model.weights])
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [n_train], [0]), dev)
+        seed = int(np.random.randint(0, 2**31 - 1))  # follows numpy's global seed, like gordo's builder set_seed
+        history: Dict[str, list] = {"loss": []}
+        if "accuracy" in spec.metrics:
+            history["accuracy"] = []
+        if n_train < len(X):
+            history["val_loss"] = []
+            vjobs = engine.jobs_to_device(engine.make_jobs([0], [len(X) - n_train], [n_train]), dev)
+            state, step0 = None, 0
+            steps = int(math.ceil(n_train / batch_size))
+            for e in range(epochs):
+                loss, acc, state = eng.fit(params, jobs, 1, n_train, xd, yd, epochs=1, batch_size=batch_size, shuffle=shuffle,
+                                           adam=spec.adam, seed=seed + e, state=state, step0=step0)
+                step0 += steps
+                history["loss"].append(float(loss[0, 0]))
+                if "accuracy" in history:
+                    history["accuracy"].append(float(acc[0, 0]))
+                res = eng.infer_score(params, vjobs, 1, len(X) - n_train, xd, yd, want=("total-anomaly-unscaled",))
+                history["val_loss"].append(float(res["total-anomaly-unscaled"][n_train:].mean()))
+        else:
+            loss, acc, _ = eng.fit(params, jobs, 1, n_train, xd, yd, epochs=epochs, batch_size=batch_size, shuffle=shuffle,
+                                   adam=spec.adam, seed=seed)
+            history["loss"] = [float(v) for v in loss[0].cpu().numpy()]
+            if "accuracy" in history:
+                history["accuracy"] = [float(v) for v in acc[0].cpu().numpy()]
+        self.model.weights = eng.unpack_params(params)[0]
+        self.__dict__["_dev_cache"] = (self.model.weights, params)
+        self._history = History(history, {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n_train / batch_size))}, list(range(epochs)))
+        self.model.history = self._history
+        return self
+
+    def predict(self, X, **kwargs) -> np.ndarray:
+        """Model output for every row of ``X`` as a float32 array ``[len(X), n_features_out]``."""
+        from ... import engine
+
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        X = _as_2d_values(X)
+        if X.ndim != 2 or X.shape[1] != self.model.spec.dims[0]:
+            raise ValueError(f"X has shape {X.shape}; the model expects [n, {self.model.spec.dims[0]}]")
+        eng = self._engine()
+        if len(X) == 0:
+            return np.empty((0, eng.n_out), np.float32)
+        xd = engine.to_device_f32(X, eng.device)
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [len(X)], [0]), eng.device)
+        res = eng.infer_score(self._device_params(), jobs, 1, len(X), xd)
+        return res["model-output"].cpu().numpy()
+
+    def get_metadata(self):
+        """``{"history": {<metric>: [per epoch...], "params": {...}}}`` after fit, ``{}`` before."""
+        if self._history is not None:
+            history = self._history.history
+            history["params"] = self._history.params
+            return {"history": history}
+        return {}
+
+
+class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
+    """Feed-forward autoencoder; ``score`` is the explained variance of the reconstruction."""
+
+    def score(self, X, y, sample_weight=None, **kwargs) -> float:
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        return explained_variance_score(_as_2d_values(y), self.predict(X, **kwargs))
+
+
+class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin, metaclass=abc.ABCMeta):
+    """Many-to-one LSTM over a sliding ``lookback_window`` (autoencoder: lookahead 0, forecast: lookahead 1)."""
+
+    def __init__(self, kind: Union[Callable, str], lookback_window: int = 1, batch_size: int = 32, **kwargs) -> None:
+        self.lookback_window = lookback_window
+        self.batch_size = batch_size
+        kwargs["lookback_window"] = lookback_window
+        kwargs["batch_size"] = batch_size
+        super().__init__(kind, **kwargs)
+
+    def __sklearn_clone__(self):
+        kw = deepcopy(self.kwargs)
+        kw.pop("lookback_window", None)
+        kw.pop("batch_size", None)
+        return self.__class__(self.kind, lookback_window=self.lookback_window, batch_size=self.batch_size, **kw)
+
+    @property
+    @abc.abstractmethod
+    def lookahead(self) -> int:
+        """Steps ahead in y the model targets."""
+
+    def get_metadata(self):
+        metadata = super().get_metadata()
+        metadata.update({"forecast_steps": self.lookahead})
+        return metadata
+
+    def _validate_and_fix_size_of_X(self, X):
+        if X.ndim == 1:
+            X = X.reshape(len(X), 1)
+        if self.lookback_window >= X.shape[0]:
+            raise ValueError("For KerasLSTMForecast lookback_window must be < size of X")
+        return X
+
+    def _engine(self):
+        from ... import engine
+
+        return engine.lstm_engine_for(self.model.spec)
+
+    def initialize(self, n_features: int, n_features_out: Optional[int] = None):
+        """Build the network with freshly initialised weights (what the reference's primer fit does, models.py:585-597)."""
+        self.kwargs.update({"n_features": int(n_features), "n_features_out": int(n_features_out or n_features)})
+        self._prepare_model()
+        return self
+
+    def fit(self, X, y, **kwargs):
+        """
+        LSTM training (BPTT) has no B200 kernel yet: the network is built and initialised exactly as the reference's
+        primer fit does, then NotImplementedError is raised rather than silently training somewhere else.
+        """
+        X = self._validate_and_fix_size_of_X(_as_2d_values(X))
+        y = _as_2d_values(y)
+        if y.ndim == 1:
+            y = y.reshape(-1, 1)
+        self.initialize(X.shape[1], y.shape[1])
+        raise NotImplementedError(
+            "KerasLSTM*.fit: the LSTM training kernel is not built yet (round-1 scope is LSTM inference); "
+            "install weights with set_weights() -- there is deliberately no CPU/framework fallback"
+        )
+
+    def predict(self, X, **kwargs) -> np.ndarray:
+        """``[len(X) - lookback_window + 1 - lookahead, n_features_out]`` float32: row j is the net applied to X[j : j+lookback]."""
+        from ... import engine
+
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        X = self._validate_and_fix_size_of_X(_as_2d_values(X))
+        eng = self._engine()
+        n_win = len(X) - self.lookback_window + 1 - self.lookahead
+        if n_win <= 0:
+            return np.empty((0, eng.n_out), np.float32)
+        xd = engine.to_device_f32(X, eng.device)
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [n_win], [0]), eng.device)
+        cache = self.__dict__.get("_dev_cache")
+        if cache is None or cache[0] is not self.model.weights:
+            cache = (self.model.weights, eng.pack_params([self.model.weights]))
+            self.__dict__["_dev_cache"] = cache
+        return eng.infer(cache[1], jobs, 1, n_win, xd, n_win).cpu().numpy()
+
+    def score(self, X, y, sample_weight=None, **kwargs) -> float:
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        out = self.predict(X, **kwargs)
+        return explained_variance_score(_as_2d_values(y)[-len(out):], out)
+
+
+class KerasLSTMForecast(KerasLSTMBaseEstimator):
+    @property
+    def lookahead(self) -> int:
+        return 1
+
+
+class KerasLSTMAutoEncoder(KerasLSTMBaseEstimator):
+    @property
+    def lookahead(self) -> int:
+        return 0
+
+
+class TimeseriesWindows:
+    """
+    Index form of the reference's generator: sample j is ``X[j : j+lookback]`` with target
+    ``y[j + lookback - 1 + lookahead]``.  Batches are materialised only when indexed (host side, for
+    inspection/tests); the LSTM kernels read the windows straight out of ``X``.
+    """
+
+    def __init__(self, X, y, batch_size, lookback_window, lookahead):
+        self.X, self.y = np.asarray(X), (np.asarray(y) if y is not None else None)
+        self.batch_size, self.lookback_window, self.lookahead = int(batch_size), int(lookback_window), int(lookahead)
+        count = max(len(self.X) - self.lookback_window + 1 - self.lookahead, 0)
+        self.starts = np.arange(count)
+        self.targets = self.starts + self.lookback_window - 1 + self.lookahead
+
+    def __len__(self):
+        return int(math.ceil(len(self.starts) / self.batch_size))
+
+    def __getitem__(self, i):
+        js = self.starts[i * self.batch_size : (i + 1) * self.batch_size]
+        bx = np.array([self.X[j : j + self.lookback_window] for j in js])
+        by = self.y[self.targets[i * self.batch_size : (i + 1) * self.batch_size]] if self.y is not None else None
+        return bx, by
+
+
+def create_keras_timeseriesgenerator(X, y, batch_size: int, lookback_window: int, lookahead: int) -> TimeseriesWindows:
+    """
+    Windows over ``X`` with the target shifted ``lookahead`` steps past the window's last row.
+
+    >>> import numpy as np
+    >>> X, y = np.random.rand(100, 2), np.random.rand(100, 2)
+    >>> gen = create_keras_timeseriesgenerator(X, y, batch_size=10, lookback_window=20, lookahead=0)
+    >>> len(gen), len(gen[0]), len(gen[0][0]), len(gen[0][0][0]), len(gen[0][0][0][0])
+    (9, 2, 10, 20, 2)
+    """
+    if lookahead < 0:
+        raise ValueError(f"Value of `lookahead` can not be negative, is {lookahead}")
+    return TimeseriesWindows(X, y, batch_size, lookback_window, lookahead)

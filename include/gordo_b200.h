@@ -1,0 +1,191 @@
+/*
+ * gordo_b200.h -- C ABI of the B200 (sm_100a) implementation of gordo's per-machine
+ * autoencoder train-and-score hot path.
+ *
+ * The reference (equinor/gordo-components) has no native FFI: its plug-in boundary is a
+ * Python class path + the sklearn/GordoBase protocol (gordo/machine/model/base.py:10-35,
+ * gordo/machine/model/anomaly/base.py:11-23, gordo/serializer/from_definition.py:176-191).
+ * This header is the seam *below* that protocol: every arithmetic library call the
+ * reference makes on the hot path (Keras Model.predict / Model.fit, sklearn MinMaxScaler,
+ * pandas rolling/abs/mean in DiffBasedAnomalyDetector) maps to one entry point here.
+ * Each entry point cites the reference call it replaces.  INTEGRATION.md shows the
+ * ctypes binding (gordo_components_b200/_cabi.py is the live copy).
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no torch types.  Unless stated otherwise every
+ *    pointer is a DEVICE pointer owned by the caller; nothing here allocates or frees.
+ *  - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns
+ *    without synchronising.  Return value: 0 or a negative gb_status; the message of
+ *    the last failure on the calling thread is available from gb_last_error().
+ *  - float32 everywhere on device; row-major; rows of all machines are concatenated:
+ *    x[total_rows][n_features], y / outputs [total_rows][n_features_out].
+ *  - a *slot* is one trained network (a machine, or one CV fold of a machine); a *job*
+ *    binds a slot to a contiguous range of rows.
+ */
+#ifndef GORDO_B200_H
+#define GORDO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_ABI_VERSION 1
+#define GB_MAX_LAYERS 16
+#define GB_MAX_WIDTH 128 /* widest layer / feature count the resident-weight kernels accept */
+
+typedef enum gb_status {
+  GB_OK = 0,
+  GB_E_ARG = -1,     /* null pointer / bad enum / inconsistent sizes          -> ValueError  */
+  GB_E_SHAPE = -2,   /* architecture outside what the kernels support          -> ValueError  */
+  GB_E_ALIGN = -3,   /* pointer not 16-byte aligned                            -> ValueError  */
+  GB_E_SMEM = -4,    /* architecture does not fit in shared memory             -> ValueError  */
+  GB_E_CUDA = -5,    /* CUDA runtime error (message has cudaGetErrorString)    -> RuntimeError*/
+  GB_E_DEVICE = -6   /* no sm_100 device                                       -> RuntimeError*/
+} gb_status;
+
+typedef enum gb_act { GB_ACT_LINEAR = 0, GB_ACT_TANH = 1, GB_ACT_RELU = 2, GB_ACT_SIGMOID = 3 } gb_act;
+
+/* Dense stack built by feedforward_model / feedforward_symmetric / feedforward_hourglass
+ * (gordo/machine/model/factories/feedforward_autoencoder.py:65-104).  dims[0] = n_features,
+ * dims[l+1] = units of Dense layer l; l1[l] = activity_regularizer l1 coefficient of layer l
+ * (10e-5 on encoder layers i>=1, :80-81), used by training only. */
+typedef struct gb_ffnet {
+  int32_t n_layers;
+  int32_t dims[GB_MAX_LAYERS + 1];
+  int32_t act[GB_MAX_LAYERS];
+  float l1[GB_MAX_LAYERS];
+} gb_ffnet;
+
+/* One unit of work: network `slot` applied to rows [x_row, x_row + n_rows) of x / y,
+ * results written to rows [out_row, out_row + n_rows) of the output arrays. */
+typedef struct gb_job {
+  int32_t slot;
+  int32_t n_rows;
+  int64_t x_row;
+  int64_t out_row;
+} gb_job;
+
+/* ---- library ------------------------------------------------------------------------ */
+int gb_abi_version(void);
+const char* gb_last_error(void);
+/* 0 if `device` is an sm_100 part; GB_E_DEVICE otherwise.  Fills sm count if non-null. */
+int gb_device_check(int device, int* sm_count);
+
+/* ---- parameter layout ---------------------------------------------------------------
+ * Canonical per-slot parameter vector ("Keras order"): for each layer l: kernel
+ * W_l[dims[l]][dims[l+1]] row-major (Keras Dense kernel layout [in,out]) then bias
+ * b_l[dims[l+1]].  Slots are `gb_ffnet_param_stride()` floats apart (count rounded up to 4). */
+size_t gb_ffnet_param_count(const gb_ffnet* net);
+size_t gb_ffnet_param_stride(const gb_ffnet* net);
+
+/* ---- K1+K4: predict + anomaly score, fused --------------------------------------------
+ * Replaces, per job: KerasBaseEstimator.predict -> keras Model.predict
+ * (gordo/machine/model/models.py:289-300) and the arithmetic of
+ * DiffBasedAnomalyDetector.anomaly (gordo/machine/model/anomaly/diff.py:350-385, 420-444):
+ *   out_model            = net(x)                                   [rows][n_out]
+ *   out_tag_unscaled     = |out_model - y|                          [rows][n_out]
+ *   out_tag_scaled       = |out_model - y| * scale[slot]            [rows][n_out]   (MinMax offset cancels)
+ *   out_total_unscaled   = mean_j(out_tag_unscaled^2)               [rows]
+ *   out_total_scaled     = mean_j(out_tag_scaled^2)                 [rows]
+ *   out_conf             = out_tag_unscaled / feat_thr[slot]        [rows][n_out]   (diff.py:421 uses the unscaled diff)
+ *   out_total_conf       = out_total_scaled / agg_thr[slot]         [rows]
+ * y == NULL -> prediction only (all score outputs must be NULL).  Any score output may be
+ * NULL and is then skipped; feat_thr / agg_thr NULL -> the confidences must be NULL.
+ * params: [n_slots][param_stride]; scale, feat_thr: [n_slots][n_out]; agg_thr: [n_slots].
+ * jobs: DEVICE array of n_jobs gb_job; max_rows = max n_rows over jobs (host value, sizes the grid).
+ * variant: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 3xTF32 kernel (GB_E_SHAPE if unsupported). */
+int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* jobs, int32_t n_jobs,
+                        int32_t max_rows, const float* x, const float* y, const float* scale,
+                        const float* feat_thr, const float* agg_thr, float* out_model,
+                        float* out_tag_scaled, float* out_tag_unscaled, float* out_total_scaled,
+                        float* out_total_unscaled, float* out_conf, float* out_total_conf,
+                        int32_t variant, void* stream);
+
+/* GB_OK if the tcgen05 (variant 2) kernel covers this architecture, else GB_E_SHAPE. */
+int gb_ffae_tc_supported(const gb_ffnet* net);
+
+/* ---- K4 alone: anomaly score of predictions that already exist ----------------------------
+ * Same outputs as gb_ffae_infer_score, for a `yhat` produced elsewhere (a base estimator that is not
+ * one of ours, e.g. the sklearn regressors the reference's detector tests use; an LSTM prediction from
+ * gb_lstm_infer).  yhat and all outputs are indexed by out_row, y by x_row. */
+int gb_anomaly_score(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* yhat, const float* y,
+                     int32_t n_out, const float* scale, const float* feat_thr, const float* agg_thr,
+                     float* out_tag_scaled, float* out_tag_unscaled, float* out_total_scaled,
+                     float* out_total_unscaled, float* out_conf, float* out_total_conf, void* stream);
+
+/* ---- K7: MinMaxScaler.fit on the targets (diff.py:173; sklearn MinMaxScaler [3P]) -------
+ * per job: scale[slot][j] = 1/(max_j - min_j) (zero range -> 1), offset[slot][j] = -min_j*scale.
+ * minmax_ws: workspace [n_slots][2][n_out] floats (overwritten). */
+int gb_minmax_fit(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* y, int32_t n_out,
+                  float* scale, float* offset, float* minmax_ws, int32_t n_slots, void* stream);
+
+/* ---- K5: thresholds of one CV fold (diff.py:222-233) ------------------------------------
+ *   feat_thr[slot][j] = max_t min(tag_unscaled[t-window+1 .. t][j])   (rolling(window).min().max())
+ *   agg_thr[slot]     = max_t min(total_scaled[t-window+1 .. t])
+ * rows are taken at [out_row, out_row+n_rows) of the score arrays produced by
+ * gb_ffae_infer_score for the fold's test rows.  n_rows < window -> NaN (pandas semantics). */
+int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* tag_unscaled,
+                  const float* total_scaled, int32_t n_out, int32_t window, float* feat_thr,
+                  float* agg_thr, int32_t n_slots, void* stream);
+
+/* ---- K2: fit ---------------------------------------------------------------------------
+ * Replaces scikeras KerasRegressor.fit -> keras Model.fit (models.py:284) for the Dense
+ * stacks above: per job, `epochs` passes over rows [x_row, x_row+n_rows) in batches of
+ * `batch_size`, loss = mean((net(x)-y)^2) + sum_l l1[l]*sum|a_l|, Adam (Keras defaults).
+ * One CTA per job trains the whole fit with weights resident in shared memory. */
+typedef struct gb_fit_hparams {
+  int32_t epochs;
+  int32_t batch_size;
+  int32_t shuffle;        /* 0: sequential order; 1: on-device keyed permutation per (seed, slot, epoch);
+                             2: explicit `perm` (parity testing / reproducing a given order) */
+  int32_t l1_div_batch;   /* 0: keras 3.3.3 behaviour (activity loss not divided by batch size) */
+  float lr, beta1, beta2, eps;
+  uint64_t seed;
+  int32_t step0;          /* Adam step count already taken (warm start); 0 for a fresh fit */
+  int32_t reserved;
+} gb_fit_hparams;
+
+/* Adam moments are opaque optimizer state in the kernel's padded layout: gb_ffae_fit_state_stride() floats per slot. */
+size_t gb_ffae_fit_state_stride(const gb_ffnet* net);
+
+/* params: [n_slots][param_stride], updated in place.  adam_m / adam_v: [n_slots][state_stride], updated in place
+ * (all zero for a fresh fit).  batch_size <= 32 in this version (one mini-batch row per lane).
+ * perm: [n_jobs][epochs][max_rows] int32 row indices relative to the job (shuffle == 2), else NULL.
+ * out_loss / out_acc: [n_jobs][epochs] per-epoch sample-weighted mean loss / categorical accuracy
+ * (keras History.history["loss"], ["accuracy"], models.py:339-357). */
+int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v, const gb_job* jobs,
+                int32_t n_jobs, int32_t max_rows, const float* x, const float* y, const int32_t* perm,
+                const gb_fit_hparams* hp, float* out_loss, float* out_acc, void* stream);
+
+/* ---- K3: LSTM autoencoder predict --------------------------------------------------------
+ * lstm_model / lstm_symmetric / lstm_hourglass (factories/lstm_autoencoder.py:72-103):
+ * LSTM layers (gate order i,f,c,o; sigmoid recurrent activation; zero initial state per
+ * window) then Dense.  Replaces KerasLSTMBaseEstimator.predict (models.py:618-660) without
+ * materialising windows (create_keras_timeseriesgenerator, models.py:713-793): output row j
+ * of a job is the network applied to x rows [x_row + j, x_row + j + lookback). */
+typedef struct gb_lstmnet {
+  int32_t n_layers;                 /* LSTM layers */
+  int32_t n_features, n_features_out;
+  int32_t units[GB_MAX_LAYERS];
+  int32_t act[GB_MAX_LAYERS];       /* cell/output activation of each LSTM layer (tanh default) */
+  int32_t out_act;                  /* Dense activation */
+  int32_t lookback;
+} gb_lstmnet;
+
+/* per-slot parameter vector: for each layer: kernel [in][4u], recurrent_kernel [u][4u], bias [4u];
+ * then Dense kernel [u_last][n_out], bias [n_out]. */
+size_t gb_lstm_param_count(const gb_lstmnet* net);
+size_t gb_lstm_param_stride(const gb_lstmnet* net);
+/* jobs: n_rows = number of *windows* (output rows); x rows read = n_rows + lookback - 1.
+ * workspace: gb_lstm_workspace_bytes() bytes of device scratch. */
+size_t gb_lstm_workspace_bytes(const gb_lstmnet* net, int32_t n_jobs, int32_t max_rows);
+int gb_lstm_infer(const gb_lstmnet* net, const float* params, const gb_job* jobs, int32_t n_jobs,
+                  int32_t max_rows, const float* x, float* out_model, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORDO_B200_H */

@@ -1,0 +1,487 @@
+"""
+Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden fixtures.
+
+Tolerance (north_star: "within 1e-4 relative"): model output |got - want| <= 1e-4*|want| + 1e-4*SCALE*eps-floor,
+where the floor covers outputs near zero; quantities formed by subtracting the target (abs diffs, their squares,
+confidences) carry the same *absolute* uncertainty as the model output, so they are compared with
+atol = 1e-4 * (magnitude of y) -- a relative bound on a difference of nearly equal numbers is not meaningful in
+any float32 implementation, the reference's included.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    if not t.cuda.is_available():
+        pytest.skip("needs a B200")
+    import __graft_entry__ as ge
+
+    ge.build()
+    return t
+
+
+@pytest.fixture(scope="module")
+def engine(torch):
+    from gordo_components_b200 import engine as e
+
+    return e
+
+
+def close(got, want, mag=1.0, rtol=RTOL, name=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    err = np.abs(got - want)
+    tol = rtol * np.abs(want) + rtol * mag
+    bad = ~(err <= tol) & ~(np.isnan(got) & np.isnan(want))
+    assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} outside tolerance; max err {err[bad].max():.3e} (tol {tol[bad].min():.3e})"
+
+
+def random_net(km, dims_or_T, seed, acts=None):
+    rng = np.random.default_rng(seed)
+    spec = km.ff_hourglass_spec(dims_or_T) if isinstance(dims_or_T, int) else km.FFSpec(list(dims_or_T), acts or ["tanh"] * (len(dims_or_T) - 2) + ["linear"])
+    w = km.init_ff_weights(spec, rng)
+    w = [(W, rng.uniform(-0.2, 0.2, b.shape).astype(np.float32)) for W, b in w]
+    return spec, w
+
+
+def run_infer(engine, torch, spec, weights_per_slot, X, y, jobs_h, scale=None, feat=None, agg=None, out_rows=None, variant=0):
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+    res = eng.infer_score(eng.pack_params(weights_per_slot), engine.jobs_to_device(jobs_h, dev), len(jobs_h), int(jobs_h["n_rows"].max()),
+                          t(X), t(y), t(scale), t(feat), t(agg), out_rows=out_rows, variant=variant)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+# ------------------------------------------------------------------------------------------------ K1 + K4
+@pytest.mark.parametrize("T", [4, 8, 10, 64, 128])
+def test_ffae_infer_score_matches_oracle(engine, torch, T):
+    from oracle import anomaly_math as am
+    from oracle import keras_math as km
+
+    M, R = 5, 333  # ragged against the 128-row tile
+    rng = np.random.default_rng(T)
+    nets = [random_net(km, T, 10 * T + m) for m in range(M)]
+    spec = nets[0][0]
+    X = (rng.random((M * R, T)) * 2 - 0.5).astype(np.float32)
+    y = (X + rng.normal(0, 0.05, X.shape)).astype(np.float32)
+    jobs = engine.uniform_jobs(M, R)
+    scales = np.stack([am.minmax_fit(y[m * R:(m + 1) * R])[0] for m in range(M)]).astype(np.float32)
+    feat = (rng.random((M, T)) * 0.2 + 0.05).astype(np.float32)
+    agg = (rng.random(M) * 0.1 + 0.01).astype(np.float32)
+    got = run_infer(engine, torch, spec, [w for _, w in nets], X, y, jobs, scales, feat, agg, variant=1)
+    for m in range(M):
+        sl = slice(m * R, (m + 1) * R)
+        want_out = km.ff_forward(spec, nets[m][1], X[sl], dtype=np.float64)
+        sc, mn = am.minmax_fit(y[sl])
+        want = am.anomaly_arrays(want_out, y[sl], scales[m].astype(np.float64), mn, feat[m], float(agg[m]))
+        close(got["model-output"][sl], want_out, 1.0, name="model-output")
+        close(got["tag-anomaly-unscaled"][sl], want["tag-anomaly-unscaled"], 1.0, name="tag-anomaly-unscaled")
+        close(got["tag-anomaly-scaled"][sl], want["tag-anomaly-scaled"], float(scales[m].max()), name="tag-anomaly-scaled")
+        close(got["total-anomaly-unscaled"][sl], want["total-anomaly-unscaled"], 1.0 * np.sqrt(want["total-anomaly-unscaled"].max()), name="total-unscaled")
+        close(got["total-anomaly-scaled"][sl], want["total-anomaly-scaled"], float(scales[m].max()) * np.sqrt(want["total-anomaly-scaled"].max()), name="total-scaled")
+        close(got["anomaly-confidence"][sl], want["anomaly-confidence"], float((1 / feat[m]).max()), name="confidence")
+        close(got["total-anomaly-confidence"][sl], want["total-anomaly-confidence"], float(scales[m].max()) * np.sqrt(want["total-anomaly-scaled"].max()) / float(agg[m]), name="total-confidence")
+
+
+def test_ffae_jobs_slots_and_row_offsets(engine, torch):
+    """Jobs may share a slot, read any row range and write anywhere; empty jobs are no-ops; predict-only mode."""
+    from oracle import keras_math as km
+
+    T = 8
+    nets = [random_net(km, T, s) for s in (1, 2)]
+    spec = nets[0][0]
+    X = np.random.default_rng(0).random((1000, T)).astype(np.float32)
+    jobs = engine.make_jobs([1, 0, 1, 0], [130, 1, 0, 257], [700, 5, 0, 100], [0, 130, 131, 131])
+    got = run_infer(engine, torch, spec, [w for _, w in nets], X, None, jobs, out_rows=131 + 257)
+    out = got["model-output"]
+    close(out[:130], km.ff_forward(spec, nets[1][1], X[700:830], np.float64), name="job0")
+    close(out[130:131], km.ff_forward(spec, nets[0][1], X[5:6], np.float64), name="job1")
+    close(out[131:388], km.ff_forward(spec, nets[0][1], X[100:357], np.float64), name="job3")
+    assert set(got) == {"model-output"}
+
+
+@pytest.mark.parametrize("dims,acts", [([6, 5, 3, 7], ["relu", "sigmoid", "linear"]), ([33, 17, 33], ["tanh", "tanh"]), ([5, 9, 2], ["sigmoid", "relu"])])
+def test_ffae_generic_architectures(engine, torch, dims, acts):
+    """feedforward_model / feedforward_symmetric with arbitrary widths, activations and n_features_out != n_features."""
+    from oracle import keras_math as km
+
+    spec, w = random_net(km, dims, 3, acts)
+    rng = np.random.default_rng(1)
+    X = rng.random((200, dims[0])).astype(np.float32)
+    y = rng.random((200, dims[-1])).astype(np.float32)
+    sc = np.ones((1, dims[-1]), np.float32)
+    got = run_infer(engine, torch, spec, [w], X, y, engine.uniform_jobs(1, 200), sc)
+    want = km.ff_forward(spec, w, X, np.float64)
+    close(got["model-output"], want, name="out")
+    close(got["tag-anomaly-unscaled"], np.abs(want - y), name="tu")
+    close(got["total-anomaly-scaled"], ((want - y) ** 2).mean(axis=1), name="tot")
+
+
+@pytest.mark.parametrize("case", ["ffnet_anomaly", "ffnet_anomaly_t64"])
+def test_ffae_against_reference_generated_fixture(engine, torch, case):
+    """Fixture columns were produced by the reference's own diff.py (tests/golden/make_golden.py)."""
+    from oracle import keras_math as km
+
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    dims = [int(d) for d in g["net_dims"]]
+    spec = km.ff_hourglass_spec(dims[0])
+    w = [(g[f"W{l}"], g[f"b{l}"]) for l in range(spec.n_layers)]
+    X, y = g["X"], g["y"]
+    got = run_infer(engine, torch, spec, [w], X, y, engine.uniform_jobs(1, len(X)), g["scale"][None], g["feature_thresholds"][None],
+                    np.array([float(g["aggregate_threshold"])]))
+    smax = float(g["scale"].max())
+    close(got["model-output"], g["frame_model-output"], name="model-output")
+    close(got["tag-anomaly-unscaled"], g["frame_tag-anomaly-unscaled"], name="tag-anomaly-unscaled")
+    close(got["tag-anomaly-scaled"], g["frame_tag-anomaly-scaled"], smax, name="tag-anomaly-scaled")
+    close(got["total-anomaly-scaled"], g["frame_total-anomaly-scaled"].ravel(), smax * np.sqrt(g["frame_total-anomaly-scaled"].max()), name="total-scaled")
+    close(got["total-anomaly-unscaled"], g["frame_total-anomaly-unscaled"].ravel(), np.sqrt(g["frame_total-anomaly-unscaled"].max()), name="total-unscaled")
+    close(got["anomaly-confidence"], g["frame_anomaly-confidence"], float((1 / g["feature_thresholds"]).max()), name="confidence")
+    close(got["total-anomaly-confidence"], g["frame_total-anomaly-confidence"].ravel(),
+          smax * np.sqrt(g["frame_total-anomaly-scaled"].max()) / float(g["aggregate_threshold"]), name="total-confidence")
+
+
+# ------------------------------------------------------------------------------------------------ K7, K5, K4-alone
+def test_minmax_and_thresholds_against_reference_fixture(engine, torch):
+    dev = engine.cuda_device()
+    for case in ("anomaly_plain", "anomaly_smm", "ffnet_anomaly"):
+        g = np.load(os.path.join(GOLDEN, case + ".npz"))
+        y = g["y"].astype(np.float32)
+        n, T = y.shape
+        yd = torch.from_numpy(y).to(dev)
+        # per-fold scalers are fitted on the fold's training rows [0, test_start)
+        starts = [int(g[f"fold{i}_test_start"]) for i in range(3)]
+        jobs_h = engine.make_jobs([0, 1, 2, 3], starts + [n], [0, 0, 0, 0])
+        scale, offset = engine.minmax_fit(engine.jobs_to_device(jobs_h, dev), 4, n, yd, T, 4, dev)
+        scale, offset = scale.cpu().numpy(), offset.cpu().numpy()
+        for i in range(3):
+            close(scale[i], g[f"fold{i}_scale"], rtol=1e-5, mag=0, name="fold scale")
+            close(offset[i], g[f"fold{i}_min"], rtol=1e-5, mag=1e-2, name="fold min_")
+        close(scale[3], g["scale"], rtol=1e-5, mag=0, name="scale_")
+        # thresholds of every fold from the fixture's fold predictions
+        tlen = int(g["fold0_test_len"])
+        pred = np.concatenate([g[f"fold{i}_pred"] for i in range(3)]).astype(np.float32)
+        ytest = np.concatenate([y[starts[i]: starts[i] + tlen] for i in range(3)])
+        jobs_h = engine.make_jobs([0, 1, 2], [tlen] * 3, [0, tlen, 2 * tlen])
+        jd = engine.jobs_to_device(jobs_h, dev)
+        res = engine.anomaly_score(jd, 3, tlen, torch.from_numpy(pred).to(dev), torch.from_numpy(ytest).to(dev), T,
+                                   torch.from_numpy(scale[:3].copy()).to(dev), want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
+        for window, fkey, akey in ((6, "feature_thresholds_per_fold", "aggregate_thresholds_per_fold"),):
+            feat, agg = engine.thresholds(jd, 3, tlen, res["tag-anomaly-unscaled"], res["total-anomaly-scaled"], T, 3, window, dev)
+            close(feat.cpu().numpy(), g[fkey], rtol=2e-5, mag=1e-3, name=f"{case} feature thresholds")
+            close(agg.cpu().numpy(), g[akey], rtol=1e-4, mag=1e-4, name=f"{case} aggregate thresholds")
+        if int(g["window"]) > 0:
+            feat, agg = engine.thresholds(jd, 3, tlen, res["tag-anomaly-unscaled"], res["total-anomaly-scaled"], T, 3, int(g["window"]), dev)
+            close(feat.cpu().numpy()[2], g["smooth_feature_thresholds"], rtol=2e-5, mag=1e-3, name="smooth feature thresholds")
+            close(agg.cpu().numpy()[2], g["smooth_aggregate_threshold"], rtol=1e-4, mag=1e-4, name="smooth aggregate threshold")
+
+
+def test_thresholds_edge_cases(engine, torch):
+    from oracle import anomaly_math as am
+
+    dev = engine.cuda_device()
+    rng = np.random.default_rng(5)
+    T = 7
+    # three jobs: long (crosses the 1024-row chunk), exactly the window, shorter than the window (-> NaN)
+    lens = [2300, 6, 4]
+    tu = rng.random((sum(lens), T)).astype(np.float32)
+    ts = rng.random(sum(lens)).astype(np.float32)
+    starts = np.cumsum([0] + lens[:-1])
+    jobs = engine.make_jobs([0, 1, 2], lens, starts)
+    feat, agg = engine.thresholds(engine.jobs_to_device(jobs, dev), 3, max(lens), torch.from_numpy(tu).to(dev), torch.from_numpy(ts).to(dev), T, 3, 6, dev)
+    feat, agg = feat.cpu().numpy(), agg.cpu().numpy()
+    for i, (s, n) in enumerate(zip(starts, lens)):
+        want_f = am.rolling_min_then_max(tu[s:s + n], 6)
+        want_a = am.rolling_min_then_max(ts[s:s + n], 6)
+        np.testing.assert_array_equal(feat[i], want_f.astype(np.float32))  # min/max of float32 values is exact
+        np.testing.assert_array_equal(agg[i], np.float32(want_a))
+    assert np.isnan(feat[2]).all() and np.isnan(agg[2])
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("T,batch", [(8, 32), (64, 32), (10, 7)])
+def test_ffae_fit_matches_oracle_adam(engine, torch, T, batch):
+    """Same initial weights + same visiting order => same weights/loss as the oracle's Keras-style Adam loop."""
+    from oracle import keras_math as km
+
+    M, N, E = 3, 150, 2
+    spec = km.ff_hourglass_spec(T)
+    rng = np.random.default_rng(T)
+    t = np.linspace(0, 12, N)[:, None]
+    datas = [(0.5 + 0.35 * np.sin(t * rng.uniform(0.5, 2, T) + rng.uniform(0, 3, T)) + rng.normal(0, 0.02, (N, T))).astype(np.float32) for _ in range(M)]
+    X = np.concatenate(datas)
+    w0 = [km.init_ff_weights(spec, np.random.default_rng(50 + m)) for m in range(M)]
+    perm = np.stack([[np.random.default_rng(1000 * m + e).permutation(N) for e in range(E)] for m in range(M)]).astype(np.int32)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    params = eng.pack_params(w0)
+    xd = torch.from_numpy(X).to(dev)
+    jobs = engine.jobs_to_device(engine.uniform_jobs(M, N), dev)
+    loss, acc, _ = eng.fit(params, jobs, M, N, xd, xd.clone(), epochs=E, batch_size=batch, perm=torch.from_numpy(perm).to(dev))
+    torch.cuda.synchronize()
+    got = eng.unpack_params(params)
+    loss, acc = loss.cpu().numpy(), acc.cpu().numpy()
+    for m in range(M):
+        w_ref, hist, _ = km.ff_fit(spec, w0[m], datas[m], datas[m], epochs=E, batch_size=batch, perms=list(perm[m]))
+        for l, ((Wg, bg), (Wr, br)) in enumerate(zip(got[m], w_ref)):
+            # weights moved by ~lr*steps = 1e-2; agreement to 1e-4 of the weight scale after 2 epochs of fp32 Adam
+            close(Wg, Wr, mag=float(np.abs(Wr).max()), name=f"W{l}")
+            close(bg, br, mag=max(float(np.abs(br).max()), 1e-2), name=f"b{l}")
+        close(loss[m], np.array(hist["loss"]), mag=0.0, rtol=5e-4, name="loss history")
+        close(acc[m], np.array(hist["accuracy"]), mag=2.0 / N, rtol=0, name="accuracy history")
+    assert (loss[:, -1] < loss[:, 0]).all()
+
+
+def test_ffae_fit_shuffle_modes_and_reproducibility(engine, torch):
+    from oracle import keras_math as km
+
+    T, N = 8, 200
+    spec = km.ff_hourglass_spec(T)
+    X = np.random.default_rng(0).random((N, T)).astype(np.float32)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    xd = torch.from_numpy(X).to(dev)
+    jobs = engine.jobs_to_device(engine.uniform_jobs(1, N), dev)
+    w0 = km.init_ff_weights(spec, np.random.default_rng(1))
+
+    def run(shuffle, seed):
+        p = eng.pack_params([w0])
+        loss, _, _ = eng.fit(p, jobs, 1, N, xd, xd, epochs=3, batch_size=32, shuffle=shuffle, seed=seed)
+        torch.cuda.synchronize()
+        return p.cpu().numpy(), loss.cpu().numpy()
+
+    a, la = run(True, 7)
+    b, lb = run(True, 7)
+    c, _ = run(True, 8)
+    np.testing.assert_array_equal(a, b)  # same seed -> bit-identical fit
+    assert np.abs(a - c).max() > 0  # different visiting order
+    # shuffle=False equals the oracle with the identity order
+    d, ld = run(False, 0)
+    w_ref, hist, _ = km.ff_fit(spec, w0, X, X, epochs=3, batch_size=32, shuffle=False)
+    close(ld[0], np.array(hist["loss"]), mag=0, rtol=5e-4, name="loss")
+    assert np.isfinite(la).all() and la[0, -1] < la[0, 0]
+
+
+# ------------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("F,units,lookback", [(3, [4, 3, 3, 4], 3), (10, [8, 7, 5, 5, 7, 8], 12), (128, [256, 128, 64, 64, 128, 256], 20)])
+def test_lstm_infer_matches_oracle(engine, torch, F, units, lookback):
+    from oracle import keras_math as km
+
+    spec = km.LSTMSpec(F, units, ["tanh"] * len(units), F, "linear", lookback)
+    M, N = 2, lookback + 37
+    ws = [km.init_lstm_weights(spec, np.random.default_rng(20 + m)) for m in range(M)]
+    X = np.random.default_rng(3).random((M * N, F)).astype(np.float32)
+    eng = engine.LSTMEngine(F, units, spec.acts, F, "linear", lookback)
+    dev = eng.device
+    nwin = N - lookback + 1
+    jobs_h = engine.make_jobs([0, 1], [nwin, nwin], [0, N], [0, nwin])
+    out = eng.infer(eng.pack_params(ws), engine.jobs_to_device(jobs_h, dev), 2, nwin, torch.from_numpy(X).to(dev), 2 * nwin)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for m in range(M):
+        want = km.lstm_predict(spec, ws[m], X[m * N:(m + 1) * N], dtype=np.float64)
+        assert want.shape == (nwin, F)
+        close(out[m * nwin:(m + 1) * nwin], want, 1.0, name="lstm output")
+
+
+# ------------------------------------------------------------------------------------------------ estimator API end to end
+def test_detector_end_to_end_like_reference_tests(engine, torch):
+    """tests/gordo/machine/model/anomaly/test_anomaly_detectors.py:28-120 with our KerasAutoEncoder as base estimator."""
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_components_b200.machine.model.models import KerasAutoEncoder
+    from oracle import anomaly_math as am
+    from oracle import keras_math as km
+
+    np.random.seed(0)
+    n, T = 400, 8
+    idx = pd.date_range("2019-01-01", periods=n, freq="10min", tz="UTC")
+    t = np.linspace(0, 30, n)[:, None]
+    Xv = 0.5 + 0.4 * np.sin(t * np.linspace(0.5, 2, T)) + np.random.normal(0, 0.02, (n, T))
+    cols = [f"tag-{i}" for i in range(T)]
+    X = pd.DataFrame(Xv, columns=cols, index=idx)
+    y = X.copy()
+    model = DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass", epochs=3, batch_size=32))
+    with pytest.raises(AttributeError):
+        model.fit(X, y).anomaly(X, y)
+    cvo = model.cross_validate(X=X, y=y)
+    assert {"fit_time", "score_time", "estimator", "test_score"} <= set(cvo)
+    assert len(model.feature_thresholds_) == T and model.feature_thresholds_per_fold_.shape == (3, T)
+    assert list(model.aggregate_thresholds_per_fold_) == ["fold-0", "fold-1", "fold-2"]
+    model.fit(X, y)
+    frame = model.anomaly(X, y, frequency=pd.Timedelta("10min"))
+    level0 = list(dict.fromkeys(frame.columns.get_level_values(0)))
+    assert level0 == ["start", "end", "model-input", "model-output", "tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled",
+                      "total-anomaly-unscaled", "anomaly-confidence", "total-anomaly-confidence"]
+    # the frame equals the oracle's arithmetic applied to the oracle's forward of the trained weights
+    ae = model.base_estimator
+    spec = km.ff_hourglass_spec(T)
+    pred = km.ff_forward(spec, ae.model.weights, Xv, np.float64)
+    close(model.predict(X), pred, name="predict")
+    sc, mn = am.minmax_fit(Xv)
+    close(model.scaler.scale_, sc, rtol=1e-5, mag=0, name="scaler")
+    want = am.anomaly_arrays(pred, Xv, sc, mn, model.feature_thresholds_.values, model.aggregate_threshold_)
+    close(frame["model-output"].values, pred, name="model-output")
+    close(frame["tag-anomaly-unscaled"].values, want["tag-anomaly-unscaled"], name="tag-anomaly-unscaled")
+    close(frame["tag-anomaly-scaled"].values, want["tag-anomaly-scaled"], float(sc.max()), name="tag-anomaly-scaled")
+    close(frame["anomaly-confidence"].values, want["anomaly-confidence"], float((1 / model.feature_thresholds_.values).max()), name="confidence")
+    # thresholds re-derived by the oracle from the fold models the detector trained
+    for i, ((tr, te), fold) in enumerate(zip(am.time_series_split(n, 3), cvo["estimator"])):
+        fpred = km.ff_forward(spec, fold.base_estimator.model.weights, Xv[te], np.float64)
+        fs, fm = am.minmax_fit(Xv[tr])
+        ft, at = am.fold_thresholds(Xv[te], fpred, fs, fm, 6)
+        close(model.feature_thresholds_per_fold_.values[i], ft, rtol=1e-3, mag=1e-4, name="fold feature thresholds")
+        close(model.aggregate_thresholds_per_fold_[f"fold-{i}"], at, rtol=1e-3, mag=1e-5, name="fold aggregate threshold")
+    md = model.get_metadata()
+    assert {"feature-thresholds", "aggregate-threshold", "feature-thresholds-per-fold", "aggregate-thresholds-per-fold", "history"} <= set(md)
+    assert {"loss", "accuracy", "params"} <= set(md["history"]) and len(md["history"]["loss"]) == 3
+    # pickle round trip: identical predictions, history preserved (test_model.py:112-158)
+    import pickle
+
+    clone_ = pickle.loads(pickle.dumps(model))
+    np.testing.assert_array_equal(clone_.predict(X), model.predict(X))
+    assert clone_.base_estimator._history.history["loss"] == ae._history.history["loss"]
+
+
+def test_detector_with_foreign_base_estimator(engine, torch):
+    """The reference's detector tests drive it with sklearn regressors; the anomaly arithmetic still runs on the GPU."""
+    from sklearn.linear_model import LinearRegression
+    from sklearn.multioutput import MultiOutputRegressor
+    from sklearn.preprocessing import RobustScaler
+
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+
+    g = np.load(os.path.join(GOLDEN, "anomaly_plain.npz"))
+    X, y = pd.DataFrame(g["X"]), pd.DataFrame(g["y"])
+    model = DiffBasedAnomalyDetector(base_estimator=MultiOutputRegressor(LinearRegression()))
+    model.cross_validate(X=X, y=y)
+    model.fit(X, y)
+    frame = model.anomaly(X, y)
+    close(model.feature_thresholds_.values, g["feature_thresholds"], rtol=1e-4, mag=1e-4, name="feature thresholds")
+    close(model.aggregate_threshold_, g["aggregate_threshold"], rtol=1e-4, mag=1e-5, name="aggregate threshold")
+    for top in ("model-output", "tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-unscaled",
+                "anomaly-confidence", "total-anomaly-confidence"):
+        want = g[f"frame_{top}"]
+        got = frame[top].values
+        close(got.reshape(want.shape), want, float(np.abs(want).max()), name=top)
+    # RobustScaler (reference test parametrisation): slope = 1/scale_
+    m2 = DiffBasedAnomalyDetector(base_estimator=MultiOutputRegressor(LinearRegression()), scaler=RobustScaler(), require_thresholds=False)
+    f2 = m2.fit(X, y).anomaly(X, y)
+    want = np.abs(m2.scaler.transform(m2.predict(X)) - m2.scaler.transform(y))
+    close(f2["tag-anomaly-scaled"].values, want, float(np.abs(want).max()), name="robust scaled")
+    assert "anomaly-confidence" not in f2.columns
+
+
+def test_estimator_validation_split_and_score(engine, torch):
+    from gordo_components_b200.machine.model.models import KerasAutoEncoder
+
+    np.random.seed(1)
+    X = np.random.random((300, 4))
+    m = KerasAutoEncoder(kind="feedforward_hourglass", epochs=2, validation_split=0.2)
+    m.fit(X, X)
+    h = m.get_metadata()["history"]
+    assert len(h["loss"]) == 2 and len(h["val_loss"]) == 2 and h["params"]["steps"] == 8
+    assert m.predict(X).shape == (300, 4) and m.predict(X).dtype == np.float32
+    assert isinstance(m.score(X, X), float)
+    # seeded numpy => reproducible build (tests/gordo/builder/test_builder.py:658-707)
+    np.random.seed(3)
+    a = KerasAutoEncoder(kind="feedforward_hourglass", epochs=1).fit(X, X).predict(X)
+    np.random.seed(3)
+    b = KerasAutoEncoder(kind="feedforward_hourglass", epochs=1).fit(X, X).predict(X)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_lstm_estimator_predict_shapes(engine, torch):
+    """tests/gordo/machine/model/test_model.py:324-338 and tests/gordo/builder/test_builder.py:99-115 (offsets)."""
+    from gordo_components_b200.machine.model.models import KerasLSTMAutoEncoder, KerasLSTMForecast
+
+    np.random.seed(0)
+    m = KerasLSTMAutoEncoder(kind="lstm_model", lookback_window=3).initialize(3)
+    assert m.predict(np.random.random((4, 3))).shape == (2, 3)
+    f = KerasLSTMForecast(kind="lstm_hourglass", lookback_window=10).initialize(5)
+    X = np.random.random((40, 5))
+    assert len(X) - len(f.predict(X)) == 10
+    a = KerasLSTMAutoEncoder(kind="lstm_hourglass", lookback_window=10).initialize(5)
+    assert len(X) - len(a.predict(X)) == 9
+    with pytest.raises(ValueError):
+        a.predict(np.random.random((10, 5)))
+    with pytest.raises(NotImplementedError):
+        a.fit(X, X)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-size properties
+def test_full_size_properties(engine, torch):
+    """
+    configs[1] size (1000 machines x 64 tags x 10000 rows): too big for the oracle, so check size-independent
+    properties -- internal consistency of the fused outputs, idempotence, job-order invariance -- plus oracle
+    parity on a random sample of (machine, row-block) pairs.
+    """
+    from oracle import keras_math as km
+
+    M, R, T = 1000, 10000, 64
+    spec = km.ff_hourglass_spec(T)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand((M * R, T), generator=g, device=dev)
+    y = x + 0.05 * torch.randn((M * R, T), generator=g, device=dev)
+    lim = [np.sqrt(6.0 / (i + o)) for i, o in zip(spec.dims[:-1], spec.dims[1:])]
+    params = torch.zeros((M, eng.param_stride), device=dev)
+    ofs = 0
+    for (i, o), l in zip(zip(spec.dims[:-1], spec.dims[1:]), lim):
+        params[:, ofs:ofs + i * o] = (torch.rand((M, i * o), generator=g, device=dev) * 2 - 1) * l
+        ofs += i * o
+        params[:, ofs:ofs + o] = (torch.rand((M, o), generator=g, device=dev) * 2 - 1) * 0.1
+        ofs += o
+    jobs_h = engine.uniform_jobs(M, R)
+    jobs = engine.jobs_to_device(jobs_h, dev)
+    scale, _ = eng.minmax_fit(jobs, M, R, y, M)
+    feat = torch.rand((M, T), generator=g, device=dev) * 0.2 + 0.05
+    agg = torch.rand((M,), generator=g, device=dev) * 0.1 + 0.01
+    res = eng.infer_score(params, jobs, M, R, x, y, scale, feat, agg)
+    torch.cuda.synchronize()
+    out, tu, ts = res["model-output"], res["tag-anomaly-unscaled"], res["tag-anomaly-scaled"]
+    sc_rows = scale.repeat_interleave(R, dim=0)
+    assert torch.equal(tu, (out - y).abs())
+    assert torch.equal(ts, tu * sc_rows)
+    assert torch.allclose(res["total-anomaly-unscaled"], (tu * tu).mean(dim=1), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(res["total-anomaly-scaled"], (ts * ts).mean(dim=1), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(res["anomaly-confidence"], tu / feat.repeat_interleave(R, dim=0), rtol=1e-6)
+    assert torch.allclose(res["total-anomaly-confidence"], res["total-anomaly-scaled"] / agg.repeat_interleave(R), rtol=1e-6)
+    assert bool(torch.isfinite(out).all())
+    checksum = out.double().sum().item()
+    del sc_rows
+    # idempotent + independent of job order
+    perm = np.random.default_rng(0).permutation(M)
+    res2 = eng.infer_score(params, engine.jobs_to_device(jobs_h[perm], dev), M, R, x, y, scale, feat, agg, want=())
+    torch.cuda.synchronize()
+    assert torch.equal(res2["model-output"], out)
+    assert res2["model-output"].double().sum().item() == checksum
+    # oracle parity on sampled blocks
+    rng = np.random.default_rng(1)
+    host_params = params.cpu().numpy()
+    for m in rng.choice(M, 6, replace=False):
+        r0 = int(rng.integers(0, R - 200))
+        w, o = [], 0
+        for i, oo in zip(spec.dims[:-1], spec.dims[1:]):
+            W = host_params[m, o:o + i * oo].reshape(i, oo); o += i * oo
+            b = host_params[m, o:o + oo]; o += oo
+            w.append((W, b))
+        rows = slice(m * R + r0, m * R + r0 + 200)
+        want = km.ff_forward(spec, w, x[rows].cpu().numpy(), np.float64)
+        close(out[rows].cpu().numpy(), want, name="sampled block")
+    # min-max scaler statistics at full size: exact reductions
+    ymin = y.view(M, R, T).amin(dim=1)
+    ymax = y.view(M, R, T).amax(dim=1)
+    assert torch.allclose(scale, 1.0 / (ymax - ymin), rtol=1e-6)
