@@ -73,7 +73,7 @@ def _declare(lib):
         getattr(lib, name).argtypes = [C.POINTER(GbLstmNet)]
     lib.gb_lstm_workspace_bytes.restype = C.c_size_t
     lib.gb_lstm_workspace_bytes.argtypes = [C.POINTER(GbLstmNet), C.c_int32, C.c_int32]
-    lib.gb_ffae_infer_score.argtypes = [C.POINTER(GbFFNet), _P, _P, C.c_int32, C.c_int32] + [_P] * 12 + [C.c_int32, _P]
+    lib.gb_ffae_infer_score.argtypes = [C.POINTER(GbFFNet), _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64] + [_P] * 12 + [C.c_int32, _P]
     lib.gb_ffae_tc_supported.argtypes = [C.POINTER(GbFFNet)]
     lib.gb_ffae_tc_supported.restype = C.c_int
     lib.gb_anomaly_score.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, C.c_int32] + [_P] * 9 + [_P]

@@ -84,13 +84,13 @@ size_t gb_ffnet_param_stride(const gb_ffnet* net) { return (gb_ffnet_param_count
 int gb_ffae_infer_score_fma(const gb_ffnet*, const float*, const gb_job*, int32_t, int32_t, const float*, const float*,
                             const float*, const float*, const float*, float*, float*, float*, float*, float*, float*,
                             float*, void*);
-int gb_ffae_infer_score_tc(const gb_ffnet*, const float*, const gb_job*, int32_t, int32_t, const float*, const float*,
-                           const float*, const float*, const float*, float*, float*, float*, float*, float*, float*,
-                           float*, void*);
+int gb_ffae_infer_score_tc(const gb_ffnet*, const float*, const gb_job*, int32_t, int32_t, int64_t, int64_t, const float*,
+                           const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*,
+                           float*, float*, int32_t, void*);
 int gb_ffae_tc_supported(const gb_ffnet*);
 
 int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* jobs, int32_t n_jobs, int32_t max_rows,
-                        const float* x, const float* y, const float* scale, const float* feat_thr,
+                        int64_t n_x_rows, int64_t n_out_rows, const float* x, const float* y, const float* scale, const float* feat_thr,
                         const float* agg_thr, float* out_model, float* out_tag_scaled, float* out_tag_unscaled,
                         float* out_total_scaled, float* out_total_unscaled, float* out_conf, float* out_total_conf,
                         int32_t variant, void* stream) {
@@ -98,6 +98,8 @@ int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* 
   if (rc != GB_OK) return rc;
   GB_REQUIRE(params && jobs && x && out_model, GB_E_ARG, "params/jobs/x/out_model must be non-NULL");
   GB_REQUIRE(n_jobs >= 0 && max_rows >= 0, GB_E_ARG, "negative n_jobs/max_rows");
+  const int32_t tc_flags = variant >> 8;
+  variant &= 0xff;
   GB_REQUIRE(variant >= 0 && variant <= 2, GB_E_ARG, "variant=%d unknown", variant);
   if (y == nullptr)
     GB_REQUIRE(!out_tag_scaled && !out_tag_unscaled && !out_total_scaled && !out_total_unscaled && !out_conf &&
@@ -114,9 +116,9 @@ int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* 
   bool tc_ok = gb_ffae_tc_supported(net) == GB_OK;
   if (variant == 2 && !tc_ok) return GB_E_SHAPE;
   if (variant == 2 || (variant == 0 && tc_ok))
-    return gb_ffae_infer_score_tc(net, params, jobs, n_jobs, max_rows, x, y, scale, feat_thr, agg_thr, out_model,
-                                  out_tag_scaled, out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf,
-                                  out_total_conf, stream);
+    return gb_ffae_infer_score_tc(net, params, jobs, n_jobs, max_rows, n_x_rows, n_out_rows, x, y, scale, feat_thr, agg_thr,
+                                  out_model, out_tag_scaled, out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf,
+                                  out_total_conf, tc_flags, stream);
   return gb_ffae_infer_score_fma(net, params, jobs, n_jobs, max_rows, x, y, scale, feat_thr, agg_thr, out_model,
                                  out_tag_scaled, out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf,
                                  out_total_conf, stream);

@@ -152,7 +152,7 @@ class FFEngine:
         o_totc = g("total-anomaly-confidence", (total,))
         p = _cabi.ptr
         _cabi.check(self.lib.gb_ffae_infer_score(
-            C.byref(self.net), p(params), p(jobs_dev), int(n_jobs), int(max_rows), p(x), p(y), p(scale), p(feat_thr), p(agg_thr),
+            C.byref(self.net), p(params), p(jobs_dev), int(n_jobs), int(max_rows), int(x.shape[0]), total, p(x), p(y), p(scale), p(feat_thr), p(agg_thr),
             p(o_model), p(o_ts), p(o_tu), p(o_tots), p(o_totu), p(o_conf), p(o_totc), int(variant), _stream_ptr()))
         return res
 

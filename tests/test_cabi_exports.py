@@ -52,7 +52,7 @@ def test_param_counts_match_survey(lib):
 
 def test_argument_validation_needs_no_gpu(lib):
     net = _cabi.make_ffnet([4, 3, 4], ["tanh", "linear"])
-    rc = lib.gb_ffae_infer_score(C.byref(net), None, None, 1, 10, None, None, None, None, None, None, None, None, None, None, None, None, 0, None)
+    rc = lib.gb_ffae_infer_score(C.byref(net), None, None, 1, 10, 10, 10, None, None, None, None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"non-NULL" in lib.gb_last_error()
     with pytest.raises(ValueError):
         _cabi.check(rc)
