@@ -159,7 +159,7 @@ def test_minmax_and_thresholds_against_reference_fixture(engine, torch):
     dev = engine.cuda_device()
     for case in ("anomaly_plain", "anomaly_smm", "ffnet_anomaly"):
         g = np.load(os.path.join(GOLDEN, case + ".npz"))
-        y = g["y"].astype(np.float32)
+        y = np.ascontiguousarray(g["y"], dtype=np.float32)  # DataFrame.values saved by the generator is F-ordered
         n, T = y.shape
         yd = torch.from_numpy(y).to(dev)
         # per-fold scalers are fitted on the fold's training rows [0, test_start)
@@ -173,8 +173,8 @@ def test_minmax_and_thresholds_against_reference_fixture(engine, torch):
         close(scale[3], g["scale"], rtol=1e-5, mag=0, name="scale_")
         # thresholds of every fold from the fixture's fold predictions
         tlen = int(g["fold0_test_len"])
-        pred = np.concatenate([g[f"fold{i}_pred"] for i in range(3)]).astype(np.float32)
-        ytest = np.concatenate([y[starts[i]: starts[i] + tlen] for i in range(3)])
+        pred = np.ascontiguousarray(np.concatenate([g[f"fold{i}_pred"] for i in range(3)]), dtype=np.float32)
+        ytest = np.ascontiguousarray(np.concatenate([y[starts[i]: starts[i] + tlen] for i in range(3)]))
         jobs_h = engine.make_jobs([0, 1, 2], [tlen] * 3, [0, tlen, 2 * tlen])
         jd = engine.jobs_to_device(jobs_h, dev)
         res = engine.anomaly_score(jd, 3, tlen, torch.from_numpy(pred).to(dev), torch.from_numpy(ytest).to(dev), T,
