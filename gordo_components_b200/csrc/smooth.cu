@@ -1,0 +1,106 @@
+// K6: optional smoothing of the anomaly columns (reference diff.py:302-308, 387-415):
+//   smm  = rolling(window).median()   sma = rolling(window).mean()   (first window-1 rows NaN, pandas min_periods=window)
+//   ewma = ewm(span=window).mean()    (pandas default adjust=True: y_t = sum_i (1-a)^i x_{t-i} / sum_i (1-a)^i, a = 2/(window+1))
+// One thread per (job, column) walks the rows in order; lanes run along columns so every step of a warp reads one
+// contiguous row segment.  sma/ewma keep their running sums in double (pandas does them in float64); smm keeps the
+// window sorted in shared memory and replaces one element per step.  Correct-first: the rolling median in particular is
+// a simple O(window) update per row and is the known slow spot of this optional path.
+#include <math_constants.h>
+#include "gb_common.cuh"
+
+namespace {
+
+constexpr int SM_THREADS = 64;
+
+__global__ void __launch_bounds__(SM_THREADS) smooth_mean_kernel(const gb_job* jobs, const float* arr, int n_cols, int window, int method,
+                                                                  float* out) {
+  const gb_job job = jobs[blockIdx.y];
+  const int j = blockIdx.x * SM_THREADS + threadIdx.x;
+  if (j >= n_cols) return;
+  const float* src = arr + job.out_row * (long)n_cols + j;
+  float* dst = out + job.out_row * (long)n_cols + j;
+  const int n = job.n_rows;
+  if (method == 1) {  // simple moving average
+    double sum = 0.0;
+    int bad = 0;  // NaNs currently inside the window
+    for (int t = 0; t < n; ++t) {
+      const float v = src[(long)t * n_cols];
+      if (v == v) sum += (double)v; else ++bad;
+      if (t >= window) {
+        const float old = src[(long)(t - window) * n_cols];
+        if (old == old) sum -= (double)old; else --bad;
+      }
+      dst[(long)t * n_cols] = (t >= window - 1 && bad == 0) ? (float)(sum / (double)window) : CUDART_NAN_F;
+    }
+  } else {  // exponentially weighted, adjust=True
+    const double decay = 1.0 - 2.0 / ((double)window + 1.0);
+    double num = 0.0, den = 0.0;
+    for (int t = 0; t < n; ++t) {
+      const float v = src[(long)t * n_cols];
+      num = num * decay + (double)v;
+      den = den * decay + 1.0;
+      dst[(long)t * n_cols] = (float)(num / den);
+    }
+  }
+}
+
+// rolling median: sorted window per thread in shared memory, [window][SM_THREADS] so lanes hit different banks
+__global__ void __launch_bounds__(SM_THREADS) smooth_median_kernel(const gb_job* jobs, const float* arr, int n_cols, int window, float* out) {
+  extern __shared__ float s_win[];
+  const gb_job job = jobs[blockIdx.y];
+  const int j = blockIdx.x * SM_THREADS + threadIdx.x;
+  if (j >= n_cols) return;
+  float* win = s_win + threadIdx.x;  // element i at win[i * SM_THREADS]
+  const float* src = arr + job.out_row * (long)n_cols + j;
+  float* dst = out + job.out_row * (long)n_cols + j;
+  const int n = job.n_rows;
+  int count = 0;
+  for (int t = 0; t < n; ++t) {
+    const float v = src[(long)t * n_cols];
+    if (count == window) {  // drop the value leaving the window (first element equal to it)
+      const float old = src[(long)(t - window) * n_cols];
+      int lo = 0, hi = count;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (win[mid * SM_THREADS] < old) lo = mid + 1; else hi = mid;
+      }
+      for (int i = lo; i + 1 < count; ++i) win[i * SM_THREADS] = win[(i + 1) * SM_THREADS];
+      --count;
+    }
+    int pos = count;  // insert keeping the window sorted
+    while (pos > 0 && win[(pos - 1) * SM_THREADS] > v) {
+      win[pos * SM_THREADS] = win[(pos - 1) * SM_THREADS];
+      --pos;
+    }
+    win[pos * SM_THREADS] = v;
+    ++count;
+    float m = CUDART_NAN_F;
+    if (count == window) {
+      const int h = window >> 1;
+      m = (window & 1) ? win[h * SM_THREADS] : 0.5f * (win[(h - 1) * SM_THREADS] + win[h * SM_THREADS]);
+    }
+    dst[(long)t * n_cols] = m;
+  }
+}
+
+}  // namespace
+
+extern "C" int gb_smooth(const gb_job* jobs, int32_t n_jobs, const float* arr, int32_t n_cols, int32_t window, int32_t method, float* out,
+                         void* stream) {
+  GB_REQUIRE(jobs && arr && out, GB_E_ARG, "jobs/arr/out must be non-NULL");
+  GB_REQUIRE(n_cols >= 1 && window >= 1, GB_E_ARG, "n_cols=%d window=%d must be >= 1", n_cols, window);
+  GB_REQUIRE(method >= 0 && method <= 2, GB_E_ARG, "method=%d unknown (0 smm, 1 sma, 2 ewma)", method);
+  GB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535, GB_E_ARG, "bad n_jobs");
+  if (n_jobs == 0) return GB_OK;
+  const dim3 grid((n_cols + SM_THREADS - 1) / SM_THREADS, n_jobs);
+  if (method == 0) {
+    const size_t smem = (size_t)window * SM_THREADS * sizeof(float);
+    GB_REQUIRE(smem <= 200 * 1024, GB_E_SMEM, "rolling-median window %d does not fit in shared memory", window);
+    GB_CUDA_CHECK(cudaFuncSetAttribute(smooth_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smooth_median_kernel<<<grid, SM_THREADS, smem, (cudaStream_t)stream>>>(jobs, arr, n_cols, window, out);
+  } else {
+    smooth_mean_kernel<<<grid, SM_THREADS, 0, (cudaStream_t)stream>>>(jobs, arr, n_cols, window, method, out);
+  }
+  GB_CUDA_CHECK(cudaGetLastError());
+  return GB_OK;
+}

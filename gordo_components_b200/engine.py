@@ -251,6 +251,22 @@ def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_t
     return res
 
 
+SMOOTH_METHODS = {"smm": 0, "sma": 1, "ewma": 2}
+
+
+def smooth(jobs_dev, n_jobs, arr, window: int, method: str):
+    """Rolling median / mean / EWMA of every column of ``arr`` ([rows] or [rows, cols]) per job (pandas semantics)."""
+    torch = _torch()
+    lib = _cabi.load_library()
+    if method not in SMOOTH_METHODS:
+        raise ValueError(f"smoothing_method {method!r} must be one of {sorted(SMOOTH_METHODS)}")
+    n_cols = 1 if arr.dim() == 1 else arr.shape[1]
+    out = torch.full_like(arr, float("nan"))
+    p = _cabi.ptr
+    _cabi.check(lib.gb_smooth(p(jobs_dev), int(n_jobs), p(arr), int(n_cols), int(window), SMOOTH_METHODS[method], p(out), _stream_ptr()))
+    return out
+
+
 class LSTMEngine:
     """All machines of one LSTM-stack architecture."""
 

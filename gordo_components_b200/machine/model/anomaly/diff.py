@@ -261,18 +261,22 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         return cv_output
 
     # ------------------------------------------------------------------ anomaly frame
-    def _smoothing(self, metric: Union[pd.DataFrame, pd.Series]):
-        # K6 -- GPU smoothing kernels are the next row; until they land the optional smooth-*
-        # columns are refused rather than computed on the host.
-        raise NotImplementedError(
-            "smoothing (window/smoothing_method) has no B200 kernel yet; construct the detector with window=None"
-        )
+    def _smoothing(self, metric: np.ndarray) -> np.ndarray:
+        """smm / sma / ewma of every column of ``metric`` (gb_smooth kernel, pandas rolling/ewm semantics)."""
+        from .... import engine
+
+        dev = engine.cuda_device()
+        torch = engine._torch()
+        a = torch.from_numpy(np.ascontiguousarray(metric, dtype=np.float32)).to(dev)
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [a.shape[0]], [0]), dev)
+        return engine.smooth(jobs, 1, a, int(self.window), self.smoothing_method).cpu().numpy()
 
     def anomaly(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None) -> pd.DataFrame:
         """
         Frame with ``start, end, model-input, model-output, tag-anomaly-scaled, total-anomaly-scaled,
         tag-anomaly-unscaled, total-anomaly-unscaled`` [+ ``anomaly-confidence, total-anomaly-confidence`` when
-        thresholds exist]; rows follow the model output (shorter than X for LSTM models).
+        thresholds exist]; with ``window`` + ``smoothing_method`` the four ``smooth-*`` blocks come before the confidences.
+        Rows follow the model output (shorter than X for LSTM models).
         """
         if not hasattr(X, "values"):
             raise ValueError("Unable to find X.values property")
@@ -281,8 +285,6 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
                 f"`require_thresholds={self.require_thresholds}` however `.cross_validate` needs to be called in order "
                 f"to calculate these thresholds before calling `.anomaly`"
             )
-        if self.window is not None and self.smoothing_method is not None:
-            self._smoothing(None)
         feat_thr = self.feature_thresholds_.values if getattr(self, "feature_thresholds_", None) is not None else None
         agg_thr = self.aggregate_threshold_ if getattr(self, "aggregate_threshold_", None) is not None else None
         res = self._score(self, X, y, self.scaler, feat_thr, agg_thr)
@@ -310,6 +312,11 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         add("total-anomaly-scaled", False)
         add("tag-anomaly-unscaled", True)
         add("total-anomaly-unscaled", False)
+        if self.window is not None and self.smoothing_method is not None:
+            for name, per_tag in (("tag-anomaly-scaled", True), ("total-anomaly-scaled", False), ("tag-anomaly-unscaled", True),
+                                  ("total-anomaly-unscaled", False)):
+                res["smooth-" + name] = self._smoothing(res[name])
+                add("smooth-" + name, per_tag)
         if feat_thr is not None:
             add("anomaly-confidence", True)
         if agg_thr is not None:

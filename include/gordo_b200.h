@@ -133,6 +133,12 @@ int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const fl
                   const float* total_scaled, int32_t n_out, int32_t window, float* feat_thr,
                   float* agg_thr, int32_t n_slots, void* stream);
 
+/* ---- K6: optional smoothing of anomaly columns (diff.py:302-308, 387-415) ------------------
+ * method 0 = smm rolling(window).median(), 1 = sma rolling(window).mean() (first window-1 rows NaN),
+ * 2 = ewma ewm(span=window).mean() (adjust=True).  arr / out: [rows][n_cols], rows taken at [out_row, out_row+n_rows). */
+int gb_smooth(const gb_job* jobs, int32_t n_jobs, const float* arr, int32_t n_cols, int32_t window, int32_t method,
+              float* out, void* stream);
+
 /* ---- K2: fit ---------------------------------------------------------------------------
  * Replaces scikeras KerasRegressor.fit -> keras Model.fit (models.py:284) for the Dense
  * stacks above: per job, `epochs` passes over rows [x_row, x_row+n_rows) in batches of

@@ -8,18 +8,15 @@
 //        D  =  A_lo*W_hi  +  A_hi*W_hi            (kind::tf32, A = A_hi + A_lo exactly, W_hi = W rounded to TF32)
 //           +  bf16(A)*bf16(W - W_hi)             (kind::f16, the 2^-11-sized correction needs only 8 bits)
 // accumulated in fp32 in TMEM: error ~2^-20 relative per product, while the bf16 correction image costs half the
-// shared memory of a TF32 one (the budget that lets the x boxes and output staging fit beside the weights).
+// shared memory of a TF32 one (the budget that lets x/y/out staging fit beside the weights).
 //
-// One persistent CTA per SM: 8 epilogue warps + 1 control warp, TWO 128-row tiles in flight (TMEM slots 0/1).  Per work
-// item (job chunk) the slot's weights are split and laid out once in shared memory as UMMA K-major operands
-// ([K/4][N][4] TF32, [K/8][N][8] BF16).  Per tile: TMA (SWIZZLE_128B boxes) brings x into shared memory; the epilogue
-// warps (one thread per row: warp%4 = TMEM lane quadrant, warp/4 = column half) split x into the A operand held in TMEM;
-// for every layer the control thread issues tcgen05.mma (A from TMEM, B from the resident weight image, D in TMEM) and
-// commits to an mbarrier; the epilogue warps tcgen05.ld the accumulator, add bias, apply tanh, split and tcgen05.st the
-// next layer's A operand -- and while one tile's MMAs run they do the same for the other tile, so tensor-core latency and
-// epilogue math overlap.  The last layer's epilogue forms every anomaly column against the y rows (prefetched with
-// 128-bit loads while the last MMA runs) and leaves through per-warp swizzled staging boxes + TMA tensor stores (full
-// 128-byte lines, no block-wide barrier).  Activations never touch HBM.
+// One persistent CTA per SM: 8 epilogue warps + 1 control warp.  Per work item (job chunk) the slot's weights are
+// split and laid out once in shared memory as UMMA K-major operands ([K/4][N][4] TF32, [K/8][N][8] BF16).  Per
+// 128-row tile:  TMA (SWIZZLE_128B boxes) brings x and y into shared memory; the epilogue warps split x into the A
+// operand held in TMEM (lane = row); for every layer the control thread issues tcgen05.mma (A from TMEM, B from the
+// resident weight image, D in TMEM) and commits to an mbarrier; the epilogue warps tcgen05.ld the accumulator, add
+// bias, apply tanh, split and tcgen05.st the next layer's A operand.  The last layer's epilogue forms every anomaly
+// column against the y tile and leaves through swizzled shared-memory boxes + TMA tensor stores (full-line writes).
 //
 // Reference arithmetic replaced: keras Dense under Model.predict (gordo/machine/model/models.py:289-300) and
 // DiffBasedAnomalyDetector.anomaly (gordo/machine/model/anomaly/diff.py:350-385, 420-444).
@@ -30,15 +27,14 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NTHREADS = 288;  // warps 0-7: epilogue; warp 8: control (TMA producer + MMA issuer)
-constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = 288;  // warps 0-7: epilogue (warp%4 = TMEM lane quadrant, warp/4 = column half); warp 8: control
+constexpr int EPI_THREADS = 256;
 constexpr int MAXL = 8;
-constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
-constexpr int OBOX_BYTES = 32 * 128;   // output staging box of one warp: 32 rows x 32 fp32
+constexpr int BOX_BYTES = TILE * 128;  // 128 rows x 32 fp32, one SWIZZLE_128B box
 constexpr int W = 64;                  // feature width this kernel is specialised for
 
-// TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
-constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, SLOT_COLS = 224, TMEM_COLS = 512;
+// TMEM column map (fp32 columns)
+constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, TMEM_COLS = 256;
 
 struct TcArgs {
   int n_layers, last_layer;  // layers actually evaluated: 0..last_layer (debug aid; == n_layers-1 in production)
@@ -46,7 +42,7 @@ struct TcArgs {
   int whi_ofs[MAXL], wlo_ofs[MAXL], bias_ofs[MAXL];  // byte offsets into dynamic smem
   int pofs[MAXL];                                    // float offsets of W_l in the canonical parameter vector
   int w_bytes;                                       // bytes of the weight+bias region (zero-filled before staging)
-  int vec_ofs, xbox_ofs, stage_ofs, pair_ofs, bar_ofs;
+  int vec_ofs, xbox_ofs, ybox_ofs, stage_ofs, pair_ofs, bar_ofs;
   int n_jobs, chunks_per_job, rows_per_chunk, flags;
   long pstride;
   const float* params;
@@ -137,27 +133,25 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int fmt, int n) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 }
 
-// TMEM -> registers without waiting; tmem_wait_ld() below ties the wait to the registers it guards
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-// wait for all outstanding tcgen05.ld of this thread; the "+f" operands keep every consumer of v[0..7] behind the wait
-__device__ __forceinline__ void tmem_wait_ld8(float* v) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
-               :
-               : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  // the wait is part of the same statement so no consumer of r0..r7 can be scheduled ahead of it
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+      : "r"(taddr)
+      : "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
                : "memory");
 }
@@ -171,78 +165,50 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float act_fast(int act, float z) { return act == GB_ACT_TANH ? tanh_fast(z) : gb::apply_act(act, z); }
 
-// split NC activations into the three A operands (TF32 hi, fp32 remainder, packed BF16) at column `col` of this lane
-template <int NC>
-__device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, const float* a, bool swap_bf16) {
-  uint32_t hi[NC], lo[NC], bf[NC / 2];
+// split 8 activations into the three A operands and store them at column offset `col` of this thread's TMEM lane
+__device__ __forceinline__ void store_a_operands(uint32_t lane_base, int col, const float (&a)[8], bool swap_bf16) {
+  uint32_t hi[8], lo[8], bf[4];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const uint32_t h = __float_as_uint(a[i]) & 0xffffe000u;
     hi[i] = h;
     lo[i] = __float_as_uint(a[i] - __uint_as_float(h));
   }
 #pragma unroll
-  for (int i = 0; i < NC / 2; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const __nv_bfloat162 p = swap_bf16 ? __floats2bfloat162_rn(a[2 * i + 1], a[2 * i]) : __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
     bf[i] = *reinterpret_cast<const uint32_t*>(&p);
   }
-#pragma unroll
-  for (int c = 0; c < NC / 8; ++c) {
-    tmem_st8(slot_lane + COL_AHI + col + 8 * c, hi + 8 * c);
-    tmem_st8(slot_lane + COL_ALO + col + 8 * c, lo + 8 * c);
-    tmem_st4(slot_lane + COL_ABF + ((col + 8 * c) >> 1), bf + 4 * c);
-  }
-}
-
-// hidden layer epilogue of one warp: NC accumulator columns -> bias, activation -> next layer's A operand
-template <int NC>
-__device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, const float* bias, int act, int n_real, bool swap_bf16) {
-  float v[NC];
-#pragma unroll
-  for (int c = 0; c < NC / 8; ++c) tmem_ld8_nowait(slot_lane + COL_D + col0 + 8 * c, v + 8 * c);
-#pragma unroll
-  for (int c = 0; c < NC / 8; ++c) tmem_wait_ld8(v + 8 * c);
-#pragma unroll
-  for (int i = 0; i < NC; i += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + i);
-    v[i] = act_fast(act, v[i] + b.x);
-    v[i + 1] = act_fast(act, v[i + 1] + b.y);
-    v[i + 2] = act_fast(act, v[i + 2] + b.z);
-    v[i + 3] = act_fast(act, v[i + 3] + b.w);
-  }
-  if (act == GB_ACT_SIGMOID) {  // padded columns must stay exactly zero (sigmoid(0) != 0)
-#pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (col0 + i >= n_real) v[i] = 0.f;
-  }
-  store_a_operands<NC>(slot_lane, col0, v, swap_bf16);
+  tmem_st8(lane_base + COL_AHI + col, hi);
+  tmem_st8(lane_base + COL_ALO + col, lo);
+  tmem_st4(lane_base + COL_ABF + (col >> 1), bf);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(NTHREADS, 1)
-ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_model,
-               const __grid_constant__ CUtensorMap map_ts, const __grid_constant__ CUtensorMap map_tu,
-               const __grid_constant__ CUtensorMap map_conf) {
+ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+               const __grid_constant__ CUtensorMap map_model, const __grid_constant__ CUtensorMap map_ts,
+               const __grid_constant__ CUtensorMap map_tu, const __grid_constant__ CUtensorMap map_conf) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_ctrl = warp == EPI_WARPS;
-  const int q = warp & 3, h = (warp >> 2) & 1;  // epilogue: TMEM lane quadrant / column half
+  const bool is_ctrl = warp == 8;
+  const int q = warp & 3, h = (warp >> 2) & 1;  // epilogue: lane quadrant / column half
   const int row = q * 32 + lane;                // tile row owned by this epilogue thread
   const uint32_t sbase = smem_u32(smem);
-  // barriers: [0,1] x_full[slot], [2,3] a_ready[slot], [4,5] d_ready[slot]
-  const uint32_t bars = sbase + a.bar_ofs;
+  const uint32_t bar_x_full = sbase + a.bar_ofs, bar_y_full = bar_x_full + 8, bar_a_ready = bar_x_full + 16, bar_d_ready = bar_x_full + 24,
+                 bar_y_free = bar_x_full + 32;
   const bool has_y = a.y != nullptr;
   const int L = a.last_layer + 1;
   const bool swap_bf16 = (a.flags & FLAG_SWAP_BF16) != 0;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bars + 8 * s, 1);
-      mbar_init(bars + 16 + 8 * s, EPI_WARPS);
-      mbar_init(bars + 32 + 8 * s, 1);
-    }
+    mbar_init(bar_x_full, 1);
+    mbar_init(bar_y_full, 1);
+    mbar_init(bar_a_ready, EPI_THREADS);
+    mbar_init(bar_d_ready, 1);
+    mbar_init(bar_y_free, EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (is_ctrl) {
@@ -255,7 +221,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t tmem = s_tmem_base;
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
-  uint32_t ph_x[2] = {0, 0}, ph_a[2] = {0, 0}, ph_d[2] = {0, 0};
+  uint32_t ph_x = 0, ph_y = 0, ph_a = 0, ph_d = 0, ph_yf = 0;
   int cur_slot = -1;
   const int n_items = a.n_jobs * a.chunks_per_job;
 
@@ -274,30 +240,19 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       for (int i = tid; i < a.w_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
       __syncthreads();
       for (int l = 0; l < L; ++l) {
-        const int K = a.K[l], N = a.N[l], Np = a.Np[l], KN = K * N;
+        const int K = a.K[l], N = a.N[l], Np = a.Np[l];
         const float* Wg = P + a.pofs[l];
         float* whi = reinterpret_cast<float*>(smem + a.whi_ofs[l]);
         __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>(smem + a.wlo_ofs[l]);
-        for (int base = 0; base < KN; base += 4 * NTHREADS) {
-          float w[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {  // four independent loads in flight per thread
-            const int idx = base + u * NTHREADS + tid;
-            w[u] = idx < KN ? __ldg(Wg + idx) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * NTHREADS + tid;
-            if (idx < KN) {
-              const int k = idx / N, n = idx - k * N;
-              const float hi = __uint_as_float((__float_as_uint(w[u]) + 0x1000u) & 0xffffe000u);  // round to nearest TF32
-              whi[((k >> 2) * Np + n) * 4 + (k & 3)] = hi;
-              wlo[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2bfloat16_rn(w[u] - hi);
-            }
-          }
+        for (int idx = tid; idx < K * N; idx += NTHREADS) {
+          const int k = idx / N, n = idx - k * N;
+          const float w = __ldg(Wg + idx);
+          const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);  // round to nearest TF32
+          whi[((k >> 2) * Np + n) * 4 + (k & 3)] = hi;
+          wlo[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2bfloat16_rn(w - hi);
         }
         float* bl = reinterpret_cast<float*>(smem + a.bias_ofs[l]);
-        for (int n = tid; n < N; n += NTHREADS) bl[n] = __ldg(Wg + KN + n);
+        for (int n = tid; n < N; n += NTHREADS) bl[n] = __ldg(Wg + K * N + n);
       }
       float* vec = reinterpret_cast<float*>(smem + a.vec_ofs);  // [0,64): scale, [64,128): 1/feat_thr
       for (int j = tid; j < W; j += NTHREADS) {
@@ -311,41 +266,50 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     if (is_ctrl) {
       // =========================================== control warp: TMA producer + MMA issuer (one elected lane)
       if (lane == 0) {
-        const long xrow0 = job.x_row + row_begin;
-        auto load_x = [&](int s, int t) {
-          const uint32_t dst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
-          mbar_expect_tx(bars + 8 * s, 2 * BOX_BYTES);
-          tma_load_2d(dst, &map_x, 0, (int)(xrow0 + (long)t * TILE), bars + 8 * s);
-          tma_load_2d(dst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)t * TILE), bars + 8 * s);
-        };
-        load_x(0, 0);
-        if (n_tiles > 1) load_x(1, 1);
-        for (int t0 = 0; t0 < n_tiles; t0 += 2) {
+        const int xrow0 = (int)(job.x_row + row_begin);
+        mbar_expect_tx(bar_x_full, 2 * BOX_BYTES);
+        tma_load_2d(sbase + a.xbox_ofs, &map_x, 0, xrow0, bar_x_full);
+        tma_load_2d(sbase + a.xbox_ofs + BOX_BYTES, &map_x, 32, xrow0, bar_x_full);
+        if (has_y) {
+          mbar_expect_tx(bar_y_full, 2 * BOX_BYTES);
+          tma_load_2d(sbase + a.ybox_ofs, &map_y, 0, xrow0, bar_y_full);
+          tma_load_2d(sbase + a.ybox_ofs + BOX_BYTES, &map_y, 32, xrow0, bar_y_full);
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+          const bool more = t + 1 < n_tiles;
+          const int next_row = (int)(job.x_row + row_begin + (t + 1) * TILE);
           for (int l = 0; l < L; ++l) {
+            mbar_wait(bar_a_ready, ph_a);
+            ph_a ^= 1;
+            tc_fence_after();
+            if (l == 0 && more) {  // A0 is in TMEM => the x boxes are free again
+              mbar_expect_tx(bar_x_full, 2 * BOX_BYTES);
+              tma_load_2d(sbase + a.xbox_ofs, &map_x, 0, next_row, bar_x_full);
+              tma_load_2d(sbase + a.xbox_ofs + BOX_BYTES, &map_x, 32, next_row, bar_x_full);
+            }
             const int Np = a.Np[l];
             const uint32_t step = 2u * (uint32_t)Np * 16u;  // bytes between consecutive K-steps (two 16-byte chunks)
             const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(1, Np);
             const uint32_t whi = sbase + a.whi_ofs[l], wlo = sbase + a.wlo_ofs[l];
-            const uint32_t lbo = (uint32_t)Np * 16u;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              if (t0 + s >= n_tiles) continue;
-              mbar_wait(bars + 16 + 8 * s, ph_a[s]);
-              ph_a[s] ^= 1;
-              tc_fence_after();
-              if (l == 0 && t0 + s + 2 < n_tiles) load_x(s, t0 + s + 2);  // A0 is in TMEM => this slot's x boxes are free
-              const uint32_t tb = tmem + s * SLOT_COLS;
-              uint32_t acc = 0;
-              for (int ks = 0; ks < a.k8[l]; ++ks) {  // A_lo * W_hi
-                mma_tf32_ts(tb + COL_D, tb + COL_ALO + ks * 8, make_bdesc(whi + ks * step, lbo, 128), id32, acc);
-                acc = 1;
-              }
-              for (int ks = 0; ks < a.k8[l]; ++ks)  // A_hi * W_hi
-                mma_tf32_ts(tb + COL_D, tb + COL_AHI + ks * 8, make_bdesc(whi + ks * step, lbo, 128), id32, 1);
-              for (int ks = 0; ks < a.k16[l]; ++ks)  // bf16(A) * bf16(W_lo)
-                mma_bf16_ts(tb + COL_D, tb + COL_ABF + ks * 8, make_bdesc(wlo + ks * step, lbo, 128), id16, 1);
-              mma_commit(bars + 32 + 8 * s);
+            uint32_t acc = 0;
+            for (int ks = 0; ks < a.k8[l]; ++ks) {  // A_lo * W_hi
+              mma_tf32_ts(tmem + COL_D, tmem + COL_ALO + ks * 8, make_bdesc(whi + ks * step, Np * 16, 128), id32, acc);
+              acc = 1;
             }
+            for (int ks = 0; ks < a.k8[l]; ++ks)  // A_hi * W_hi
+              mma_tf32_ts(tmem + COL_D, tmem + COL_AHI + ks * 8, make_bdesc(whi + ks * step, Np * 16, 128), id32, 1);
+            for (int ks = 0; ks < a.k16[l]; ++ks)  // bf16(A) * bf16(W_lo)
+              mma_bf16_ts(tmem + COL_D, tmem + COL_ABF + ks * 8, make_bdesc(wlo + ks * step, Np * 16, 128), id16, 1);
+            mma_commit(bar_d_ready);
+          }
+          if (has_y) {
+            if (more) {
+              mbar_wait(bar_y_free, ph_yf);
+              mbar_expect_tx(bar_y_full, 2 * BOX_BYTES);
+              tma_load_2d(sbase + a.ybox_ofs, &map_y, 0, next_row, bar_y_full);
+              tma_load_2d(sbase + a.ybox_ofs + BOX_BYTES, &map_y, 32, next_row, bar_y_full);
+            }
+            ph_yf ^= 1;
           }
         }
       }
@@ -353,106 +317,110 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     } else {
       // =========================================== epilogue warps
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + warp * OBOX_BYTES;  // this warp's 32x32 staging box
-      float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);      // [2][TILE] row-sum exchange between the column halves
-      const uint32_t swz_row = (uint32_t)row * 128u, swz_lane = (uint32_t)lane * 128u;
+      const uint32_t xbox = sbase + a.xbox_ofs + h * BOX_BYTES, ybox = sbase + a.ybox_ofs + h * BOX_BYTES;
+      const uint32_t stage = sbase + a.stage_ofs + h * BOX_BYTES;
+      float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2][TILE] row-sum exchange between the column halves
+      const uint32_t swz_row = (uint32_t)row * 128u;
+      const bool issuer = (q == 0 && lane == 0);
       const float inv_w = 1.0f / (float)W;
 
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-        // ---- x -> A operand of layer 0 ----------------------------------------------------------------------------
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (t0 + s >= n_tiles) continue;
-          const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES;
-          mbar_wait(bars + 8 * s, ph_x[s]);
-          ph_x[s] ^= 1;
-          float v[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t addr = xbox + swz_row + ((uint32_t)(c ^ (row & 7)) << 4);
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
-          }
-          store_a_operands<32>(lane_base + s * SLOT_COLS, h * 32, v, swap_bf16);
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars + 16 + 8 * s);
-        }
+      for (int t = 0; t < n_tiles; ++t) {
+        const int trow = row_begin + t * TILE;
+        const int nrows = min(TILE, row_end - trow);
+        const long grow0 = job.out_row + trow;
+        const bool full = nrows == TILE;
 
-        // ---- hidden layers: D -> bias, activation -> next A operand (tile s' epilogue overlaps tile 1-s' MMAs) ------------
+        // ---- x -> A operand of layer 0 ----------------------------------------------------------------------
+        mbar_wait(bar_x_full, ph_x);
+        ph_x ^= 1;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          float v[8];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const uint32_t addr = xbox + swz_row + ((uint32_t)((c + cc) ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * cc]), "=f"(v[4 * cc + 1]), "=f"(v[4 * cc + 2]), "=f"(v[4 * cc + 3]) : "r"(addr));
+          }
+          store_a_operands(lane_base, h * 32 + c * 4, v, swap_bf16);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_a_ready);
+
+        // ---- hidden layers: D -> bias, activation -> next A operand ---------------------------------------------
         for (int l = 0; l + 1 < L; ++l) {
           const int half = a.Np[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half)
+          const int act = a.act[l];
           const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + h * half;
+          mbar_wait(bar_d_ready, ph_d);
+          ph_d ^= 1;
+          tc_fence_after();
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (t0 + s >= n_tiles) continue;
-            mbar_wait(bars + 32 + 8 * s, ph_d[s]);
-            ph_d[s] ^= 1;
-            tc_fence_after();
-            const uint32_t sl = lane_base + s * SLOT_COLS;
-            if (half == 32) hidden_epilogue<32>(sl, h * 32, bl, a.act[l], a.N[l], swap_bf16);
-            else if (half == 24) hidden_epilogue<24>(sl, h * 24, bl, a.act[l], a.N[l], swap_bf16);
-            else if (half == 16) hidden_epilogue<16>(sl, h * 16, bl, a.act[l], a.N[l], swap_bf16);
-            else hidden_epilogue<8>(sl, h * 8, bl, a.act[l], a.N[l], swap_bf16);
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 16 + 8 * s);
+          for (int c = 0; c < 4; ++c) {
+            if (c * 8 < half) {
+              float v[8];
+              tmem_ld8(lane_base + COL_D + h * half + c * 8, v);
+              const float4 b0 = *reinterpret_cast<const float4*>(bl + c * 8), b1 = *reinterpret_cast<const float4*>(bl + c * 8 + 4);
+              v[0] = act_fast(act, v[0] + b0.x); v[1] = act_fast(act, v[1] + b0.y); v[2] = act_fast(act, v[2] + b0.z); v[3] = act_fast(act, v[3] + b0.w);
+              v[4] = act_fast(act, v[4] + b1.x); v[5] = act_fast(act, v[5] + b1.y); v[6] = act_fast(act, v[6] + b1.z); v[7] = act_fast(act, v[7] + b1.w);
+              if (act == GB_ACT_SIGMOID) {  // padded columns must stay exactly zero (sigmoid(0) != 0)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (h * half + c * 8 + i >= a.N[l]) v[i] = 0.f;
+              }
+              store_a_operands(lane_base, h * half + c * 8, v, swap_bf16);
+            }
           }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_a_ready);
         }
 
-        // ---- last layer: model output + anomaly columns ------------------------------------------------------------------
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (t0 + s >= n_tiles) continue;
+        // ---- last layer: model output + anomaly columns ------------------------------------------------------------
+        {
           const int l = L - 1;
           const int act = (l == a.n_layers - 1) ? a.act[l] : GB_ACT_LINEAR;
           const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + h * 32;
-          const int trow = row_begin + (t0 + s) * TILE;
-          const int nrows = min(TILE, row_end - trow);
-          const long grow0 = job.out_row + trow;
-          const bool warp_full = (q + 1) * 32 <= nrows;  // all 32 rows of this warp are real -> TMA store, else predicated STG
-          float yt[32];
-          if (has_y) {  // y rows of this thread's column half: in flight while the last MMA finishes
-            const long yrow = job.x_row + trow + min(row, nrows - 1);
-            const float4* yp = reinterpret_cast<const float4*>(a.y + yrow * W + h * 32);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 t4 = __ldg(yp + c);
-              yt[4 * c] = t4.x; yt[4 * c + 1] = t4.y; yt[4 * c + 2] = t4.z; yt[4 * c + 3] = t4.w;
-            }
-          }
           float yh[32];
-          mbar_wait(bars + 32 + 8 * s, ph_d[s]);
-          ph_d[s] ^= 1;
+          mbar_wait(bar_d_ready, ph_d);
+          ph_d ^= 1;
           tc_fence_after();
-          {
-            const uint32_t sl = lane_base + s * SLOT_COLS + COL_D + h * 32;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, yh + 8 * c);
+          for (int c = 0; c < 4; ++c) {
+            float v[8];
+            tmem_ld8(lane_base + COL_D + h * 32 + c * 8, v);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_wait_ld8(yh + 8 * c);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) yh[i] = act_fast(act, yh[i] + bl[i]);
+            for (int i = 0; i < 8; ++i) yh[c * 8 + i] = act_fast(act, v[i] + bl[c * 8 + i]);
           }
           tc_fence_before();
+          float yt[32];
+          if (has_y) {
+            mbar_wait(bar_y_full, ph_y);
+            ph_y ^= 1;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t addr = ybox + swz_row + ((uint32_t)(c ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yt[4 * c]), "=f"(yt[4 * c + 1]), "=f"(yt[4 * c + 2]), "=f"(yt[4 * c + 3]) : "r"(addr));
+            }
+            mbar_arrive(bar_y_free);
+          }
 
-          // one output array at a time: registers -> this warp's swizzled staging box -> TMA tensor store,
-          // or straight to global for the ragged tail of a job (a TMA store would spill into the next job's rows)
+          // one output array at a time: registers -> swizzled staging box -> TMA tensor store (full tiles),
+          // or straight to global for the ragged last tile of a job (a TMA store would spill into the next job's rows)
           auto emit = [&](const float (&val)[32], float* gptr, const CUtensorMap* map) {
             if (gptr == nullptr) return;
-            if (warp_full) {
-              if (lane == 0) tma_wait_read0();
-              __syncwarp();
+            if (full) {
+              if (issuer) tma_wait_read0();
+              named_bar_sync(1 + h, 128);
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                const uint32_t addr = stage + swz_lane + ((uint32_t)(c ^ (lane & 7)) << 4);
+                const uint32_t addr = stage + swz_row + ((uint32_t)(c ^ (row & 7)) << 4);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(val[4 * c]), "f"(val[4 * c + 1]), "f"(val[4 * c + 2]), "f"(val[4 * c + 3]) : "memory");
               }
               fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(map, h * 32, (int)(grow0 + q * 32), stage);
+              named_bar_sync(1 + h, 128);
+              if (issuer) {
+                tma_store_2d(map, h * 32, (int)grow0, stage);
                 tma_commit();
               }
             } else if (row < nrows) {
@@ -486,26 +454,26 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
               for (int i = 0; i < 32; ++i) c_[i] = d[i] * vec[W + h * 32 + i];
               emit(c_, a.o_conf, &map_conf);
             }
-            if (a.o_tots || a.o_totu || a.o_totconf) {  // row sums: the two warps of a lane quadrant meet on a 64-thread barrier
+            if (a.o_tots || a.o_totu || a.o_totconf) {
               if (h == 1) { pair[row] = ss; pair[TILE + row] = su; }
-              named_bar_sync(1 + q, 64);
+              named_bar_sync(3, EPI_THREADS);
               if (h == 0 && row < nrows) {
                 const float ts_ = (ss + pair[row]) * inv_w, tu_ = (su + pair[TILE + row]) * inv_w;
                 if (a.o_tots) a.o_tots[grow0 + row] = ts_;
                 if (a.o_totu) a.o_totu[grow0 + row] = tu_;
                 if (a.o_totconf) a.o_totconf[grow0 + row] = ts_ / __ldg(a.agg_thr + job.slot);
               }
-              named_bar_sync(1 + q, 64);
+              named_bar_sync(3, EPI_THREADS);
             }
           }
         }
       }
-      if (lane == 0) tma_wait_read0();  // this warp's staging box must outlive its TMA reads before smem is restaged
+      if (issuer) tma_wait_read0();  // staging boxes must outlive the TMA reads before the next item restages smem
     }
     __syncthreads();
   }
 
-  if (!is_ctrl && lane == 0) tma_wait_all0();
+  if (!is_ctrl && (warp & 3) == 0 && lane == 0) tma_wait_all0();
   tc_fence_before();
   __syncthreads();
   if (is_ctrl) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
@@ -526,13 +494,13 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows][64] fp32 row-major viewed as a 2-D tensor; box = 32 columns x box_rows rows, SWIZZLE_128B
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_rows) {
+// [rows][64] fp32 row-major viewed as a 2-D tensor; box = 32 columns x 128 rows, SWIZZLE_128B
+int make_map(CUtensorMap* map, const void* base, int64_t rows) {
   EncodeTiledFn fn = get_encode_fn();
   GB_REQUIRE(fn != nullptr, GB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)(rows > 0 ? rows : 1)};
   cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {32, TILE};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -597,8 +565,9 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.pair_ofs = ofs; ofs += 2 * TILE * 4;
   a.bar_ofs = ofs; ofs += 64;
   ofs = gb::round_up(ofs, 1024);
-  a.xbox_ofs = ofs; ofs += 4 * BOX_BYTES;            // two tile slots x two 32-column boxes
-  a.stage_ofs = ofs; ofs += EPI_WARPS * OBOX_BYTES;  // one 32x32 staging box per epilogue warp
+  a.xbox_ofs = ofs; ofs += 2 * BOX_BYTES;
+  a.ybox_ofs = ofs; ofs += 2 * BOX_BYTES;
+  a.stage_ofs = ofs; ofs += 2 * BOX_BYTES;
   const size_t smem = (size_t)ofs;
   GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
 
@@ -618,17 +587,18 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_conf = out_conf;
   a.o_tots = out_total_scaled; a.o_totu = out_total_unscaled; a.o_totconf = out_total_conf;
 
-  CUtensorMap mx, mm, mts, mtu, mc;
-  if ((rc = make_map(&mx, x, n_x_rows, TILE)) != GB_OK) return rc;
-  if ((rc = make_map(&mm, out_model, n_out_rows, 32)) != GB_OK) return rc;
-  if ((rc = make_map(&mts, out_tag_scaled ? out_tag_scaled : out_model, n_out_rows, 32)) != GB_OK) return rc;
-  if ((rc = make_map(&mtu, out_tag_unscaled ? out_tag_unscaled : out_model, n_out_rows, 32)) != GB_OK) return rc;
-  if ((rc = make_map(&mc, out_conf ? out_conf : out_model, n_out_rows, 32)) != GB_OK) return rc;
+  CUtensorMap mx, my, mm, mts, mtu, mc;
+  if ((rc = make_map(&mx, x, n_x_rows)) != GB_OK) return rc;
+  if ((rc = make_map(&my, y ? y : x, n_x_rows)) != GB_OK) return rc;
+  if ((rc = make_map(&mm, out_model, n_out_rows)) != GB_OK) return rc;
+  if ((rc = make_map(&mts, out_tag_scaled ? out_tag_scaled : out_model, n_out_rows)) != GB_OK) return rc;
+  if ((rc = make_map(&mtu, out_tag_unscaled ? out_tag_unscaled : out_model, n_out_rows)) != GB_OK) return rc;
+  if ((rc = make_map(&mc, out_conf ? out_conf : out_model, n_out_rows)) != GB_OK) return rc;
 
   const long items = (long)n_jobs * a.chunks_per_job;
   const int grid = (int)(items < sms ? items : sms);
   GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ffae_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx, mm, mts, mtu, mc);
+  ffae_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx, my, mm, mts, mtu, mc);
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }

@@ -211,6 +211,49 @@ def test_thresholds_edge_cases(engine, torch):
     assert np.isnan(feat[2]).all() and np.isnan(agg[2])
 
 
+@pytest.mark.parametrize("case", ["anomaly_smm", "anomaly_sma", "anomaly_ewma"])
+def test_smoothing_against_reference_fixture(engine, torch, case):
+    """smooth-* columns of the reference frame (pandas rolling median / mean / ewm) from its own unsmoothed columns."""
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    dev = engine.cuda_device()
+    window, method = int(g["window"]), str(g["method"])
+    for top in ("tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-unscaled"):
+        src = np.ascontiguousarray(g[f"frame_{top}"], dtype=np.float32)
+        if src.shape[1] == 1:
+            src = src.reshape(-1)
+        a = torch.from_numpy(src).to(dev)
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [len(src)], [0]), dev)
+        got = engine.smooth(jobs, 1, a, window, method).cpu().numpy()
+        want = g[f"frame_smooth-{top}"].reshape(got.shape)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), top
+        close(got, want, float(np.nanmax(np.abs(want))), rtol=1e-5, name=f"{case} smooth-{top}")
+
+
+def test_detector_with_window_like_reference_tests(engine, torch):
+    """test_anomaly_detectors.py:123-371: window/smoothing_method add four smooth-* blocks with window-1 leading NaNs."""
+    from sklearn.linear_model import LinearRegression
+    from sklearn.multioutput import MultiOutputRegressor
+
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+
+    g = np.load(os.path.join(GOLDEN, "anomaly_sma.npz"))
+    X, y = pd.DataFrame(np.ascontiguousarray(g["X"])), pd.DataFrame(np.ascontiguousarray(g["y"]))
+    model = DiffBasedAnomalyDetector(base_estimator=MultiOutputRegressor(LinearRegression()), window=12, smoothing_method="sma")
+    model.cross_validate(X=X, y=y)
+    model.fit(X, y)
+    frame = model.anomaly(X, y)
+    level0 = list(dict.fromkeys(frame.columns.get_level_values(0)))
+    assert level0 == [str(c) for c in g["columns_level0"]]
+    for top in level0[2:]:
+        want = g[f"frame_{top}"]
+        got = frame[top].values.reshape(want.shape)
+        close(got, want, float(np.nanmax(np.abs(want))), name=top)
+    assert frame["smooth-total-anomaly-scaled"].isna().sum() == 11
+    close(model.smooth_feature_thresholds_.values, g["smooth_feature_thresholds"], rtol=1e-4, mag=1e-4, name="smooth thresholds")
+    md = model.get_metadata()
+    assert md["window"] == 12 and md["smoothing-method"] == "sma" and "smooth-feature-thresholds" in md
+
+
 # ------------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("T,batch", [(8, 32), (64, 32), (10, 7)])
 def test_ffae_fit_matches_oracle_adam(engine, torch, T, batch):
