@@ -69,7 +69,9 @@ __device__ __forceinline__ void adam_update(float& w, float g, float& m, float& 
                                             float eps) {
   m += (g - m) * omb1;
   v += (g * g - v) * omb2;
-  w -= alpha * m / (sqrtf(v) + eps);
+  float sq;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));  // ~1 ulp, exact 0 at v = 0
+  w -= __fdividef(alpha * m, sq + eps);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
@@ -287,6 +289,12 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
           float* Vl = Vg + a.im.wofs[l];
           for (int bid = tid; bid < nblocks; bid += THREADS) {
             const int kb = bid % kblocks, n0 = (bid / kblocks) << 2, k0 = kb << 2;
+            float4 mq[4], vq[4];  // Adam moments of this block: requested now, consumed after the reduction over the batch rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              mq[i] = *reinterpret_cast<const float4*>(Ml + (k0 + i) * Np + n0);
+              vq[i] = *reinterpret_cast<const float4*>(Vl + (k0 + i) * Np + n0);
+            }
             float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
 #pragma unroll 4
             for (int r = 0; r < BR; ++r) {
@@ -302,8 +310,8 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
             for (int i = 0; i < 4; ++i) {
               const int off = (k0 + i) * Np + n0;
               float4 w = *reinterpret_cast<float4*>(Wl + off);
-              float4 m = *reinterpret_cast<float4*>(Ml + off);
-              float4 v = *reinterpret_cast<float4*>(Vl + off);
+              float4 m = mq[i];
+              float4 v = vq[i];
               adam_update(w.x, gs[i].x, m.x, v.x, alpha, omb1, omb2, eps);
               adam_update(w.y, gs[i].y, m.y, v.y, alpha, omb1, omb2, eps);
               adam_update(w.z, gs[i].z, m.z, v.z, alpha, omb1, omb2, eps);

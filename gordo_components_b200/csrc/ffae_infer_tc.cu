@@ -30,7 +30,7 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NTHREADS = 288;  // warps 0-7: epilogue; warp 8: control (TMA producer + MMA issuer)
+constexpr int NTHREADS = 320;  // warps 0-7: epilogue; warps 8,9: control of tile slot 0 / 1 (TMA producer + MMA issuer)
 constexpr int EPI_WARPS = 8;
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
@@ -162,14 +162,15 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
-// tanh(x) = 1 - 2/(1 + 2^(2x*log2 e)); absolute error ~2e-7 (ex2.approx / rcp.approx are ~1-2 ulp), exact limits at +-inf
-__device__ __forceinline__ float tanh_fast(float x) {
+// tanh(x) = 1 - 2/(1 + 2^(2x*log2 e)); absolute error ~2e-7 (ex2.approx / rcp.approx are ~1-2 ulp), exact limits at +-inf.
+// The argument arrives pre-scaled: t = (z + b) * 2*log2(e) is formed as fma(z, TANH_ARG_SCALE, b*TANH_ARG_SCALE).
+constexpr float TANH_ARG_SCALE = 2.8853900817779268f;
+__device__ __forceinline__ float tanh_from_scaled(float t) {
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return fmaf(-2.0f, r, 1.0f);
 }
-__device__ __forceinline__ float act_fast(int act, float z) { return act == GB_ACT_TANH ? tanh_fast(z) : gb::apply_act(act, z); }
 
 // split NC activations into the three A operands (TF32 hi, fp32 remainder, packed BF16) at column `col` of this lane
 template <int NC>
@@ -195,8 +196,10 @@ __device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, co
 }
 
 // hidden layer epilogue of one warp: NC accumulator columns -> bias, activation -> next layer's A operand
+// (activation is tanh by construction: gb_ffae_tc_supported admits only tanh hidden layers + linear output, so the
+// compiler sees straight-line code and interleaves the NC independent ex2/rcp chains)
 template <int NC>
-__device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, const float* bias, int act, int n_real, bool swap_bf16) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, const float* bias, bool swap_bf16) {
   float v[NC];
 #pragma unroll
   for (int c = 0; c < NC / 8; ++c) tmem_ld8_nowait(slot_lane + COL_D + col0 + 8 * c, v + 8 * c);
@@ -205,15 +208,10 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, co
 #pragma unroll
   for (int i = 0; i < NC; i += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + i);
-    v[i] = act_fast(act, v[i] + b.x);
-    v[i + 1] = act_fast(act, v[i + 1] + b.y);
-    v[i + 2] = act_fast(act, v[i + 2] + b.z);
-    v[i + 3] = act_fast(act, v[i + 3] + b.w);
-  }
-  if (act == GB_ACT_SIGMOID) {  // padded columns must stay exactly zero (sigmoid(0) != 0)
-#pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (col0 + i >= n_real) v[i] = 0.f;
+    v[i] = tanh_from_scaled(fmaf(v[i], TANH_ARG_SCALE, b.x));
+    v[i + 1] = tanh_from_scaled(fmaf(v[i + 1], TANH_ARG_SCALE, b.y));
+    v[i + 2] = tanh_from_scaled(fmaf(v[i + 2], TANH_ARG_SCALE, b.z));
+    v[i + 3] = tanh_from_scaled(fmaf(v[i + 3], TANH_ARG_SCALE, b.w));
   }
   store_a_operands<NC>(slot_lane, col0, v, swap_bf16);
 }
@@ -226,8 +224,9 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem_base;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_ctrl = warp == EPI_WARPS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction (lets the compiler use uniform registers)
+  const bool is_ctrl = warp >= EPI_WARPS;
   const int q = warp & 3, h = (warp >> 2) & 1;  // epilogue: TMEM lane quadrant / column half
   const int row = q * 32 + lane;                // tile row owned by this epilogue thread
   const uint32_t sbase = smem_u32(smem);
@@ -245,14 +244,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (is_ctrl) {
+  if (warp == EPI_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = s_tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem_base, 0);
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
   uint32_t ph_x[2] = {0, 0}, ph_a[2] = {0, 0}, ph_d[2] = {0, 0};
@@ -297,7 +296,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
         float* bl = reinterpret_cast<float*>(smem + a.bias_ofs[l]);
-        for (int n = tid; n < N; n += NTHREADS) bl[n] = __ldg(Wg + KN + n);
+        const float bscale = (l + 1 < L) ? TANH_ARG_SCALE : 1.0f;  // hidden layers: bias folded into the tanh argument scale
+        for (int n = tid; n < N; n += NTHREADS) bl[n] = __ldg(Wg + KN + n) * bscale;
       }
       float* vec = reinterpret_cast<float*>(smem + a.vec_ofs);  // [0,64): scale, [64,128): 1/feat_thr
       for (int j = tid; j < W; j += NTHREADS) {
@@ -309,47 +309,49 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     __syncthreads();
 
     if (is_ctrl) {
-      // =========================================== control warp: TMA producer + MMA issuer (one elected lane)
-      if (lane == 0) {
-        const long xrow0 = job.x_row + row_begin;
-        auto load_x = [&](int s, int t) {
-          const uint32_t dst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
-          mbar_expect_tx(bars + 8 * s, 2 * BOX_BYTES);
-          tma_load_2d(dst, &map_x, 0, (int)(xrow0 + (long)t * TILE), bars + 8 * s);
-          tma_load_2d(dst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)t * TILE), bars + 8 * s);
-        };
-        load_x(0, 0);
-        if (n_tiles > 1) load_x(1, 1);
-        for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-          for (int l = 0; l < L; ++l) {
-            const int Np = a.Np[l];
-            const uint32_t step = 2u * (uint32_t)Np * 16u;  // bytes between consecutive K-steps (two 16-byte chunks)
-            const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(1, Np);
-            const uint32_t whi = sbase + a.whi_ofs[l], wlo = sbase + a.wlo_ofs[l];
-            const uint32_t lbo = (uint32_t)Np * 16u;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              if (t0 + s >= n_tiles) continue;
-              mbar_wait(bars + 16 + 8 * s, ph_a[s]);
-              ph_a[s] ^= 1;
-              tc_fence_after();
-              if (l == 0 && t0 + s + 2 < n_tiles) load_x(s, t0 + s + 2);  // A0 is in TMEM => this slot's x boxes are free
-              const uint32_t tb = tmem + s * SLOT_COLS;
-              uint32_t acc = 0;
-              for (int ks = 0; ks < a.k8[l]; ++ks) {  // A_lo * W_hi
-                mma_tf32_ts(tb + COL_D, tb + COL_ALO + ks * 8, make_bdesc(whi + ks * step, lbo, 128), id32, acc);
-                acc = 1;
-              }
-              for (int ks = 0; ks < a.k8[l]; ++ks)  // A_hi * W_hi
-                mma_tf32_ts(tb + COL_D, tb + COL_AHI + ks * 8, make_bdesc(whi + ks * step, lbo, 128), id32, 1);
-              for (int ks = 0; ks < a.k16[l]; ++ks)  // bf16(A) * bf16(W_lo)
-                mma_bf16_ts(tb + COL_D, tb + COL_ABF + ks * 8, make_bdesc(wlo + ks * step, lbo, 128), id16, 1);
-              mma_commit(bars + 32 + 8 * s);
+      // =========================================== control warp of tile slot s: TMA producer + MMA issuer.
+      // The whole warp walks the (warp-uniform) control flow; one elected lane issues the asynchronous instructions.
+      const int s = warp - EPI_WARPS;
+      const bool leader = lane == 0;
+      const long xrow0 = job.x_row + row_begin;
+      const uint32_t bar_x = bars + 8 * s, bar_a = bars + 16 + 8 * s, bar_d = bars + 32 + 8 * s;
+      const uint32_t xdst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
+      const uint32_t tb = tmem + s * SLOT_COLS;
+      if (s < n_tiles && leader) {
+        mbar_expect_tx(bar_x, 2 * BOX_BYTES);
+        tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)s * TILE), bar_x);
+        tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)s * TILE), bar_x);
+      }
+      for (int t = s; t < n_tiles; t += 2) {
+        for (int l = 0; l < L; ++l) {
+          const int Np = a.Np[l], k8 = a.k8[l], k16 = a.k16[l];
+          const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(1, Np);
+          const uint32_t lbo = (uint32_t)Np * 16u;
+          const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
+          const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);
+          mbar_wait(bar_a, ph_a[0]);
+          ph_a[0] ^= 1;
+          tc_fence_after();
+          if (leader) {
+            if (l == 0 && t + 2 < n_tiles) {  // A0 is in TMEM => this slot's x boxes are free
+              mbar_expect_tx(bar_x, 2 * BOX_BYTES);
+              tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
+              tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
             }
+#pragma unroll 4
+            for (int ks = 0; ks < k8; ++ks)  // A_lo * W_hi (first MMA overwrites the accumulator)
+              mma_tf32_ts(tb + COL_D, tb + COL_ALO + ks * 8, dhi + (uint64_t)(ks * dstep), id32, ks > 0);
+#pragma unroll 4
+            for (int ks = 0; ks < k8; ++ks)  // A_hi * W_hi
+              mma_tf32_ts(tb + COL_D, tb + COL_AHI + ks * 8, dhi + (uint64_t)(ks * dstep), id32, 1);
+#pragma unroll 4
+            for (int ks = 0; ks < k16; ++ks)  // bf16(A) * bf16(W_lo)
+              mma_bf16_ts(tb + COL_D, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+            mma_commit(bar_d);
           }
+          __syncwarp();
         }
       }
-      __syncwarp();
     } else {
       // =========================================== epilogue warps
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
@@ -390,10 +392,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             ph_d[s] ^= 1;
             tc_fence_after();
             const uint32_t sl = lane_base + s * SLOT_COLS;
-            if (half == 32) hidden_epilogue<32>(sl, h * 32, bl, a.act[l], a.N[l], swap_bf16);
-            else if (half == 24) hidden_epilogue<24>(sl, h * 24, bl, a.act[l], a.N[l], swap_bf16);
-            else if (half == 16) hidden_epilogue<16>(sl, h * 16, bl, a.act[l], a.N[l], swap_bf16);
-            else hidden_epilogue<8>(sl, h * 8, bl, a.act[l], a.N[l], swap_bf16);
+            if (half == 32) hidden_epilogue<32>(sl, h * 32, bl, swap_bf16);
+            else if (half == 24) hidden_epilogue<24>(sl, h * 24, bl, swap_bf16);
+            else if (half == 16) hidden_epilogue<16>(sl, h * 16, bl, swap_bf16);
+            else hidden_epilogue<8>(sl, h * 8, bl, swap_bf16);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -406,7 +408,6 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         for (int s = 0; s < 2; ++s) {
           if (t0 + s >= n_tiles) continue;
           const int l = L - 1;
-          const int act = (l == a.n_layers - 1) ? a.act[l] : GB_ACT_LINEAR;
           const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + h * 32;
           const int trow = row_begin + (t0 + s) * TILE;
           const int nrows = min(TILE, row_end - trow);
@@ -433,7 +434,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_wait_ld8(yh + 8 * c);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) yh[i] = act_fast(act, yh[i] + bl[i]);
+            for (int i = 0; i < 32; i += 4) {  // output layer is linear
+              const float4 b = *reinterpret_cast<const float4*>(bl + i);
+              yh[i] += b.x; yh[i + 1] += b.y; yh[i + 2] += b.z; yh[i + 3] += b.w;
+            }
           }
           tc_fence_before();
 
@@ -508,7 +512,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   if (!is_ctrl && lane == 0) tma_wait_all0();
   tc_fence_before();
   __syncthreads();
-  if (is_ctrl) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -552,6 +556,11 @@ extern "C" int gb_ffae_tc_supported(const gb_ffnet* net) {
   for (int l = 1; l < L; ++l)
     if (net->dims[l] > W) {
       gb::set_error("tcgen05 variant needs hidden widths <= %d", W);
+      return GB_E_SHAPE;
+    }
+  for (int l = 0; l < L; ++l)
+    if (net->act[l] != (l + 1 < L ? GB_ACT_TANH : GB_ACT_LINEAR)) {
+      gb::set_error("tcgen05 variant is specialised for tanh hidden layers and a linear output (the factory defaults)");
       return GB_E_SHAPE;
     }
   return GB_OK;

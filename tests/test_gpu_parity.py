@@ -219,7 +219,7 @@ def test_smoothing_against_reference_fixture(engine, torch, case):
     window, method = int(g["window"]), str(g["method"])
     for top in ("tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-unscaled"):
         src = np.ascontiguousarray(g[f"frame_{top}"], dtype=np.float32)
-        if src.shape[1] == 1:
+        if src.ndim == 2 and src.shape[1] == 1:
             src = src.reshape(-1)
         a = torch.from_numpy(src).to(dev)
         jobs = engine.jobs_to_device(engine.make_jobs([0], [len(src)], [0]), dev)
