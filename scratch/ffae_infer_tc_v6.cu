@@ -31,11 +31,11 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NTHREADS = 576;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17: control of slot 0 / 1
-constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;  // in both groups: warp%4 = TMEM lane quadrant, (warp/4)%2 = column half
+constexpr int NTHREADS = 576;  // warps 0-15: epilogue; warps 16,17: control of tile slot 0 / 1 (TMA producer + MMA issuer)
+constexpr int EPI_WARPS = 16;  // warp%4 = TMEM lane quadrant (rows), warp/4 = column quarter
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
-constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 rows x 32 fp32
+constexpr int OBOX_BYTES = 32 * 64;    // staging box of one warp: 32 rows x 16 fp32
 constexpr int W = 64;                  // feature width this kernel is specialised for
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
@@ -265,30 +265,27 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap map_x) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem_base;
-  __shared__ unsigned long long s_trace[4][TRACE_SLOTS];
+  __shared__ unsigned long long s_trace[3][TRACE_SLOTS];
   int trace_cnt = 0;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction (lets the compiler use uniform registers)
-  const bool is_ctrl = warp >= EPI_WARPS, is_out = !is_ctrl && warp >= MAIN_WARPS;
-  unsigned long long* ring = s_trace[is_ctrl ? 1 + (warp - EPI_WARPS) : (is_out ? 3 : 0)];
-  const int q = warp & 3, h = (warp >> 2) & 1;  // TMEM lane quadrant (rows 32q..) / column half
-  const int row = q * 32 + lane;                // tile row owned by this thread in the "one thread = one row" layout
+  const bool is_ctrl = warp >= EPI_WARPS;
+  unsigned long long* ring = s_trace[warp >= EPI_WARPS ? 1 + (warp - EPI_WARPS) : 0];
+  const int q = warp & 3, cq = (warp >> 2) & 3;  // epilogue: TMEM lane quadrant (rows 32q..) / column quarter
+  const int row = q * 32 + lane;                 // tile row owned by this epilogue thread
   const uint32_t sbase = smem_u32(smem);
-  // mbarriers, two of each (tile slot 0/1): x_full, a_ready, d_ready (hidden-layer MMAs), f_ready (output-layer MMAs), d_free
+  // barriers: [0,1] x_full[slot], [2,3] a_ready[slot], [4,5] d_ready[slot]
   const uint32_t bars = sbase + a.bar_ofs;
-  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64;
   const bool has_y = a.y != nullptr;
   const int L = a.last_layer + 1;
   const bool swap_bf16 = (a.flags & FLAG_SWAP_BF16) != 0;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bars + BX + 8 * s, 1);
-      mbar_init(bars + BA + 8 * s, MAIN_WARPS);
-      mbar_init(bars + BD + 8 * s, 1);
-      mbar_init(bars + BF + 8 * s, 1);
-      mbar_init(bars + BE + 8 * s, OUT_WARPS);
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 16 + 8 * s, EPI_WARPS);
+      mbar_init(bars + 32 + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -302,8 +299,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem_base, 0);
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
-  // phase parities (each role uses the subset it waits on)
-  uint32_t ph_x[2] = {0, 0}, ph_a = 0, ph_d[2] = {0, 0}, ph_f[2] = {0, 0}, ph_e = 0;
+  uint32_t ph_x[2] = {0, 0}, ph_a[2] = {0, 0}, ph_d[2] = {0, 0};
   int cur_slot = -1;
   const int n_items = a.n_jobs * a.chunks_per_job;
 
@@ -363,8 +359,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const int s = warp - EPI_WARPS;
       const bool leader = lane == 0;
       const long xrow0 = job.x_row + row_begin;
-      const uint32_t bar_x = bars + BX + 8 * s, bar_a = bars + BA + 8 * s, bar_d = bars + BD + 8 * s, bar_f = bars + BF + 8 * s,
-                     bar_e = bars + BE + 8 * s;
+      const uint32_t bar_x = bars + 8 * s, bar_a = bars + 16 + 8 * s, bar_d = bars + 32 + 8 * s;
       const uint32_t xdst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
       const uint32_t tb = tmem + s * SLOT_COLS;
       if (s < n_tiles && leader) {
@@ -379,12 +374,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           const uint32_t lbo = (uint32_t)Np * 16u;
           const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
           const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);
-          mbar_wait(bar_a, ph_a);
-          ph_a ^= 1;
-          if (l == 0 && t >= 2) {  // the output warps must have read the previous tile's accumulator out of this slot
-            mbar_wait(bar_e, ph_e);
-            ph_e ^= 1;
-          }
+          mbar_wait(bar_a, ph_a[0]);
+          ph_a[0] ^= 1;
           tc_fence_after();
           if (leader) trace_ev(a, ring, trace_cnt, 1, t, l, s);
           if (leader) {
@@ -403,185 +394,190 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)  // bf16(A) * bf16(W_lo)
               if (ks < k16) mma_bf16_ts(tb + COL_D, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
-            if (l + 1 < L) {
-              mma_commit(bar_d);
-            } else {
-              mma_commit(bar_f);  // output layer: watched by the output warps (accumulator) and the layer warps (A regions reusable)
-            }
+            mma_commit(bar_d);
             trace_ev(a, ring, trace_cnt, 2, t, l, s);
           }
           __syncwarp();
         }
       }
-      if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
-    } else if (!is_out) {
-      // =========================================== layer-epilogue warps (SFU-bound): x split + hidden layers
+    } else {
+      // =========================================== epilogue warps: rows 32q.., 16 of the 64 columns each
+      const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
+      const uint32_t stage = sbase + a.stage_ofs + warp * OBOX_BYTES;  // this warp's 32-row x 64-byte staging box
+      float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);      // [3][2][TILE] row-sum partials of column quarters 1..3
+      const float inv_w = 1.0f / (float)W;
+      // staging box: row r at r*64, 16-byte chunk c stored at c ^ ((r >> 1) & 3) => conflict-free for both access patterns
+      const uint32_t st_own = stage + (uint32_t)lane * 64u;
+      const int own_x = (lane >> 1) & 3;
+      const int tr = lane >> 2, tc = lane & 3;  // transposed mapping: row i*8 + tr, 16-byte chunk tc (4 lanes = 64 contiguous bytes)
+
       for (int t0 = 0; t0 < n_tiles; t0 += 2) {
         // ---- x -> A operand of layer 0 ----------------------------------------------------------------------------
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (t0 + s >= n_tiles) continue;
-          if (t0 >= 2) {  // the previous tile's output-layer MMA has finished reading this slot's A regions
-            mbar_wait(bars + BF + 8 * s, ph_f[s]);
-            ph_f[s] ^= 1;
-          }
-          const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-          mbar_wait(bars + BX + 8 * s, ph_x[s]);
+          const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + (cq >> 1)) * BOX_BYTES + (uint32_t)row * 128u;
+          mbar_wait(bars + 8 * s, ph_x[s]);
           ph_x[s] ^= 1;
+          float v[16];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float v[16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t addr = xbox + ((uint32_t)((half * 4 + c) ^ (row & 7)) << 4);
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
-            }
-            store_a_operands<16>(lane_base + s * SLOT_COLS, h * 32 + half * 16, v, swap_bf16);
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = xbox + ((uint32_t)(((cq & 1) * 4 + c) ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
           }
+          store_a_operands<16>(lane_base + s * SLOT_COLS, cq * 16, v, swap_bf16);
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+          if (lane == 0) mbar_arrive(bars + 16 + 8 * s);
           if (tid == 0) trace_ev(a, ring, trace_cnt, 3, t0 + s, 0, s);
         }
 
         // ---- hidden layers: D -> bias, activation -> next A operand (tile s' epilogue overlaps tile 1-s' MMAs) ------------
         for (int l = 0; l + 1 < L; ++l) {
-          const int half = a.Np[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), processed in two chunks
-          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + h * half;
+          const int quarter = a.Np[l] >> 2;  // columns this warp owns: [cq*quarter, (cq+1)*quarter)
+          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + cq * quarter;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             if (t0 + s >= n_tiles) continue;
             if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, ph_d[s]);
+            mbar_wait(bars + 32 + 8 * s, ph_d[s]);
             ph_d[s] ^= 1;
             tc_fence_after();
             if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
             const uint32_t sl = lane_base + s * SLOT_COLS;
-            if (half == 32) { hidden_epilogue<16>(sl, h * 32, bl, swap_bf16); hidden_epilogue<16>(sl, h * 32 + 16, bl + 16, swap_bf16); }
-            else if (half == 24) { hidden_epilogue<12>(sl, h * 24, bl, swap_bf16); hidden_epilogue<12>(sl, h * 24 + 12, bl + 12, swap_bf16); }
-            else if (half == 16) { hidden_epilogue<8>(sl, h * 16, bl, swap_bf16); hidden_epilogue<8>(sl, h * 16 + 8, bl + 8, swap_bf16); }
-            else { hidden_epilogue<4>(sl, h * 8, bl, swap_bf16); hidden_epilogue<4>(sl, h * 8 + 4, bl + 4, swap_bf16); }
+            if (quarter == 16) hidden_epilogue<16>(sl, cq * 16, bl, swap_bf16);
+            else if (quarter == 12) hidden_epilogue<12>(sl, cq * 12, bl, swap_bf16);
+            else if (quarter == 8) hidden_epilogue<8>(sl, cq * 8, bl, swap_bf16);
+            else hidden_epilogue<4>(sl, cq * 4, bl, swap_bf16);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+            if (lane == 0) mbar_arrive(bars + 16 + 8 * s);
             if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t0 + s, l, s);
           }
         }
-      }
-      // consume the output-layer phases of the last tile of each slot so the parities stay aligned across items
-#pragma unroll
-      for (int s = 0; s < 2; ++s)
-        if (s < n_tiles) {
-          mbar_wait(bars + BF + 8 * s, ph_f[s]);
-          ph_f[s] ^= 1;
-        }
-    } else {
-      // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
-      // Global traffic is row-major with 8 lanes per 128-byte row segment ("transposed" layout: row = i*4 + tr, 16-byte chunk tc).
-      // Only the accumulator has to change layout (TMEM gives one thread = one row): it goes once through this warp's swizzled
-      // staging box; y is loaded straight into the transposed layout and every output column is formed and stored there.
-      const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * OBOX_BYTES;
-      float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2 halves][2][TILE] row sums
-      const int tr = lane >> 3, tc = lane & 7;
-      const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
-      const float4 rt4 = *reinterpret_cast<const float4*>(vec + W + h * 32 + tc * 4);
-      const float4 b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + a.bias_ofs[L - 1]) + h * 32 + tc * 4);
-      const float inv_w = 1.0f / (float)W;
-      const bool totals = has_y && (a.o_tots || a.o_totu || a.o_totconf);
 
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t & 1;
-        const int trow = row_begin + t * TILE;
-        const int nrows = min(TILE, row_end - trow);
-        const long grow0 = job.out_row + trow;
-        const int wrow0 = q * 32;
-        float4 yt[8];
-        if (has_y) {  // requested before the accumulator is ready
+        // ---- last layer: model output + anomaly columns ------------------------------------------------------------------
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = min(wrow0 + i * 4 + tr, nrows - 1);
-            yt[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + h * 32) + tc);
+        for (int s = 0; s < 2; ++s) {
+          if (t0 + s >= n_tiles) continue;
+          const int l = L - 1;
+          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + cq * 16;
+          const int trow = row_begin + (t0 + s) * TILE;
+          const int nrows = min(TILE, row_end - trow);
+          const long grow0 = job.out_row + trow;
+          const int wrow0 = q * 32;  // first tile row of this warp
+          // Row-major global traffic is done 8 rows per warp instruction (4 lanes x 16 B = this warp's 64 contiguous bytes of
+          // a row); the transposition to/from "one thread = one row" goes through this warp's swizzled staging box.
+          float4 ytmp[4];
+          if (has_y) {  // requested now, used after the last MMA has been waited for
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = min(wrow0 + i * 8 + tr, nrows - 1);
+              ytmp[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + cq * 16) + tc);
+            }
           }
-        }
-        if (tid == MAIN_WARPS * 32) trace_ev(a, ring, trace_cnt, 7, t, L - 1, s);
-        mbar_wait(bars + BF + 8 * s, ph_f[s]);
-        ph_f[s] ^= 1;
-        tc_fence_after();
-        {
-          float acc[32];
-          const uint32_t sl = lane_base + s * SLOT_COLS + COL_D + h * 32;
+          float yh[16];
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 7, t0 + s, l, s);
+          mbar_wait(bars + 32 + 8 * s, ph_d[s]);
+          ph_d[s] ^= 1;
+          tc_fence_after();
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 8, t0 + s, l, s);
+          tmem_load_cols<16>(lane_base + s * SLOT_COLS + COL_D + cq * 16, yh);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_wait_ld8(acc + 8 * c);
+          for (int i = 0; i < 16; i += 4) {  // output layer is linear
+            const float4 b = *reinterpret_cast<const float4*>(bl + i);
+            yh[i] += b.x; yh[i + 1] += b.y; yh[i + 2] += b.z; yh[i + 3] += b.w;
+          }
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars + BE + 8 * s);  // the slot's accumulator may be overwritten by the next tile
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t addr = stage + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(acc[4 * c]), "f"(acc[4 * c + 1]), "f"(acc[4 * c + 2]), "f"(acc[4 * c + 3]) : "memory");
-          }
-        }
-        __syncwarp();
-        float ss[8], su[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + tr;
-          float4 yh;
-          const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
-          yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
-          const bool live = wrow0 + r < nrows;
-          const long g = (grow0 + wrow0 + r) * (long)W + h * 32 + tc * 4;
-          if (live) *reinterpret_cast<float4*>(a.o_model + g) = yh;
-          ss[i] = 0.f; su[i] = 0.f;
+          float yt[16];
           if (has_y) {
-            float4 d, e;
-            d.x = fabsf(yh.x - yt[i].x); d.y = fabsf(yh.y - yt[i].y); d.z = fabsf(yh.z - yt[i].z); d.w = fabsf(yh.w - yt[i].w);
-            su[i] = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-            if (live && a.o_tu) *reinterpret_cast<float4*>(a.o_tu + g) = d;
-            e.x = d.x * sc4.x; e.y = d.y * sc4.y; e.z = d.z * sc4.z; e.w = d.w * sc4.w;
-            ss[i] = e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
-            if (live && a.o_ts) *reinterpret_cast<float4*>(a.o_ts + g) = e;
-            if (live && a.o_conf) *reinterpret_cast<float4*>(a.o_conf + g) = make_float4(d.x * rt4.x, d.y * rt4.y, d.z * rt4.z, d.w * rt4.w);
-          }
-        }
-        __syncwarp();  // staging box reusable
-        if (totals) {
-          // row sums: 8 lanes (tc) hold the 32 columns of this half; halves meet in shared memory
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + tr;
+              const uint32_t addr = stage + (uint32_t)r * 64u + ((uint32_t)(tc ^ ((r >> 1) & 3)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(ytmp[i].x), "f"(ytmp[i].y), "f"(ytmp[i].z), "f"(ytmp[i].w) : "memory");
+            }
+            __syncwarp();
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
-              su[i] += __shfl_xor_sync(0xffffffffu, su[i], o);
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t addr = st_own + ((uint32_t)(c ^ own_x) << 4);
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yt[4 * c]), "=f"(yt[4 * c + 1]), "=f"(yt[4 * c + 2]), "=f"(yt[4 * c + 3]) : "r"(addr));
             }
-            if (tc == 0) {
-              pair[h * 2 * TILE + wrow0 + i * 4 + tr] = ss[i];
-              pair[h * 2 * TILE + TILE + wrow0 + i * 4 + tr] = su[i];
+            __syncwarp();
+          }
+
+          auto emit = [&](const float (&val)[16], float* gptr) {
+            if (gptr == nullptr) return;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t addr = st_own + ((uint32_t)(c ^ own_x) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(val[4 * c]), "f"(val[4 * c + 1]), "f"(val[4 * c + 2]), "f"(val[4 * c + 3]) : "memory");
+            }
+            __syncwarp();
+            float* gbase = gptr + (grow0 + wrow0 + tr) * (long)W + cq * 16 + tc * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + tr;
+              float4 v4;
+              const uint32_t addr = stage + (uint32_t)r * 64u + ((uint32_t)(tc ^ ((r >> 1) & 3)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w) : "r"(addr));
+              if (wrow0 + r < nrows) *reinterpret_cast<float4*>(gbase + (long)i * 8 * W) = v4;
+            }
+            __syncwarp();
+          };
+
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 10, t0 + s, l, s);
+          emit(yh, a.o_model);
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 11, t0 + s, l, s);
+          if (has_y) {
+            float d[16], ss = 0.f, su = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              d[i] = fabsf(yh[i] - yt[i]);
+              su = fmaf(d[i], d[i], su);
+            }
+            emit(d, a.o_tu);
+            if (a.scale) {
+              float e[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                e[i] = d[i] * vec[cq * 16 + i];
+                ss = fmaf(e[i], e[i], ss);
+              }
+              emit(e, a.o_ts);
+            }
+            if (a.o_conf) {
+              float c_[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) c_[i] = d[i] * vec[W + cq * 16 + i];
+              emit(c_, a.o_conf);
+            }
+            if (tid == 0) trace_ev(a, ring, trace_cnt, 12, t0 + s, l, s);
+            if (a.o_tots || a.o_totu || a.o_totconf) {  // row sums: the four warps of a lane quadrant meet on a 128-thread barrier
+              if (cq > 0) { pair[(cq - 1) * 2 * TILE + row] = ss; pair[(cq - 1) * 2 * TILE + TILE + row] = su; }
+              named_bar_sync(1 + q, 128);
+              if (tid == 0) trace_ev(a, ring, trace_cnt, 13, t0 + s, l, s);
+              if (cq == 0 && row < nrows) {
+                const float ts_ = (ss + pair[row] + pair[2 * TILE + row] + pair[4 * TILE + row]) * inv_w;
+                const float tu_ = (su + pair[TILE + row] + pair[3 * TILE + row] + pair[5 * TILE + row]) * inv_w;
+                if (a.o_tots) a.o_tots[grow0 + row] = ts_;
+                if (a.o_totu) a.o_totu[grow0 + row] = tu_;
+                if (a.o_totconf) a.o_totconf[grow0 + row] = ts_ / __ldg(a.agg_thr + job.slot);
+              }
+              named_bar_sync(1 + q, 128);
             }
           }
-          named_bar_sync(1 + q, 64);
-          if (h == 0 && row < nrows) {
-            const float ts_ = (pair[row] + pair[2 * TILE + row]) * inv_w, tu_ = (pair[TILE + row] + pair[3 * TILE + row]) * inv_w;
-            if (a.o_tots) a.o_tots[grow0 + row] = ts_;
-            if (a.o_totu) a.o_totu[grow0 + row] = tu_;
-            if (a.o_totconf) a.o_totconf[grow0 + row] = ts_ / __ldg(a.agg_thr + job.slot);
-          }
-          named_bar_sync(1 + q, 64);
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 9, t0 + s, l, s);
         }
-        if (tid == MAIN_WARPS * 32) trace_ev(a, ring, trace_cnt, 9, t, L - 1, s);
       }
     }
     __syncthreads();
   }
 
-  if (a.trace != nullptr && blockIdx.x == 0 && (tid == 0 || tid == MAIN_WARPS * 32 || (is_ctrl && lane == 0))) {
-    const int role = is_ctrl ? 1 + (warp - EPI_WARPS) : (is_out ? 3 : 0);
+  if (a.trace != nullptr && blockIdx.x == 0 && (tid == 0 || (is_ctrl && lane == 0))) {
+    const int role = is_ctrl ? 1 + (warp - EPI_WARPS) : 0;
     a.trace[role] = trace_cnt;
     for (int i = 0; i < trace_cnt; ++i) a.trace[4 + role * TRACE_SLOTS + i] = (long long)ring[i];
   }
@@ -619,7 +615,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_rows) {
   return GB_OK;
 }
 
-long long* g_trace = nullptr;  // 4 + 4*TRACE_SLOTS int64
+long long* g_trace = nullptr;  // 4 + 3*TRACE_SLOTS int64
 int g_trace_cap = 0;
 
 }  // namespace
@@ -688,11 +684,11 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.w_bytes = gb::round_up(ofs, 16);
   ofs = a.w_bytes;
   a.vec_ofs = ofs; ofs += 2 * W * 4;
-  a.pair_ofs = ofs; ofs += 4 * TILE * 4;
-  a.bar_ofs = ofs; ofs += 128;
+  a.pair_ofs = ofs; ofs += 6 * TILE * 4;
+  a.bar_ofs = ofs; ofs += 64;
   ofs = gb::round_up(ofs, 1024);
   a.xbox_ofs = ofs; ofs += 4 * BOX_BYTES;            // two tile slots x two 32-column boxes
-  a.stage_ofs = ofs; ofs += OUT_WARPS * OBOX_BYTES;  // one 32-row x 32-column staging box per output warp
+  a.stage_ofs = ofs; ofs += EPI_WARPS * OBOX_BYTES;  // one 32x32 staging box per epilogue warp
   const size_t smem = (size_t)ofs;
   GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
 
