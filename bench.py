@@ -293,6 +293,7 @@ def main():
 
 
 def eng_variant_name(variant, eng):
+    variant &= 0xFF
     if variant == 1:
         return "fma"
     if variant == 2:

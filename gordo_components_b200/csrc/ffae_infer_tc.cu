@@ -39,7 +39,9 @@ constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 row
 constexpr int W = 64;                  // feature width this kernel is specialised for
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
-constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, SLOT_COLS = 224, TMEM_COLS = 512;
+constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, SLOT_COLS = 224, COL_DX = 448, TMEM_COLS = 512;
+// COL_DX: spare accumulator (absolute column) that receives the OUTPUT layer of slot-1 tiles, so slot 1 can start its next
+// tile while the output warps are still busy with the previous pair (they drain slot 0's accumulator first)
 
 struct TcArgs {
   int n_layers, last_layer;  // layers actually evaluated: 0..last_layer (debug aid; == n_layers-1 in production)
@@ -59,6 +61,7 @@ struct TcArgs {
 };
 
 enum { FLAG_SWAP_BF16 = 1 };
+constexpr int DEFAULT_NE = 0;
 
 // debug timeline (gb_debug_set_trace): three recorder threads of CTA 0 (epilogue tid 0, the two control leaders) stamp
 // events into shared memory (one clock read + one store each) and flush them to global memory when the kernel ends
@@ -198,8 +201,7 @@ __device__ __forceinline__ float tanh_from_scaled_fma(float t) {
   return fmaf(-2.0f, r, 1.0f);
 }
 
-// every NEWTON_EVERY-th element takes the 1-MUFU tanh (0: never) -- the knob that trades SFU against FMA-pipe load
-constexpr int NEWTON_EVERY = 0;
+// NE: every NE-th element takes the 1-MUFU tanh (0: never) -- the knob that trades SFU against FMA-pipe load
 
 // split NC (16, 12 or 8) activations into the three A operands (TF32 hi, fp32 remainder, packed BF16) at column `col`
 template <int NC>
@@ -244,7 +246,7 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float* v) {
 // hidden layer epilogue of one warp: NC accumulator columns -> bias, activation -> next layer's A operand
 // (activation is tanh by construction: gb_ffae_tc_supported admits only tanh hidden layers + linear output, so the
 // compiler sees straight-line code and interleaves the NC independent ex2/rcp chains)
-template <int NC>
+template <int NC, int NE>
 __device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, const float* bias, bool swap_bf16) {
   float v[NC];
   tmem_load_cols<NC>(slot_lane + COL_D + col0, v);
@@ -255,12 +257,13 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, co
                         fmaf(v[i + 3], TANH_ARG_SCALE, b.w)};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      v[i + j] = (NEWTON_EVERY > 0 && ((i + j) % (NEWTON_EVERY > 0 ? NEWTON_EVERY : 1)) == 0) ? tanh_from_scaled_fma(t[j]) : tanh_from_scaled(t[j]);
+      v[i + j] = (NE > 0 && ((i + j) % (NE > 0 ? NE : 1)) == 0) ? tanh_from_scaled_fma(t[j]) : tanh_from_scaled(t[j]);
   }
   store_a_operands<NC>(slot_lane, col0, v, swap_bf16);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+template <int NE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap map_x) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -271,7 +274,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction (lets the compiler use uniform registers)
   const bool is_ctrl = warp >= EPI_WARPS, is_out = !is_ctrl && warp >= MAIN_WARPS;
-  unsigned long long* ring = s_trace[is_ctrl ? 1 + (warp - EPI_WARPS) : (is_out ? 3 : 0)];
+  unsigned long long* ring = s_trace[is_ctrl ? (warp == EPI_WARPS ? 1 : 0) : (is_out ? (warp == EPI_WARPS - 1 ? 2 : 3) : 0)];
   const int q = warp & 3, h = (warp >> 2) & 1;  // TMEM lane quadrant (rows 32q..) / column half
   const int row = q * 32 + lane;                // tile row owned by this thread in the "one thread = one row" layout
   const uint32_t sbase = smem_u32(smem);
@@ -303,7 +306,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
   // phase parities (each role uses the subset it waits on)
-  uint32_t ph_x[2] = {0, 0}, ph_a = 0, ph_d[2] = {0, 0}, ph_f[2] = {0, 0}, ph_e = 0;
+  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0;
   int cur_slot = -1;
   const int n_items = a.n_jobs * a.chunks_per_job;
 
@@ -381,12 +384,15 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);
           mbar_wait(bar_a, ph_a);
           ph_a ^= 1;
-          if (l == 0 && t >= 2) {  // the output warps must have read the previous tile's accumulator out of this slot
+          // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
+          // layer (wait before layer 0); slot 1 sends only its output layer to the spare accumulator (wait before that layer)
+          if (t >= 2 && l == (s == 0 ? 0 : L - 1)) {
             mbar_wait(bar_e, ph_e);
             ph_e ^= 1;
           }
+          const uint32_t dcol = (s == 1 && l == L - 1) ? tmem + COL_DX : tb + COL_D;
           tc_fence_after();
-          if (leader) trace_ev(a, ring, trace_cnt, 1, t, l, s);
+          if (leader && s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
           if (leader) {
             if (l == 0 && t + 2 < n_tiles) {  // A0 is in TMEM => this slot's x boxes are free
               mbar_expect_tx(bar_x, 2 * BOX_BYTES);
@@ -396,19 +402,19 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             // straight-line issue (K <= 64 => at most 8 / 8 / 4 steps): measured 49 cycles per MMA against 73 for a rolled loop
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)  // A_lo * W_hi (first MMA overwrites the accumulator)
-              if (ks < k8) mma_tf32_ts(tb + COL_D, tb + COL_ALO + ks * 8, dhi + (uint64_t)(ks * dstep), id32, ks > 0);
+              if (ks < k8) mma_tf32_ts(dcol, tb + COL_ALO + ks * 8, dhi + (uint64_t)(ks * dstep), id32, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi
-              if (ks < k8) mma_tf32_ts(tb + COL_D, tb + COL_AHI + ks * 8, dhi + (uint64_t)(ks * dstep), id32, 1);
+              if (ks < k8) mma_tf32_ts(dcol, tb + COL_AHI + ks * 8, dhi + (uint64_t)(ks * dstep), id32, 1);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)  // bf16(A) * bf16(W_lo)
-              if (ks < k16) mma_bf16_ts(tb + COL_D, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+              if (ks < k16) mma_bf16_ts(dcol, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
             if (l + 1 < L) {
               mma_commit(bar_d);
             } else {
               mma_commit(bar_f);  // output layer: watched by the output warps (accumulator) and the layer warps (A regions reusable)
             }
-            trace_ev(a, ring, trace_cnt, 2, t, l, s);
+            if (s == 0) trace_ev(a, ring, trace_cnt, 2, t, l, s);
           }
           __syncwarp();
         }
@@ -422,12 +428,12 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         for (int s = 0; s < 2; ++s) {
           if (t0 + s >= n_tiles) continue;
           if (t0 >= 2) {  // the previous tile's output-layer MMA has finished reading this slot's A regions
-            mbar_wait(bars + BF + 8 * s, ph_f[s]);
-            ph_f[s] ^= 1;
+            mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
+            if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
           }
           const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-          mbar_wait(bars + BX + 8 * s, ph_x[s]);
-          ph_x[s] ^= 1;
+          mbar_wait(bars + BX + 8 * s, s ? ph_x1 : ph_x0);
+          if (s) ph_x1 ^= 1; else ph_x0 ^= 1;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float v[16];
@@ -453,15 +459,15 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           for (int s = 0; s < 2; ++s) {
             if (t0 + s >= n_tiles) continue;
             if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, ph_d[s]);
-            ph_d[s] ^= 1;
+            mbar_wait(bars + BD + 8 * s, s ? ph_d1 : ph_d0);
+            if (s) ph_d1 ^= 1; else ph_d0 ^= 1;
             tc_fence_after();
             if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
             const uint32_t sl = lane_base + s * SLOT_COLS;
-            if (half == 32) { hidden_epilogue<16>(sl, h * 32, bl, swap_bf16); hidden_epilogue<16>(sl, h * 32 + 16, bl + 16, swap_bf16); }
-            else if (half == 24) { hidden_epilogue<12>(sl, h * 24, bl, swap_bf16); hidden_epilogue<12>(sl, h * 24 + 12, bl + 12, swap_bf16); }
-            else if (half == 16) { hidden_epilogue<8>(sl, h * 16, bl, swap_bf16); hidden_epilogue<8>(sl, h * 16 + 8, bl + 8, swap_bf16); }
-            else { hidden_epilogue<4>(sl, h * 8, bl, swap_bf16); hidden_epilogue<4>(sl, h * 8 + 4, bl + 4, swap_bf16); }
+            if (half == 32) { hidden_epilogue<16, NE>(sl, h * 32, bl, swap_bf16); hidden_epilogue<16, NE>(sl, h * 32 + 16, bl + 16, swap_bf16); }
+            else if (half == 24) { hidden_epilogue<12, NE>(sl, h * 24, bl, swap_bf16); hidden_epilogue<12, NE>(sl, h * 24 + 12, bl + 12, swap_bf16); }
+            else if (half == 16) { hidden_epilogue<8, NE>(sl, h * 16, bl, swap_bf16); hidden_epilogue<8, NE>(sl, h * 16 + 8, bl + 8, swap_bf16); }
+            else { hidden_epilogue<4, NE>(sl, h * 8, bl, swap_bf16); hidden_epilogue<4, NE>(sl, h * 8 + 4, bl + 4, swap_bf16); }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -474,8 +480,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
       for (int s = 0; s < 2; ++s)
         if (s < n_tiles) {
-          mbar_wait(bars + BF + 8 * s, ph_f[s]);
-          ph_f[s] ^= 1;
+          mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
+          if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
         }
     } else {
       // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
@@ -506,13 +512,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             yt[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + h * 32) + tc);
           }
         }
-        if (tid == MAIN_WARPS * 32) trace_ev(a, ring, trace_cnt, 7, t, L - 1, s);
-        mbar_wait(bars + BF + 8 * s, ph_f[s]);
-        ph_f[s] ^= 1;
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t, L - 1, s);
+        mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
+        if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
         tc_fence_after();
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
         {
           float acc[32];
-          const uint32_t sl = lane_base + s * SLOT_COLS + COL_D + h * 32;
+          const uint32_t sl = lane_base + (s == 1 ? COL_DX : COL_D) + h * 32;
 #pragma unroll
           for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
 #pragma unroll
@@ -520,6 +527,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bars + BE + 8 * s);  // the slot's accumulator may be overwritten by the next tile
+          if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 10, t, L - 1, s);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t addr = stage + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4);
@@ -551,6 +559,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
         __syncwarp();  // staging box reusable
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, s);
         if (totals) {
           // row sums: 8 lanes (tc) hold the 32 columns of this half; halves meet in shared memory
 #pragma unroll
@@ -574,14 +583,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
           named_bar_sync(1 + q, 64);
         }
-        if (tid == MAIN_WARPS * 32) trace_ev(a, ring, trace_cnt, 9, t, L - 1, s);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, s);
       }
     }
     __syncthreads();
   }
 
-  if (a.trace != nullptr && blockIdx.x == 0 && (tid == 0 || tid == MAIN_WARPS * 32 || (is_ctrl && lane == 0))) {
-    const int role = is_ctrl ? 1 + (warp - EPI_WARPS) : (is_out ? 3 : 0);
+  if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MAIN_WARPS || warp == EPI_WARPS - 1 || warp == EPI_WARPS)) {
+    const int role = is_ctrl ? 1 : (is_out ? (warp == EPI_WARPS - 1 ? 2 : 3) : 0);
     a.trace[role] = trace_cnt;
     for (int i = 0; i < trace_cnt; ++i) a.trace[4 + role * TRACE_SLOTS + i] = (long long)ring[i];
   }
@@ -718,8 +727,17 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
 
   const long items = (long)n_jobs * a.chunks_per_job;
   const int grid = (int)(items < sms ? items : sms);
-  GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ffae_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx);
+  const int ne_sel = (flags >> 4) & 3;  // debug knob: share of tanh evaluations that take the 1-MUFU form
+  auto launch = [&](auto kern) -> int {
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx);
+    return GB_OK;
+  };
+  if (ne_sel == 1) rc = launch(ffae_tc_kernel<2>);
+  else if (ne_sel == 2) rc = launch(ffae_tc_kernel<3>);
+  else if (ne_sel == 3) rc = launch(ffae_tc_kernel<4>);
+  else rc = launch(ffae_tc_kernel<DEFAULT_NE>);
+  if (rc != GB_OK) return rc;
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }

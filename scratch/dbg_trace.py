@@ -32,7 +32,8 @@ for role in range(4):
         rec.append((v >> 24, role, (v >> 12) & 0xfff, (v >> 8) & 0xf, (v >> 4) & 0xf, v & 0xf))
 rec.sort()
 t0 = rec[0][0]
-names = {1: 'ctrl wake(a_ready)', 2: 'ctrl committed', 3: 'epi X arrive', 4: 'epi wait d (hidden)', 5: 'epi woke d (hidden)', 6: 'epi arrive a (hidden)', 7: 'epi wait d (final)', 8: 'epi woke d (final)', 9: 'epi final done', 10: 'final: y ready, before emit model', 11: 'final: model emitted', 12: 'final: all arrays emitted', 13: 'final: rowsum barrier passed'}
+names = {1: 'ctrl wake(a_ready)', 2: 'ctrl committed', 3: 'epi X arrive', 4: 'epi wait d (hidden)', 5: 'epi woke d (hidden)', 6: 'epi arrive a (hidden)', 7: 'epi wait d (final)', 8: 'epi woke d (final)', 9: 'epi final done', 10: 'out: D read, d_free arrived', 12: 'out: stores issued'}
 print('events', len(rec))
-for clk, role, tile, layer, slot, code in rec[:300]:
+for clk, role, tile, layer, slot, code in rec[:400]:
+    if role in (0, 1) and code not in (2, 3): continue
     print(f"{clk - t0:8d}  role={role} tile={tile:2d} l={layer} s={slot}  {names.get(code, code)}")
