@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;
 constexpr int NWARPS = THREADS / 32;
 constexpr int BR = 32;  // rows of a mini-batch chunk: one row per lane
 

@@ -32,7 +32,7 @@ namespace {
 
 constexpr int TILE = 128;
 constexpr int NTHREADS = 576;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17: control of slot 0 / 1
-constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;  // in both groups: warp%4 = TMEM lane quadrant, (warp/4)%2 = column half
+constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;  // layer warps: warp%4 = TMEM lane quadrant, warp/4 = tile slot; output warps: warp%4 = quadrant, (warp/4)%2 = column half
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
 constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 rows x 32 fp32
@@ -88,11 +88,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"  // suspend-time hint: sleep in hardware, do not spin
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
+      "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -288,7 +288,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bars + BX + 8 * s, 1);
-      mbar_init(bars + BA + 8 * s, MAIN_WARPS);
+      mbar_init(bars + BA + 8 * s, MAIN_WARPS / 2);
       mbar_init(bars + BD + 8 * s, 1);
       mbar_init(bars + BF + 8 * s, 1);
       mbar_init(bars + BE + 8 * s, OUT_WARPS);
@@ -421,68 +421,65 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       }
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
-      // =========================================== layer-epilogue warps (SFU-bound): x split + hidden layers
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
+      // =========================================== layer-epilogue warps (SFU-bound): x split + hidden layers.
+      // Warps 0-3 own tile slot 0, warps 4-7 slot 1 (one warp per TMEM lane quadrant, every column of its rows): the two
+      // slots advance independently, so one slot's TMEM/MMA latencies are covered by the other slot's SFU work.
+      const int s = warp >> 2;
+      const uint32_t sl = lane_base + s * SLOT_COLS;
+      const uint32_t bar_x = bars + BX + 8 * s, bar_a = bars + BA + 8 * s, bar_d = bars + BD + 8 * s, bar_f = bars + BF + 8 * s;
+      for (int t = s; t < n_tiles; t += 2) {
+        if (t >= 2) {  // the previous tile's output-layer MMA has finished reading this slot's A regions
+          mbar_wait(bar_f, ph_f0);
+          ph_f0 ^= 1;
+        }
         // ---- x -> A operand of layer 0 ----------------------------------------------------------------------------
+        mbar_wait(bar_x, ph_x0);
+        ph_x0 ^= 1;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (t0 + s >= n_tiles) continue;
-          if (t0 >= 2) {  // the previous tile's output-layer MMA has finished reading this slot's A regions
-            mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
-            if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
+        for (int part = 0; part < 4; ++part) {  // 4 x 16 columns; columns 0-31 live in the slot's first box, 32-63 in the second
+          const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + (part >> 1)) * BOX_BYTES + (uint32_t)row * 128u;
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = xbox + ((uint32_t)(((part & 1) * 4 + c) ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
           }
-          const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-          mbar_wait(bars + BX + 8 * s, s ? ph_x1 : ph_x0);
-          if (s) ph_x1 ^= 1; else ph_x0 ^= 1;
+          store_a_operands<16>(sl, part * 16, v, swap_bf16);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+        if (tid == 0) trace_ev(a, ring, trace_cnt, 3, t, 0, s);
+
+        // ---- hidden layers: D -> bias, activation -> next A operand --------------------------------------------------------
+        for (int l = 0; l + 1 < L; ++l) {
+          const int quarter = a.Np[l] >> 2;  // processed in four chunks to keep the register footprint of 16 columns
+          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t, l, s);
+          mbar_wait(bar_d, ph_d0);
+          ph_d0 ^= 1;
+          tc_fence_after();
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t, l, s);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float v[16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t addr = xbox + ((uint32_t)((half * 4 + c) ^ (row & 7)) << 4);
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
-            }
-            store_a_operands<16>(lane_base + s * SLOT_COLS, h * 32 + half * 16, v, swap_bf16);
+          for (int part = 0; part < 4; ++part) {
+            if (quarter == 16) hidden_epilogue<16, NE>(sl, part * 16, bl + part * 16, swap_bf16);
+            else if (quarter == 12) hidden_epilogue<12, NE>(sl, part * 12, bl + part * 12, swap_bf16);
+            else if (quarter == 8) hidden_epilogue<8, NE>(sl, part * 8, bl + part * 8, swap_bf16);
+            else hidden_epilogue<4, NE>(sl, part * 4, bl + part * 4, swap_bf16);
           }
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-          if (tid == 0) trace_ev(a, ring, trace_cnt, 3, t0 + s, 0, s);
-        }
-
-        // ---- hidden layers: D -> bias, activation -> next A operand (tile s' epilogue overlaps tile 1-s' MMAs) ------------
-        for (int l = 0; l + 1 < L; ++l) {
-          const int half = a.Np[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), processed in two chunks
-          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + h * half;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (t0 + s >= n_tiles) continue;
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, s ? ph_d1 : ph_d0);
-            if (s) ph_d1 ^= 1; else ph_d0 ^= 1;
-            tc_fence_after();
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
-            const uint32_t sl = lane_base + s * SLOT_COLS;
-            if (half == 32) { hidden_epilogue<16, NE>(sl, h * 32, bl, swap_bf16); hidden_epilogue<16, NE>(sl, h * 32 + 16, bl + 16, swap_bf16); }
-            else if (half == 24) { hidden_epilogue<12, NE>(sl, h * 24, bl, swap_bf16); hidden_epilogue<12, NE>(sl, h * 24 + 12, bl + 12, swap_bf16); }
-            else if (half == 16) { hidden_epilogue<8, NE>(sl, h * 16, bl, swap_bf16); hidden_epilogue<8, NE>(sl, h * 16 + 8, bl + 8, swap_bf16); }
-            else { hidden_epilogue<4, NE>(sl, h * 8, bl, swap_bf16); hidden_epilogue<4, NE>(sl, h * 8 + 4, bl + 4, swap_bf16); }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t0 + s, l, s);
-          }
+          if (lane == 0) mbar_arrive(bar_a);
+          if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t, l, s);
         }
       }
-      // consume the output-layer phases of the last tile of each slot so the parities stay aligned across items
-#pragma unroll
-      for (int s = 0; s < 2; ++s)
-        if (s < n_tiles) {
-          mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
-          if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
-        }
+      // consume the output-layer phase of this slot's last tile so the parities stay aligned across items
+      if (s < n_tiles) {
+        mbar_wait(bar_f, ph_f0);
+        ph_f0 ^= 1;
+      }
     } else {
       // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
       // Global traffic is row-major with 8 lanes per 128-byte row segment ("transposed" layout: row = i*4 + tr, 16-byte chunk tc).
