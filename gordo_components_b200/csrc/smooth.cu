@@ -83,7 +83,37 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_median_kernel(const gb_job*
   }
 }
 
+// x'[r][c] = x[r][c] * a[slot][c] + b[slot][c] in double, rounded once to float: what sklearn's per-feature scalers compute
+// in float64 before Keras casts the batch to floatx.
+__global__ void affine_f64_kernel(const gb_job* __restrict__ jobs, const double* __restrict__ x, int n_cols, const double* __restrict__ a,
+                                  const double* __restrict__ b, float* __restrict__ out) {
+  const gb_job job = jobs[blockIdx.y];
+  const long total = (long)job.n_rows * n_cols;
+  const double* src = x + (long)job.x_row * n_cols;
+  float* dst = out + (long)job.out_row * n_cols;
+  const double* ja = a + (long)job.slot * n_cols;
+  const double* jb = b + (long)job.slot * n_cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % n_cols);
+    dst[i] = (float)(__dmul_rn(src[i], ja[c]) + jb[c]);  // two roundings like numpy's X *= scale; X += min (no fma contraction)
+  }
+}
+
 }  // namespace
+
+extern "C" int gb_affine_f64(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const double* x, int32_t n_cols, const double* a,
+                             const double* b, float* out, void* stream) {
+  GB_REQUIRE(jobs && x && a && b && out, GB_E_ARG, "jobs/x/a/b/out must be non-NULL");
+  GB_REQUIRE(n_cols >= 1 && max_rows >= 0, GB_E_ARG, "n_cols=%d max_rows=%d", n_cols, max_rows);
+  GB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535, GB_E_ARG, "bad n_jobs");
+  if (n_jobs == 0 || max_rows == 0) return GB_OK;
+  const long per_job = (long)max_rows * n_cols;
+  const int bx = (int)((per_job + 256L * 8 - 1) / (256L * 8));
+  const dim3 grid(bx < 1 ? 1 : (bx > 1184 ? 1184 : bx), n_jobs);
+  affine_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs, x, n_cols, a, b, out);
+  GB_CUDA_CHECK(cudaGetLastError());
+  return GB_OK;
+}
 
 extern "C" int gb_smooth(const gb_job* jobs, int32_t n_jobs, const float* arr, int32_t n_cols, int32_t window, int32_t method, float* out,
                          void* stream) {

@@ -251,6 +251,17 @@ def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_t
     return res
 
 
+def affine_f64(jobs_dev, n_jobs, max_rows, x64, a, b, out_rows=None):
+    """Per-feature ``x * a[slot] + b[slot]`` in float64 on the device, rounded once to float32 (sklearn scalers' transform)."""
+    torch = _torch()
+    lib = _cabi.load_library()
+    n_cols = x64.shape[1]
+    out = torch.empty((int(out_rows if out_rows is not None else x64.shape[0]), n_cols), dtype=torch.float32, device=x64.device)
+    p = _cabi.ptr
+    _cabi.check(lib.gb_affine_f64(p(jobs_dev), int(n_jobs), int(max_rows), p(x64), int(n_cols), p(a), p(b), p(out), _stream_ptr()))
+    return out
+
+
 SMOOTH_METHODS = {"smm": 0, "sma": 1, "ewma": 2}
 
 

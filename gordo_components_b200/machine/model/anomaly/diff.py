@@ -50,6 +50,41 @@ def _scaler_multiplier(scaler, n_features: int) -> np.ndarray:
     return slope.astype(np.float32)
 
 
+def _affine_of(step, n):
+    """(a, b) with step.transform(X) == X * a + b per feature, or None when the step is not a plain per-feature scaler."""
+    from sklearn.preprocessing import MaxAbsScaler, RobustScaler, StandardScaler
+
+    one, zero = np.ones(n, dtype=np.float64), np.zeros(n, dtype=np.float64)
+    try:
+        if type(step) is MinMaxScaler and not getattr(step, "clip", False):
+            a, b = np.asarray(step.scale_, dtype=np.float64), np.asarray(step.min_, dtype=np.float64)
+        elif type(step) is StandardScaler:
+            a = 1.0 / np.asarray(step.scale_, dtype=np.float64) if step.with_std else one
+            b = -np.asarray(step.mean_, dtype=np.float64) * a if step.with_mean else zero
+        elif type(step) is RobustScaler:
+            a = 1.0 / np.asarray(step.scale_, dtype=np.float64) if step.with_scaling else one
+            b = -np.asarray(step.center_, dtype=np.float64) * a if step.with_centering else zero
+        elif type(step) is MaxAbsScaler:
+            a, b = 1.0 / np.asarray(step.scale_, dtype=np.float64), zero
+        else:
+            return None
+    except AttributeError:  # not fitted: let the step raise its own NotFittedError on the host path
+        return None
+    if a.shape != (n,) or b.shape != (n,):
+        return None
+    return a, b
+
+
+def _compose_affine(steps, n):
+    a, b = np.ones(n, dtype=np.float64), np.zeros(n, dtype=np.float64)
+    for step in steps:
+        ab = _affine_of(step, n)
+        if ab is None:
+            return None
+        a, b = ab[0] * a, ab[0] * b + ab[1]
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
 class DiffBasedAnomalyDetector(AnomalyDetectorBase):
     def __init__(
         self,
@@ -190,14 +225,24 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         fused = estimator_owner._fused_target()
         if fused is not None and fused[1].model is not None:
             pre, ae = fused
-            Xt = X
-            for step in pre:
-                Xt = step.transform(Xt)
-            Xv = _values(Xt)
             eng = ae._engine()
-            n = len(Xv)
-            xd, yd = engine.to_device_f32(Xv, dev), engine.to_device_f32(yv, dev)
-            jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+            affine = _compose_affine(pre, eng.n_in)
+            if pre and affine is not None:
+                # per-feature scalers in front of the network: one f64 pass on the device (gb_affine_f64) instead of sklearn on the host
+                Xv = np.ascontiguousarray(_values(X), dtype=np.float64)
+                n = len(Xv)
+                jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+                a_d, b_d = (torch.from_numpy(v.reshape(1, -1)).to(dev) for v in affine)
+                xd = engine.affine_f64(jobs, 1, n, torch.from_numpy(Xv).to(dev), a_d, b_d) if n else torch.empty((0, eng.n_in), dtype=torch.float32, device=dev)
+            else:
+                Xt = X
+                for step in pre:
+                    Xt = step.transform(Xt)
+                Xv = _values(Xt)
+                n = len(Xv)
+                jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+                xd = engine.to_device_f32(Xv, dev)
+            yd = engine.to_device_f32(yv, dev)
             res = eng.infer_score(ae._device_params(), jobs, 1, n, xd, yd, scale_d, ft_d, at_d, want=want)
         else:
             pred = np.asarray(estimator_owner.predict(X) if hasattr(estimator_owner, "predict") else estimator_owner.transform(X))

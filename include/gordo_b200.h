@@ -139,6 +139,14 @@ int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const fl
 int gb_smooth(const gb_job* jobs, int32_t n_jobs, const float* arr, int32_t n_cols, int32_t window, int32_t method,
               float* out, void* stream);
 
+/* ---- K8: per-feature affine pre-transform (sklearn MinMaxScaler/StandardScaler/... .transform in front of the
+ * network inside a Pipeline: gordo serializer pipelines, e.g. examples/config_crd.yaml "sklearn.preprocessing.MinMaxScaler")
+ *   out[out_row+r][c] = (float)(x[x_row+r][c] * a[slot][c] + b[slot][c]), computed in double like sklearn and rounded once,
+ * i.e. exactly the float32 batch Keras sees.  (Folding a/b into the first Dense layer instead would cancel catastrophically
+ * in fp32 for offset-dominated tags, so the transform stays a separate f64 pass.) */
+int gb_affine_f64(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const double* x, int32_t n_cols, const double* a,
+                  const double* b, float* out, void* stream);
+
 /* ---- K2: fit ---------------------------------------------------------------------------
  * Replaces scikeras KerasRegressor.fit -> keras Model.fit (models.py:284) for the Dense
  * stacks above: per job, `epochs` passes over rows [x_row, x_row+n_rows) in batches of

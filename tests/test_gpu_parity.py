@@ -464,6 +464,41 @@ def test_lstm_estimator_predict_shapes(engine, torch):
         a.fit(X, X)
 
 
+@pytest.mark.parametrize("chain", ["minmax", "standard+minmax", "function"])
+def test_detector_with_scaler_pipeline(engine, torch, chain):
+    """Pipeline([scaler(s), KerasAutoEncoder]) as base estimator (the shape of gordo's example configs): raw, offset-dominated
+    tags; per-feature scalers run as one f64 pass on the device and must equal sklearn's float64 transform cast to float32."""
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import FunctionTransformer, MinMaxScaler, StandardScaler
+
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_components_b200.machine.model.models import KerasAutoEncoder
+    from oracle import anomaly_math as am
+    from oracle import keras_math as km
+
+    rng = np.random.default_rng(3)
+    n, T = 300, 8
+    t = np.linspace(0, 20, n)[:, None]
+    Xv = (1000.0 * np.arange(1, T + 1)) + np.sin(t * np.linspace(0.5, 2, T)) + rng.normal(0, 0.05, (n, T))  # range ~2 on offsets up to 8000
+    cols = [f"tag-{i}" for i in range(T)]
+    X = pd.DataFrame(Xv, columns=cols, index=pd.date_range("2019-01-01", periods=n, freq="10min", tz="UTC"))
+    steps = {"minmax": [MinMaxScaler()], "standard+minmax": [StandardScaler(), MinMaxScaler()],
+             "function": [MinMaxScaler(), FunctionTransformer(lambda v: v * 1.0)]}[chain]
+    pipe = Pipeline([(f"s{i}", s) for i, s in enumerate(steps)] + [("ae", KerasAutoEncoder(kind="feedforward_hourglass", epochs=2, batch_size=32))])
+    det = DiffBasedAnomalyDetector(base_estimator=pipe, require_thresholds=False)
+    det.fit(X, X)
+    frame = det.anomaly(X, X)
+    Xt = Xv
+    for s in steps:
+        Xt = s.transform(Xt)
+    spec = km.ff_hourglass_spec(T)
+    pred = km.ff_forward(spec, pipe.steps[-1][1].model.weights, np.asarray(Xt, dtype=np.float32), np.float64)
+    close(frame["model-output"].values, pred, name=f"pipeline[{chain}] model-output")
+    sc, mn = am.minmax_fit(Xv)
+    want = am.anomaly_arrays(pred, Xv, sc, mn)
+    close(frame["tag-anomaly-unscaled"].values, want["tag-anomaly-unscaled"], name="tag-anomaly-unscaled")
+
+
 def test_fleet_build_matches_per_machine_oracle(engine, torch):
     """build_fleet = CV folds + final fit + thresholds for all machines in one launch each; checked machine by machine against
     the oracle's fold geometry / scaler / threshold arithmetic applied to the weights the fleet trained."""
