@@ -35,5 +35,4 @@ t0 = rec[0][0]
 names = {1: 'ctrl wake(a_ready)', 2: 'ctrl committed', 3: 'epi X arrive', 4: 'epi wait d (hidden)', 5: 'epi woke d (hidden)', 6: 'epi arrive a (hidden)', 7: 'epi wait d (final)', 8: 'epi woke d (final)', 9: 'epi final done', 10: 'out: D read, d_free arrived', 12: 'out: stores issued'}
 print('events', len(rec))
 for clk, role, tile, layer, slot, code in rec[:400]:
-    if role in (0, 1) and code not in (2, 3): continue
     print(f"{clk - t0:8d}  role={role} tile={tile:2d} l={layer} s={slot}  {names.get(code, code)}")
