@@ -4,11 +4,15 @@
 // BASELINE workload).  The path is HBM-bound (1 548 algorithmic bytes and 30 236 FLOP per window => 128 TFLOP/s at
 // the measured 6.58 TB/s): fp32 CUDA cores (74 TFLOP/s peak) cannot keep up, the tensor cores can.
 //
-// Numerics: 1e-4 parity with the float32 reference forbids plain TF32 (2^-11 per operand).  Every layer is computed as
+// Numerics: 1e-4 parity with the float32 reference forbids plain TF32/FP16 (2^-11 per operand), so operands are split.
+// Layer 0 (x is raw data of any magnitude):
 //        D  =  A_lo*W_hi  +  A_hi*W_hi            (kind::tf32, A = A_hi + A_lo exactly, W_hi = W rounded to TF32)
 //           +  bf16(A)*bf16(W - W_hi)             (kind::f16, the 2^-11-sized correction needs only 8 bits)
-// accumulated in fp32 in TMEM: error ~2^-20 relative per product, while the bf16 correction image costs half the
-// shared memory of a TF32 one (the budget that lets the x boxes and output staging fit beside the weights).
+// Layers >= 1 (A = tanh(.) in [-1, 1], so FP16 cannot overflow): A = a1 + a2, W = w1 + w2 with a1 = fp16(A),
+// a2 = fp16(A - a1) and likewise for W (22 significant bits each):
+//        D  =  a2*w1  +  a1*w2  +  a1*w1          (kind::f16, products exact in the fp32 accumulator, dropped a2*w2 ~ 2^-22)
+// i.e. 3 MMAs per 16 values of K instead of 5 per 16 with the TF32 scheme, and 1 TMEM word per activation instead of 2.5.
+// Accumulation is fp32 in TMEM; measured error against the float64 oracle ~2e-6 absolute.
 //
 // One persistent CTA per SM: 8 epilogue warps + 1 control warp, TWO 128-row tiles in flight (TMEM slots 0/1).  Per work
 // item (job chunk) the slot's weights are split and laid out once in shared memory as UMMA K-major operands
@@ -25,7 +29,9 @@
 // Reference arithmetic replaced: keras Dense under Model.predict (gordo/machine/model/models.py:289-300) and
 // DiffBasedAnomalyDetector.anomaly (gordo/machine/model/anomaly/diff.py:350-385, 420-444).
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "gb_common.cuh"
 
 namespace {
@@ -40,17 +46,20 @@ constexpr int W = 64;                  // feature width this kernel is specialis
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
 constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, SLOT_COLS = 224, COL_DX = 448, TMEM_COLS = 512;
+// layers >= 1 keep their two packed-FP16 operand images (32 columns each) where layer 0's TF32-hi image was
+constexpr uint32_t COL_A1 = COL_AHI, COL_A2 = COL_AHI + 32;
 // COL_DX: spare accumulator (absolute column) that receives the OUTPUT layer of slot-1 tiles, so slot 1 can start its next
 // tile while the output warps are still busy with the previous pair (they drain slot 0's accumulator first)
 
 struct TcArgs {
   int n_layers, last_layer;  // layers actually evaluated: 0..last_layer (debug aid; == n_layers-1 in production)
-  int K[MAXL], N[MAXL], Np[MAXL], k8[MAXL], k16[MAXL], act[MAXL];
+  int K[MAXL], N[MAXL], Np[MAXL], n8[MAXL], k8[MAXL], k16[MAXL], act[MAXL];  // Np = N rounded up to 16 (MMA N), n8 = to 8 (columns evaluated)
   int whi_ofs[MAXL], wlo_ofs[MAXL], bias_ofs[MAXL];  // byte offsets into dynamic smem
   int pofs[MAXL];                                    // float offsets of W_l in the canonical parameter vector
   int w_bytes;                                       // bytes of the weight+bias region (zero-filled before staging)
+  int param_bytes, bulk_params;                      // parameter vector of one slot: bytes (multiple of 16) / 1 = fetch with one bulk copy
   int vec_ofs, xbox_ofs, stage_ofs, pair_ofs, bar_ofs;
-  int n_jobs, chunks_per_job, rows_per_chunk, flags;
+  int n_jobs, tiles_per_job, flags;
   long pstride;
   const float* params;
   const gb_job* jobs;
@@ -60,7 +69,7 @@ struct TcArgs {
   int trace_cap;
 };
 
-enum { FLAG_SWAP_BF16 = 1, FLAG_NO_STORES = 2 };  // debug aids (variant bits 8, 9)
+enum { FLAG_NO_STORES = 2 };  // debug aid (variant bit 9): skip the global stores of the output warps
 constexpr int DEFAULT_NE = 0;
 
 // debug timeline (gb_debug_set_trace): three recorder threads of CTA 0 (epilogue tid 0, the two control leaders) stamp
@@ -94,32 +103,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
-}
-// wait of a warp with slack (output warps): poll, then really sleep -- a spinning warp costs its scheduler ~5 issue slots per
-// poll, taken from the SFU-bound layer warps that share it (ncu: 19 % of all executed instructions were these polls)
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  while (!done) {
-    asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -229,9 +212,9 @@ __device__ __forceinline__ float tanh_from_scaled_fma(float t) {
 
 // NE: every NE-th element takes the 1-MUFU tanh (0: never) -- the knob that trades SFU against FMA-pipe load
 
-// split NC (16, 12 or 8) activations into the three A operands (TF32 hi, fp32 remainder, packed BF16) at column `col`
+// layer 0: split NC (16) inputs into the three A operands (TF32 hi, fp32 remainder, packed BF16) at column `col`
 template <int NC>
-__device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, const float* a, bool swap_bf16) {
+__device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, const float* a) {
   uint32_t hi[NC], lo[NC], bf[NC / 2];
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
@@ -241,7 +224,7 @@ __device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, co
   }
 #pragma unroll
   for (int i = 0; i < NC / 2; ++i) {
-    const __nv_bfloat162 p = swap_bf16 ? __floats2bfloat162_rn(a[2 * i + 1], a[2 * i]) : __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);  // low half = even k (the order the MMA expects)
     bf[i] = *reinterpret_cast<const uint32_t*>(&p);
   }
   constexpr int C8 = NC / 8, R4 = (NC % 8) / 4;  // NC = 8*C8 + 4*R4
@@ -256,6 +239,29 @@ __device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, co
     tmem_st4(slot_lane + COL_ALO + col + 8 * C8, lo + 8 * C8);
     tmem_st2(slot_lane + COL_ABF + ((col + 8 * C8) >> 1), bf + 4 * C8);
   }
+}
+
+// layers >= 1: split NC activations (|a| <= 1) into two packed-FP16 images a1 = fp16(a), a2 = fp16(a - a1)
+template <int NW>
+__device__ __forceinline__ void tmem_st_words(uint32_t taddr, const uint32_t* r) {  // NW in {2, 4, 6, 8}
+  if (NW == 8) tmem_st8(taddr, r);
+  if (NW == 6) { tmem_st4(taddr, r); tmem_st2(taddr + 4, r + 4); }
+  if (NW == 4) tmem_st4(taddr, r);
+  if (NW == 2) tmem_st2(taddr, r);
+}
+template <int NC>
+__device__ __forceinline__ void store_a_fp16(uint32_t slot_lane, int col, const float* a) {
+  uint32_t w1[NC / 2], w2[NC / 2];
+#pragma unroll
+  for (int i = 0; i < NC / 2; ++i) {
+    const __half2 h = __floats2half2_rn(a[2 * i], a[2 * i + 1]);  // low half = even k
+    const float2 f = __half22float2(h);
+    const __half2 r = __floats2half2_rn(a[2 * i] - f.x, a[2 * i + 1] - f.y);
+    w1[i] = *reinterpret_cast<const uint32_t*>(&h);
+    w2[i] = *reinterpret_cast<const uint32_t*>(&r);
+  }
+  tmem_st_words<NC / 2>(slot_lane + COL_A1 + (col >> 1), w1);
+  tmem_st_words<NC / 2>(slot_lane + COL_A2 + (col >> 1), w2);
 }
 
 template <int NC>
@@ -273,7 +279,7 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float* v) {
 // (activation is tanh by construction: gb_ffae_tc_supported admits only tanh hidden layers + linear output, so the
 // compiler sees straight-line code and interleaves the NC independent ex2/rcp chains)
 template <int NC, int NE>
-__device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, const float* bias, bool swap_bf16) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, const float* bias) {
   float v[NC];
   tmem_load_cols<NC>(slot_lane + COL_D + col0, v);
 #pragma unroll
@@ -285,7 +291,13 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, co
     for (int j = 0; j < 4; ++j)
       v[i + j] = (NE > 0 && ((i + j) % (NE > 0 ? NE : 1)) == 0) ? tanh_from_scaled_fma(t[j]) : tanh_from_scaled(t[j]);
   }
-  store_a_operands<NC>(slot_lane, col0, v, swap_bf16);
+  store_a_fp16<NC>(slot_lane, col0, v);
+}
+// the columns [c0, c0 + C1 + C2) of one warp, as two independent chunks (C2 may be 0)
+template <int C1, int C2, int NE>
+__device__ __forceinline__ void hidden_epilogue_pair(uint32_t slot_lane, int c0, const float* bias_all) {
+  hidden_epilogue<C1, NE>(slot_lane, c0, bias_all + c0);
+  if (C2 > 0) hidden_epilogue<(C2 > 0 ? C2 : 4), NE>(slot_lane, c0 + C1, bias_all + c0 + C1);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -306,10 +318,9 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t sbase = smem_u32(smem);
   // mbarriers, two of each (tile slot 0/1): x_full, a_ready, d_ready (hidden-layer MMAs), f_ready (output-layer MMAs), d_free
   const uint32_t bars = sbase + a.bar_ofs;
-  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64;
+  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64, BW = 80;  // BW: bulk copy of a slot's parameter vector
   const bool has_y = a.y != nullptr;
   const int L = a.last_layer + 1;
-  const bool swap_bf16 = (a.flags & FLAG_SWAP_BF16) != 0;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -319,6 +330,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       mbar_init(bars + BF + 8 * s, 1);
       mbar_init(bars + BE + 8 * s, OUT_WARPS);
     }
+    mbar_init(bars + BW, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI_WARPS) {
@@ -332,55 +344,91 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
   // phase parities (each role uses the subset it waits on)
-  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0;
+  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0, ph_w = 0;
   int cur_slot = -1;
-  const int n_items = a.n_jobs * a.chunks_per_job;
+  // Work split.  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so work items are as long as
+  // possible: whole jobs, dealt round-robin in waves of gridDim.x (neighbouring CTAs stream neighbouring jobs: cutting the whole
+  // fleet into gridDim.x distant ranges instead measured 18 % slower, the 148 x 9 far-apart streams thrash the TLB); the jobs of
+  // the last, partial wave are cut into gridDim.x equal contiguous tile ranges so that all CTAs finish together.
+  const int wave_jobs = (a.n_jobs / (int)gridDim.x) * (int)gridDim.x;
+  const long tail_total = (long)(a.n_jobs - wave_jobs) * a.tiles_per_job;
+  long g = tail_total * blockIdx.x / gridDim.x;
+  const long g_end = tail_total * (blockIdx.x + 1) / gridDim.x;
+  int next_wave_job = blockIdx.x;
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int job_id = item / a.chunks_per_job, chunk = item - job_id * a.chunks_per_job;
+  while (true) {
+    int job_id, tile_begin, tile_end;
+    if (next_wave_job < wave_jobs) {
+      job_id = next_wave_job;
+      tile_begin = 0;
+      tile_end = a.tiles_per_job;
+      next_wave_job += gridDim.x;
+    } else if (g < g_end) {
+      job_id = wave_jobs + (int)(g / a.tiles_per_job);
+      tile_begin = (int)(g - (long)(job_id - wave_jobs) * a.tiles_per_job);
+      tile_end = (int)min((long)a.tiles_per_job, tile_begin + (g_end - g));
+      g += tile_end - tile_begin;
+    } else {
+      break;
+    }
     const gb_job job = a.jobs[job_id];
-    const int row_begin = chunk * a.rows_per_chunk;
+    const int row_begin = tile_begin * TILE;
     if (row_begin >= job.n_rows) continue;  // uniform across the CTA
-    const int row_end = min(job.n_rows, row_begin + a.rows_per_chunk);
+    const int row_end = min(job.n_rows, tile_end * TILE);
     const int n_tiles = (row_end - row_begin + TILE - 1) / TILE;
 
-    // ---- stage this slot's weights: split to TF32-hi / BF16-lo and lay out as UMMA K-major operands ------------
+    // ---- stage this slot's weights: split (layer 0: TF32-hi / BF16-lo, others: FP16 + FP16) and lay out as UMMA K-major operands
     if (job.slot != cur_slot) {
       cur_slot = job.slot;
       const float* P = a.params + (long)job.slot * a.pstride;
+      // The whole parameter vector comes in with ONE bulk copy into the (idle between work items) x-box + staging area and is
+      // re-laid-out from shared memory: staging layer by layer straight from global memory was a chain of exposed load
+      // latencies (~23 us per work item, measured).  Unaligned or oversized parameter vectors take per-element loads.
+      float* scratch = reinterpret_cast<float*>(smem + a.xbox_ofs);
+      if (a.bulk_params) {
+        if (tid == 0) {
+          mbar_expect_tx(bars + BW, (uint32_t)a.param_bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(scratch)), "l"(P),
+                       "r"((uint32_t)a.param_bytes), "r"(bars + BW)
+                       : "memory");
+        }
+      } else {
+        for (int i = tid; i < a.param_bytes / 4; i += NTHREADS) scratch[i] = __ldg(P + i);
+      }
+      const float v_scale = (tid < W && a.scale) ? __ldg(a.scale + (long)job.slot * W + tid) : 0.f;
+      const float v_thr = (tid < W && a.feat_thr) ? __ldg(a.feat_thr + (long)job.slot * W + tid) : 1.f;
       for (int i = tid; i < a.w_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
       __syncthreads();
+      if (a.bulk_params) {
+        mbar_wait(bars + BW, ph_w);
+        ph_w ^= 1;
+      }
       for (int l = 0; l < L; ++l) {
         const int K = a.K[l], N = a.N[l], Np = a.Np[l], KN = K * N;
-        const float* Wg = P + a.pofs[l];
+        const float* Ws = scratch + a.pofs[l];
         float* whi = reinterpret_cast<float*>(smem + a.whi_ofs[l]);
         __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>(smem + a.wlo_ofs[l]);
-        for (int base = 0; base < KN; base += 4 * NTHREADS) {
-          float w[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {  // four independent loads in flight per thread
-            const int idx = base + u * NTHREADS + tid;
-            w[u] = idx < KN ? __ldg(Wg + idx) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * NTHREADS + tid;
-            if (idx < KN) {
-              const int k = idx / N, n = idx - k * N;
-              const float hi = __uint_as_float((__float_as_uint(w[u]) + 0x1000u) & 0xffffe000u);  // round to nearest TF32
-              whi[((k >> 2) * Np + n) * 4 + (k & 3)] = hi;
-              wlo[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2bfloat16_rn(w[u] - hi);
-            }
+        for (int idx = tid; idx < KN; idx += NTHREADS) {
+          const float w = Ws[idx];
+          const int k = idx / N, n = idx - k * N;
+          if (l == 0) {
+            const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);  // round to nearest TF32
+            whi[((k >> 2) * Np + n) * 4 + (k & 3)] = hi;
+            wlo[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2bfloat16_rn(w - hi);
+          } else {  // two FP16 images, both [K/8][Np][8]
+            const __half w1 = __float2half_rn(w);
+            reinterpret_cast<__half*>(whi)[((k >> 3) * Np + n) * 8 + (k & 7)] = w1;
+            reinterpret_cast<__half*>(wlo)[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2half_rn(w - __half2float(w1));
           }
         }
         float* bl = reinterpret_cast<float*>(smem + a.bias_ofs[l]);
         const float bscale = (l + 1 < L) ? TANH_ARG_SCALE : 1.0f;  // hidden layers: bias folded into the tanh argument scale
-        for (int n = tid; n < N; n += NTHREADS) bl[n] = __ldg(Wg + KN + n) * bscale;
+        for (int n = tid; n < N; n += NTHREADS) bl[n] = Ws[KN + n] * bscale;
       }
       float* vec = reinterpret_cast<float*>(smem + a.vec_ofs);  // [0,64): scale, [64,128): 1/feat_thr
-      for (int j = tid; j < W; j += NTHREADS) {
-        vec[j] = a.scale ? __ldg(a.scale + (long)job.slot * W + j) : 0.f;
-        vec[W + j] = a.feat_thr ? 1.0f / __ldg(a.feat_thr + (long)job.slot * W + j) : 0.f;
+      if (tid < W) {
+        vec[tid] = v_scale;
+        vec[W + tid] = a.feat_thr ? 1.0f / v_thr : 0.f;
       }
       fence_proxy_async();  // generic-proxy writes above are read by the tensor core (async proxy)
     }
@@ -404,7 +452,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       for (int t = s; t < n_tiles; t += 2) {
         for (int l = 0; l < L; ++l) {
           const int Np = a.Np[l], k8 = a.k8[l], k16 = a.k16[l];
-          const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(1, Np);
+          const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(l == 0 ? 1 : 0, Np);  // kind::f16 inputs: BF16 (layer 0) / FP16
           const uint32_t lbo = (uint32_t)Np * 16u;
           const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
           const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);
@@ -426,15 +474,27 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
               tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
             }
             // straight-line issue (K <= 64 => at most 8 / 8 / 4 steps): measured 49 cycles per MMA against 73 for a rolled loop
+            if (l == 0) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // A_lo * W_hi (first MMA overwrites the accumulator)
-              if (ks < k8) mma_tf32_ts(dcol, tb + COL_ALO + ks * 8, dhi + (uint64_t)(ks * dstep), id32, ks > 0);
+              for (int ks = 0; ks < 8; ++ks)  // A_lo * W_hi (first MMA overwrites the accumulator)
+                if (ks < k8) mma_tf32_ts(dcol, tb + COL_ALO + ks * 8, dhi + (uint64_t)(ks * dstep), id32, ks > 0);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi
-              if (ks < k8) mma_tf32_ts(dcol, tb + COL_AHI + ks * 8, dhi + (uint64_t)(ks * dstep), id32, 1);
+              for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi
+                if (ks < k8) mma_tf32_ts(dcol, tb + COL_AHI + ks * 8, dhi + (uint64_t)(ks * dstep), id32, 1);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)  // bf16(A) * bf16(W_lo)
-              if (ks < k16) mma_bf16_ts(dcol, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+              for (int ks = 0; ks < 4; ++ks)  // bf16(A) * bf16(W_lo)
+                if (ks < k16) mma_bf16_ts(dcol, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)  // a2 * w1 (first MMA overwrites the accumulator)
+                if (ks < k16) mma_bf16_ts(dcol, tb + COL_A2 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, ks > 0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)  // a1 * w2
+                if (ks < k16) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)  // a1 * w1
+                if (ks < k16) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, 1);
+            }
             if (l + 1 < L) {
               mma_commit(bar_d);
             } else {
@@ -447,40 +507,12 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       }
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
-      // =========================================== layer-epilogue warps (SFU-bound): x split + hidden layers
+      // =========================================== layer-epilogue warps (SFU-bound): hidden layers only
       for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-        // ---- x -> A operand of layer 0 ----------------------------------------------------------------------------
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (t0 + s >= n_tiles) continue;
-          if (t0 >= 2) {  // the previous tile's output-layer MMA has finished reading this slot's A regions
-            mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
-            if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
-          }
-          const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-          mbar_wait(bars + BX + 8 * s, s ? ph_x1 : ph_x0);
-          if (s) ph_x1 ^= 1; else ph_x0 ^= 1;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float v[16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t addr = xbox + ((uint32_t)((half * 4 + c) ^ (row & 7)) << 4);
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
-            }
-            store_a_operands<16>(lane_base + s * SLOT_COLS, h * 32 + half * 16, v, swap_bf16);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-          if (tid == 0) trace_ev(a, ring, trace_cnt, 3, t0 + s, 0, s);
-        }
-
-        // ---- hidden layers: D -> bias, activation -> next A operand (tile s' epilogue overlaps tile 1-s' MMAs) ------------
+        // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
         for (int l = 0; l + 1 < L; ++l) {
-          const int half = a.Np[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), processed in two chunks
-          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]) + h * half;
+          const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
+          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             if (t0 + s >= n_tiles) continue;
@@ -490,10 +522,22 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             tc_fence_after();
             if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
             const uint32_t sl = lane_base + s * SLOT_COLS;
-            if (half == 32) { hidden_epilogue<16, NE>(sl, h * 32, bl, swap_bf16); hidden_epilogue<16, NE>(sl, h * 32 + 16, bl + 16, swap_bf16); }
-            else if (half == 24) { hidden_epilogue<12, NE>(sl, h * 24, bl, swap_bf16); hidden_epilogue<12, NE>(sl, h * 24 + 12, bl + 12, swap_bf16); }
-            else if (half == 16) { hidden_epilogue<8, NE>(sl, h * 16, bl, swap_bf16); hidden_epilogue<8, NE>(sl, h * 16 + 8, bl + 8, swap_bf16); }
-            else { hidden_epilogue<4, NE>(sl, h * 8, bl, swap_bf16); hidden_epilogue<4, NE>(sl, h * 8 + 4, bl + 4, swap_bf16); }
+            const int c0 = h * half;
+            switch (half) {
+              case 32: hidden_epilogue_pair<16, 16, NE>(sl, c0, bl); break;
+              case 28: hidden_epilogue_pair<16, 12, NE>(sl, c0, bl); break;
+              case 24: hidden_epilogue_pair<12, 12, NE>(sl, c0, bl); break;
+              case 20: hidden_epilogue_pair<12, 8, NE>(sl, c0, bl); break;
+              case 16: hidden_epilogue_pair<8, 8, NE>(sl, c0, bl); break;
+              case 12: hidden_epilogue_pair<8, 4, NE>(sl, c0, bl); break;
+              case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
+              default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
+            }
+            if (h == 1 && a.n8[l] < a.Np[l]) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
+              const uint32_t z[4] = {0u, 0u, 0u, 0u};
+              tmem_st4(sl + COL_A1 + (a.n8[l] >> 1), z);
+              tmem_st4(sl + COL_A2 + (a.n8[l] >> 1), z);
+            }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -502,20 +546,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
       }
-      // consume the output-layer phases of the last tile of each slot so the parities stay aligned across items
-#pragma unroll
-      for (int s = 0; s < 2; ++s)
-        if (s < n_tiles) {
-          mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
-          if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
-        }
     } else {
       // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
       // Global traffic is row-major with 8 lanes per 128-byte row segment ("transposed" layout: row = i*4 + tr, 16-byte chunk tc).
       // Only the accumulator has to change layout (TMEM gives one thread = one row): it goes once through this warp's swizzled
       // staging box; y is loaded straight into the transposed layout and every output column is formed and stored there.
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * OBOX_BYTES;
+      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * 2 * OBOX_BYTES;  // transpose staging of the accumulator
+      const uint32_t ybox = stage + OBOX_BYTES;                                           // y rows of the second tile of a pair
       float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2 halves][2][TILE] row sums
       const int tr = lane >> 3, tc = lane & 7;
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
@@ -524,50 +562,63 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const float inv_w = 1.0f / (float)W;
       const bool totals = has_y && (a.o_tots || a.o_totu || a.o_totconf);
 
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t & 1;
+      // x -> A operand of layer 0 of tile `tt` (slot tt & 1): these warps have the slack, the layer warps do not
+      auto split_x = [&](int tt) {
+        const int s = tt & 1;
+        const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
+        mbar_wait(bars + BX + 8 * s, s ? ph_x1 : ph_x0);
+        if (s) ph_x1 ^= 1; else ph_x0 ^= 1;
+#pragma unroll
+        for (int piece = 0; piece < 4; ++piece) {  // 8 columns at a time keeps the register footprint small (y rows are live)
+          float v[8];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t addr = xbox + ((uint32_t)((piece * 2 + c) ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
+          }
+          store_a_operands<8>(lane_base + s * SLOT_COLS, h * 32 + piece * 8, v);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+        if (lane == 0 && warp == MAIN_WARPS) trace_ev(a, ring, trace_cnt, 3, tt, 0, s);
+      };
+      // accumulator of the output layer -> this warp's staging box ("one thread = one row" -> row-major lines), accumulator freed
+      auto park = [&](int s, int t) {
+        float acc[32];
+        const uint32_t sl = lane_base + (s == 1 ? COL_DX : COL_D) + h * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_wait_ld8(acc + 8 * c);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BE + 8 * s);  // the slot's accumulator may be overwritten by the next tile
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 10, t, L - 1, s);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = stage + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(acc[4 * c]), "f"(acc[4 * c + 1]), "f"(acc[4 * c + 2]), "f"(acc[4 * c + 3]) : "memory");
+        }
+        __syncwarp();
+      };
+      float4 yt[8];
+      // every output column of tile t from the staged accumulator; y comes from registers (first tile of a pair) or from the
+      // warp's y box in shared memory (second tile, fetched with cp.async while the first was being written)
+      auto emit = [&](int t, bool y_smem) {
         const int trow = row_begin + t * TILE;
         const int nrows = min(TILE, row_end - trow);
         const long grow0 = job.out_row + trow;
         const int wrow0 = q * 32;
-        float4 yt[8];
-        if (has_y) {  // requested before the accumulator is ready
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = min(wrow0 + i * 4 + tr, nrows - 1);
-            yt[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + h * 32) + tc);
-          }
-        }
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t, L - 1, s);
-        mbar_wait_relaxed(bars + BF + 8 * s, s ? ph_f1 : ph_f0, (uint32_t)(((a.flags >> 2) & 3) | (((a.flags >> 6) & 3) << 2)) * 32u);
-        if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
-        tc_fence_after();
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
-        {
-          float acc[32];
-          const uint32_t sl = lane_base + (s == 1 ? COL_DX : COL_D) + h * 32;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_wait_ld8(acc + 8 * c);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars + BE + 8 * s);  // the slot's accumulator may be overwritten by the next tile
-          if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 10, t, L - 1, s);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t addr = stage + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(acc[4 * c]), "f"(acc[4 * c + 1]), "f"(acc[4 * c + 2]), "f"(acc[4 * c + 3]) : "memory");
-          }
-        }
-        __syncwarp();
         float ss[8], su[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + tr;
-          float4 yh;
+          float4 yh, yv = yt[i];
           const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
+          if (y_smem) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yv.x), "=f"(yv.y), "=f"(yv.z), "=f"(yv.w) : "r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u));
           yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
           const bool live = wrow0 + r < nrows && !(a.flags & FLAG_NO_STORES);
           const long g = (grow0 + wrow0 + r) * (long)W + h * 32 + tc * 4;
@@ -575,7 +626,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           ss[i] = 0.f; su[i] = 0.f;
           if (has_y) {
             float4 d, e;
-            d.x = fabsf(yh.x - yt[i].x); d.y = fabsf(yh.y - yt[i].y); d.z = fabsf(yh.z - yt[i].z); d.w = fabsf(yh.w - yt[i].w);
+            d.x = fabsf(yh.x - yv.x); d.y = fabsf(yh.y - yv.y); d.z = fabsf(yh.z - yv.z); d.w = fabsf(yh.w - yv.w);
             su[i] = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
             if (live && a.o_tu) *reinterpret_cast<float4*>(a.o_tu + g) = d;
             e.x = d.x * sc4.x; e.y = d.y * sc4.y; e.z = d.z * sc4.z; e.w = d.w * sc4.w;
@@ -585,7 +636,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
         __syncwarp();  // staging box reusable
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, s);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t & 1);
         if (totals) {
           // row sums: 8 lanes (tc) hold the 32 columns of this half; halves meet in shared memory
 #pragma unroll
@@ -609,9 +660,59 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
           named_bar_sync(1 + q, 64);
         }
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, s);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t & 1);
+      };
+
+      split_x(0);
+      if (n_tiles > 1) split_x(1);
+
+      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
+        const bool two = t0 + 1 < n_tiles;
+        if (has_y) {
+          if (two) {  // y rows of the pair's second tile -> y box (asynchronously; needed only after the first tile is written)
+            const int trow = row_begin + (t0 + 1) * TILE;
+            const int nrows = min(TILE, row_end - trow);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + tr;
+              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)W + h * 32 + tc * 4;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
+          const int trow = row_begin + t0 * TILE;
+          const int nrows = min(TILE, row_end - trow);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // y rows of the first tile -> registers, requested before its accumulator is ready
+            const int r = min(q * 32 + i * 4 + tr, nrows - 1);
+            yt[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + h * 32) + tc);
+          }
+        }
+        // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed both slots their next tiles
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t0, L - 1, 0);
+        mbar_wait(bars + BF, ph_f0);
+        ph_f0 ^= 1;
+        tc_fence_after();
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0, L - 1, 0);
+        park(0, t0);
+        if (t0 + 2 < n_tiles) split_x(t0 + 2);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
+        if (two) {
+          mbar_wait(bars + BF + 8, ph_f1);
+          ph_f1 ^= 1;
+          tc_fence_after();
+          if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0 + 1, L - 1, 1);
+          if (t0 + 3 < n_tiles) split_x(t0 + 3);  // slot 1's output sits in the spare accumulator until the stores below are done
+        }
+        // ---- then the stores
+        emit(t0, false);
+        if (two) {
+          park(1, t0 + 1);
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          emit(t0 + 1, true);
+        }
       }
     }
+    fence_proxy_async();  // this item's generic accesses to the x boxes / staging precede the next item's bulk copy and TMA loads
     __syncthreads();
   }
 
@@ -706,13 +807,14 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
     a.K[l] = net->dims[l];
     a.N[l] = net->dims[l + 1];
     a.Np[l] = gb::round_up(a.N[l], 16);
+    a.n8[l] = gb::round_up(a.N[l], 8);
     a.k8[l] = gb::round_up(a.K[l], 8) / 8;
     a.k16[l] = gb::round_up(a.K[l], 16) / 16;
     a.act[l] = net->act[l];
     a.pofs[l] = pofs;
     pofs += a.K[l] * a.N[l] + a.N[l];
-    a.whi_ofs[l] = ofs;
-    ofs += a.k8[l] * 8 * a.Np[l] * 4;
+    a.whi_ofs[l] = ofs;  // layer 0: TF32 image [K/4][Np][4] + BF16 image [K/8][Np][8]; layers >= 1: two FP16 images [K/8][Np][8]
+    ofs += l == 0 ? a.k8[l] * 8 * a.Np[l] * 4 : a.k16[l] * 16 * a.Np[l] * 2;
     a.wlo_ofs[l] = ofs;
     ofs += a.k16[l] * 16 * a.Np[l] * 2;
   }
@@ -727,7 +829,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.bar_ofs = ofs; ofs += 128;
   ofs = gb::round_up(ofs, 1024);
   a.xbox_ofs = ofs; ofs += 4 * BOX_BYTES;            // two tile slots x two 32-column boxes
-  a.stage_ofs = ofs; ofs += OUT_WARPS * OBOX_BYTES;  // one 32-row x 32-column staging box per output warp
+  a.stage_ofs = ofs; ofs += OUT_WARPS * 2 * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box + a y box of the same shape
   const size_t smem = (size_t)ofs;
   GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
 
@@ -735,14 +837,12 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   GB_CUDA_CHECK(cudaGetDevice(&dev));
   GB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles_per_job = (max_rows + TILE - 1) / TILE;
-  int tiles_per_chunk = tiles_per_job;
-  // enough work items for every SM, long enough chunks to amortise the weight staging (~16 tiles)
-  while (tiles_per_chunk > 16 && (long)n_jobs * ((tiles_per_job + tiles_per_chunk - 1) / tiles_per_chunk) < 4L * sms) tiles_per_chunk = (tiles_per_chunk + 1) / 2;
-  if (tiles_per_chunk > 32) tiles_per_chunk = 32;
-  a.rows_per_chunk = tiles_per_chunk * TILE;
-  a.chunks_per_job = (tiles_per_job + tiles_per_chunk - 1) / tiles_per_chunk;
+  a.tiles_per_job = tiles_per_job;
   a.n_jobs = n_jobs;
   a.pstride = (long)gb_ffnet_param_stride(net);
+  a.param_bytes = (int)(gb_ffnet_param_stride(net) * sizeof(float));  // stride is a multiple of 4 floats
+  GB_REQUIRE(a.param_bytes <= 4 * BOX_BYTES + OUT_WARPS * 2 * OBOX_BYTES, GB_E_SMEM, "parameter vector of %d bytes exceeds the staging scratch", a.param_bytes);
+  a.bulk_params = (reinterpret_cast<uintptr_t>(params) % 16 == 0) ? 1 : 0;
   a.params = params; a.jobs = jobs; a.y = y; a.scale = scale; a.feat_thr = feat_thr; a.agg_thr = agg_thr;
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_conf = out_conf;
   a.o_tots = out_total_scaled; a.o_totu = out_total_unscaled; a.o_totconf = out_total_conf;
@@ -751,18 +851,14 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   CUtensorMap mx;
   if ((rc = make_map(&mx, x, n_x_rows, TILE)) != GB_OK) return rc;
 
-  const long items = (long)n_jobs * a.chunks_per_job;
-  const int grid = (int)(items < sms ? items : sms);
-  const int ne_sel = (flags >> 4) & 3;  // debug knob: share of tanh evaluations that take the 1-MUFU form
+  const long g_total = (long)n_jobs * tiles_per_job;
+  const int grid = (int)(g_total < sms ? g_total : sms);
   auto launch = [&](auto kern) -> int {
     GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx);
     return GB_OK;
   };
-  if (ne_sel == 1) rc = launch(ffae_tc_kernel<2>);
-  else if (ne_sel == 2) rc = launch(ffae_tc_kernel<3>);
-  else if (ne_sel == 3) rc = launch(ffae_tc_kernel<4>);
-  else rc = launch(ffae_tc_kernel<DEFAULT_NE>);
+  rc = launch(ffae_tc_kernel<DEFAULT_NE>);  // NE = 2..4 (part of the tanh evaluations on the FMA pipe) measured 1-5 % slower
   if (rc != GB_OK) return rc;
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
