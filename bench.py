@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 
 T = 64
 BYTES_PER_WINDOW = 4 * T + 4 * T + 4 * 4 * T + 12  # read x, y; write model-output, 2 tag-anomaly blocks, confidence; 3 row scalars
-NCU_DRAM_BYTES_PER_WINDOW = {"tcgen05": (1.575724e9 + 3.054456e9) / 3.0e6, "fma": (1.037003e9 + 2.019607e9) / 2.0e6}
+NCU_DRAM_BYTES_PER_WINDOW = {"tcgen05": (1.563999e9 + 3.071377e9) / 3.0e6, "fma": (1.037003e9 + 2.019607e9) / 2.0e6}
 METRIC = "anomaly windows/sec (64-tag feedforward_hourglass AE, 1k machines x 10k rows per GPU, fused predict+score)"
 
 
@@ -279,7 +279,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          # dram__bytes_read+write per window from the committed ncu --set full capture of this kernel, times the windows of one launch
                          "traffic": int(M * R * NCU_DRAM_BYTES_PER_WINDOW[eng_variant_name(args.variant, eng)]),
-                         "traffic_source": "profiles/r01_ffae_tc_v8_ncu.txt / profiles/r01_ffae_infer_fma_ncu.txt (300- / 200-machine captures, per window)", "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "algorithmic_bytes_per_window": BYTES_PER_WINDOW,
+                         "traffic_source": "profiles/r01_ffae_tc_v12_ncu.txt / profiles/r01_ffae_infer_fma_ncu.txt (300- / 200-machine captures, per window)", "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "algorithmic_bytes_per_window": BYTES_PER_WINDOW,
                          "kernel_ms_mean": float(np.mean(per_launch_ms)), "kernel_ms_min": float(np.min(per_launch_ms))},
             "cpu_baseline": {"value": cpu_v1, "unit": "windows/s", "cores": 1, "kind": "port",
                              "sample": f"2 machines x {R} rows, NumPy oracle (batch-32 predict loop + diff.py arithmetic), {cpu_dt1:.1f} s"},

@@ -7,7 +7,7 @@ from oracle import keras_math as km
 spec = km.ff_hourglass_spec(64)
 eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
 dev = eng.device
-M, R = 148, 128 * 16
+M, R = int(os.environ.get('TR_M', 148)), 128 * int(os.environ.get('TR_TILES', 16))
 g = torch.Generator(device=dev).manual_seed(0)
 x = torch.rand((M * R, 64), generator=g, device=dev); y = x.clone()
 params = fleet.random_glorot_params(eng, M, g)
@@ -17,13 +17,15 @@ out = {}
 for _ in range(3): eng.infer_score(params, jobs, M, R, x, y, scale, feat, agg, out=out)
 torch.cuda.synchronize()
 SLOTS = 320
-buf = torch.zeros(4 + 4 * SLOTS, dtype=torch.int64, device=dev)
+buf = torch.zeros(8 + 4 * SLOTS, dtype=torch.int64, device=dev)
 lib = _cabi.load_library()
 lib.gb_debug_set_trace(C.c_void_p(buf.data_ptr()), SLOTS)
 eng.infer_score(params, jobs, M, R, x, y, scale, feat, agg, out=out)
 torch.cuda.synchronize()
 lib.gb_debug_set_trace(None, 0)
 b = buf.cpu().numpy()
+c0, c1, n0, n1 = [int(v) for v in b[4 + 4 * SLOTS: 8 + 4 * SLOTS]]
+print(f'kernel: {c1 - c0} cycles in {n1 - n0} ns -> {(c1 - c0) / max(1, n1 - n0):.3f} GHz')
 rec = []
 for role in range(4):
     n = int(b[role])
@@ -32,7 +34,7 @@ for role in range(4):
         rec.append((v >> 24, role, (v >> 12) & 0xfff, (v >> 8) & 0xf, (v >> 4) & 0xf, v & 0xf))
 rec.sort()
 t0 = rec[0][0]
-names = {1: 'ctrl wake(a_ready)', 2: 'ctrl committed', 3: 'epi X arrive', 4: 'epi wait d (hidden)', 5: 'epi woke d (hidden)', 6: 'epi arrive a (hidden)', 7: 'epi wait d (final)', 8: 'epi woke d (final)', 9: 'epi final done', 10: 'out: D read, d_free arrived', 12: 'out: stores issued'}
+names = {1: 'ctrl wake(a_ready)', 2: 'ctrl committed', 3: 'epi X arrive', 4: 'epi wait d (hidden)', 5: 'epi woke d (hidden)', 6: 'epi arrive a (hidden)', 7: 'epi wait d (final)', 8: 'epi woke d (final)', 9: 'epi final done', 10: 'out: D read, d_free arrived', 12: 'out: stores issued', 13: 'ITEM START', 14: 'ITEM staged'}
 print('events', len(rec))
 for clk, role, tile, layer, slot, code in rec[:400]:
     print(f"{clk - t0:8d}  role={role} tile={tile:2d} l={layer} s={slot}  {names.get(code, code)}")

@@ -54,6 +54,8 @@ constexpr uint32_t COL_A1 = COL_AHI, COL_A2 = COL_AHI + 32;
 struct TcArgs {
   int n_layers, last_layer;  // layers actually evaluated: 0..last_layer (debug aid; == n_layers-1 in production)
   int K[MAXL], N[MAXL], Np[MAXL], n8[MAXL], k8[MAXL], k16[MAXL], act[MAXL];  // Np = N rounded up to 16 (MMA N), n8 = to 8 (columns evaluated)
+  int colsA[MAXL];   // hidden layer l: its first colsA[l] output columns are announced early (barrier BP) so that the next layer's
+  int ksplit[MAXL];  // first ksplit[l+1] K-steps can be issued while the remaining columns are still being evaluated (0: one piece)
   int whi_ofs[MAXL], wlo_ofs[MAXL], bias_ofs[MAXL];  // byte offsets into dynamic smem
   int pofs[MAXL];                                    // float offsets of W_l in the canonical parameter vector
   int w_bytes;                                       // bytes of the weight+bias region (zero-filled before staging)
@@ -293,6 +295,15 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t slot_lane, int col0, co
   }
   store_a_fp16<NC>(slot_lane, col0, v);
 }
+template <int NE>
+__device__ __forceinline__ void hidden_epilogue_n(int nc, uint32_t slot_lane, int c0, const float* bias_all) {  // nc in {4, 8, 12, 16}
+  switch (nc) {
+    case 16: hidden_epilogue<16, NE>(slot_lane, c0, bias_all + c0); break;
+    case 12: hidden_epilogue<12, NE>(slot_lane, c0, bias_all + c0); break;
+    case 8: hidden_epilogue<8, NE>(slot_lane, c0, bias_all + c0); break;
+    default: hidden_epilogue<4, NE>(slot_lane, c0, bias_all + c0); break;
+  }
+}
 // the columns [c0, c0 + C1 + C2) of one warp, as two independent chunks (C2 may be 0)
 template <int C1, int C2, int NE>
 __device__ __forceinline__ void hidden_epilogue_pair(uint32_t slot_lane, int c0, const float* bias_all) {
@@ -324,7 +335,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t sbase = smem_u32(smem);
   // mbarriers, two of each (tile slot 0/1): x_full, a_ready, d_ready (hidden-layer MMAs), f_ready (output-layer MMAs), d_free
   const uint32_t bars = sbase + a.bar_ofs;
-  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64, BW = 80;  // BW: bulk copy of a slot's parameter vector
+  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64, BW = 80, BP = 88;  // BW: bulk copy of a slot's parameters; BP[2]: first part of a layer's A operand ready
   const bool has_y = a.y != nullptr;
   const int L = a.last_layer + 1;
 
@@ -337,6 +348,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       mbar_init(bars + BE + 8 * s, OUT_WARPS);
     }
     mbar_init(bars + BW, 1);
+    mbar_init(bars + BP, MAIN_WARPS);
+    mbar_init(bars + BP + 8, MAIN_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI_WARPS) {
@@ -350,7 +363,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
   // phase parities (each role uses the subset it waits on)
-  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0, ph_w = 0;
+  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0, ph_w = 0, ph_p = 0;
   int cur_slot = -1;
   // Work split.  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so work items are as long as
   // possible: whole jobs, dealt round-robin in waves of gridDim.x (neighbouring CTAs stream neighbouring jobs: cutting the whole
@@ -471,8 +484,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           const uint32_t lbo = (uint32_t)Np * 16u;
           const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
           const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);
-          mbar_wait(bar_a, ph_a);
-          ph_a ^= 1;
+          const int kA = a.ksplit[l];  // > 0: the A operand arrives in two parts, K-steps [0, kA) first
+          if (kA > 0) {
+            mbar_wait(bars + BP + 8 * s, ph_p);
+            ph_p ^= 1;
+          } else {
+            mbar_wait(bar_a, ph_a);
+            ph_a ^= 1;
+          }
           // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
           // layer (wait before layer 0); slot 1 sends only its output layer to the spare accumulator (wait before that layer)
           if (t >= 2 && l == (s == 0 ? 0 : L - 1)) {
@@ -500,16 +519,36 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
               for (int ks = 0; ks < 4; ++ks)  // bf16(A) * bf16(W_lo)
                 if (ks < k16) mma_bf16_ts(dcol, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
             } else {
+              const int k_now = kA > 0 ? kA : k16;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)  // a2 * w1 (first MMA overwrites the accumulator)
-                if (ks < k16) mma_bf16_ts(dcol, tb + COL_A2 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, ks > 0);
+                if (ks < k_now) mma_bf16_ts(dcol, tb + COL_A2 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, ks > 0);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)  // a1 * w2
-                if (ks < k16) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+                if (ks < k_now) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)  // a1 * w1
-                if (ks < k16) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, 1);
+                if (ks < k_now) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, 1);
             }
+          }
+          if (kA > 0) {  // the rest of the operand: K-steps [kA, k16), issued while nothing else is pending for this slot
+            __syncwarp();
+            mbar_wait(bar_a, ph_a);
+            ph_a ^= 1;
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks)
+                if (ks >= kA && ks < k16) mma_bf16_ts(dcol, tb + COL_A2 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, 1);
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks)
+                if (ks >= kA && ks < k16) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks)
+                if (ks >= kA && ks < k16) mma_bf16_ts(dcol, tb + COL_A1 + ks * 8, dhi + (uint64_t)(ks * dstep), id16, 1);
+            }
+          }
+          if (leader) {
             if (l + 1 < L) {
               mma_commit(bar_d);
             } else {
@@ -526,7 +565,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       for (int t0 = 0; t0 < n_tiles; t0 += 2) {
         // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
         for (int l = 0; l + 1 < L; ++l) {
-          const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
+          // columns of this warp: [h*cA, (h+1)*cA) of the first part and [colsA + h*cB, colsA + (h+1)*cB) of the second
+          const int colsA = a.colsA[l], cA = colsA >> 1, cB = (a.n8[l] - colsA) >> 1;
           const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
@@ -537,16 +577,13 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             tc_fence_after();
             if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
             const uint32_t sl = lane_base + s * SLOT_COLS;
-            const int c0 = h * half;
-            switch (half) {
-              case 32: hidden_epilogue_pair<16, 16, NE>(sl, c0, bl); break;
-              case 28: hidden_epilogue_pair<16, 12, NE>(sl, c0, bl); break;
-              case 24: hidden_epilogue_pair<12, 12, NE>(sl, c0, bl); break;
-              case 20: hidden_epilogue_pair<12, 8, NE>(sl, c0, bl); break;
-              case 16: hidden_epilogue_pair<8, 8, NE>(sl, c0, bl); break;
-              case 12: hidden_epilogue_pair<8, 4, NE>(sl, c0, bl); break;
-              case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
-              default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
+            hidden_epilogue_n<NE>(cA, sl, h * cA, bl);
+            if (cB > 0) {  // announce the first part: the control warp starts on the next layer's first K-steps
+              tmem_wait_st();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bars + BP + 8 * s);
+              hidden_epilogue_n<NE>(cB, sl, colsA + h * cB, bl);
             }
             if (h == 1 && a.n8[l] < a.Np[l]) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
               const uint32_t z[4] = {0u, 0u, 0u, 0u};
@@ -839,6 +876,11 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
     a.wlo_ofs[l] = ofs;
     ofs += a.k16[l] * 16 * a.Np[l] * 2;
   }
+  for (int l = 0; l + 1 < L; ++l) {  // two-part hand-over of hidden layer l's output to layer l+1 (K-steps of 16 columns)
+    const int kA = (a.k16[l + 1] + 1) / 2;
+    a.colsA[l] = a.n8[l] < 16 * kA ? a.n8[l] : 16 * kA;
+    a.ksplit[l + 1] = a.colsA[l] < a.n8[l] ? kA : 0;
+  }
   for (int l = 0; l < L; ++l) {
     a.bias_ofs[l] = ofs;
     ofs += 64 * 4;  // padded to the widest layer so float4 reads never leave the zero-filled region
@@ -868,7 +910,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_conf = out_conf;
   a.o_tots = out_total_scaled; a.o_totu = out_total_unscaled; a.o_totconf = out_total_conf;
   a.trace = g_trace; a.trace_cap = g_trace_cap;
-  if (const char* e = getenv("GB_TC_TRACE_FROM")) a.trace_from = atoi(e);  // debug trace window (scratch/dbg_trace.py)
+  if (const char* e = getenv("GB_TC_TRACE_FROM")) a.trace_from = atoi(e);
   if (const char* e = getenv("GB_TC_TRACE_HEAD")) a.trace_head = atoi(e);
 
   CUtensorMap mx;

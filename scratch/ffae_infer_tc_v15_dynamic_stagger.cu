@@ -104,6 +104,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking: has the phase with this parity completed?
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -523,43 +536,57 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
       // =========================================== layer-epilogue warps (SFU-bound): hidden layers only
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-        // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
-        for (int l = 0; l + 1 < L; ++l) {
-          const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
-          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (t0 + s >= n_tiles) continue;
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, s ? ph_d1 : ph_d0);
-            if (s) ph_d1 ^= 1; else ph_d0 ^= 1;
-            tc_fence_after();
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
-            const uint32_t sl = lane_base + s * SLOT_COLS;
-            const int c0 = h * half;
-            switch (half) {
-              case 32: hidden_epilogue_pair<16, 16, NE>(sl, c0, bl); break;
-              case 28: hidden_epilogue_pair<16, 12, NE>(sl, c0, bl); break;
-              case 24: hidden_epilogue_pair<12, 12, NE>(sl, c0, bl); break;
-              case 20: hidden_epilogue_pair<12, 8, NE>(sl, c0, bl); break;
-              case 16: hidden_epilogue_pair<8, 8, NE>(sl, c0, bl); break;
-              case 12: hidden_epilogue_pair<8, 4, NE>(sl, c0, bl); break;
-              case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
-              default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
-            }
-            if (h == 1 && a.n8[l] < a.Np[l]) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
-              const uint32_t z[4] = {0u, 0u, 0u, 0u};
-              tmem_st4(sl + COL_A1 + (a.n8[l] >> 1), z);
-              tmem_st4(sl + COL_A2 + (a.n8[l] >> 1), z);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t0 + s, l, s);
-          }
+      // D -> bias, tanh -> next layer's A operand.  These warps are the busiest resource of the kernel, so they must never wait
+      // while either tile slot has an accumulator ready: each warp serves whichever slot's d_ready has fired (per slot the
+      // layers stay in order; warps may pick different orders -- every barrier still counts all eight of them).  Slot 1's first
+      // epilogue of a work item is held back by half a tile, so the slots run out of phase: when one is between tiles (output
+      // layer, accumulator parking, x split, layer 0) the other is mid-tile.  Lockstep service left ~2k idle cycles per pair
+      // of tiles; a fixed alternating order made each slot wait for the other (both measured).
+      const int HL = L - 1;                                        // hidden layers per tile
+      const int n0 = ((n_tiles + 1) >> 1) * HL, n1 = (n_tiles >> 1) * HL;  // epilogues of slot 0 / slot 1 in this work item
+      const int lag = HL >> 1;
+      auto epilogue = [&](int s, int e) {
+        const int l = e % HL, t = 2 * (e / HL) + s;
+        const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
+        const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
+        if (s) ph_d1 ^= 1; else ph_d0 ^= 1;  // the caller saw this phase complete
+        tc_fence_after();
+        if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t, l, s);
+        const uint32_t sl = lane_base + s * SLOT_COLS;
+        const int c0 = h * half;
+        switch (half) {
+          case 32: hidden_epilogue_pair<16, 16, NE>(sl, c0, bl); break;
+          case 28: hidden_epilogue_pair<16, 12, NE>(sl, c0, bl); break;
+          case 24: hidden_epilogue_pair<12, 12, NE>(sl, c0, bl); break;
+          case 20: hidden_epilogue_pair<12, 8, NE>(sl, c0, bl); break;
+          case 16: hidden_epilogue_pair<8, 8, NE>(sl, c0, bl); break;
+          case 12: hidden_epilogue_pair<8, 4, NE>(sl, c0, bl); break;
+          case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
+          default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
         }
+        if (h == 1 && a.n8[l] < a.Np[l]) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};
+          tmem_st4(sl + COL_A1 + (a.n8[l] >> 1), z);
+          tmem_st4(sl + COL_A2 + (a.n8[l] >> 1), z);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+        if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t, l, s);
+      };
+      int e0 = 0, e1 = 0;
+      while (e0 < n0 || e1 < n1) {
+        bool idle = true;
+        if (e0 < n0 && mbar_test(bars + BD, ph_d0)) {
+          epilogue(0, e0++);
+          idle = false;
+        }
+        if (e1 < n1 && (e1 > 0 || e0 >= lag || e0 >= n0) && mbar_test(bars + BD + 8, ph_d1)) {
+          epilogue(1, e1++);
+          idle = false;
+        }
+        if (idle) __nanosleep(20);
       }
     } else {
       // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
@@ -567,8 +594,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // Only the accumulator has to change layout (TMEM gives one thread = one row): it goes once through this warp's swizzled
       // staging box; y is loaded straight into the transposed layout and every output column is formed and stored there.
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * 2 * OBOX_BYTES;  // transpose staging of the accumulator
-      const uint32_t ybox = stage + OBOX_BYTES;                                           // y rows of the second tile of a pair
+      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * OBOX_BYTES;  // transpose staging of the accumulator
       float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2 halves][2][TILE] row sums
       const int tr = lane >> 3, tc = lane & 7;
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
@@ -619,9 +645,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         __syncwarp();
       };
       float4 yt[8];
-      // every output column of tile t from the staged accumulator; y comes from registers (first tile of a pair) or from the
-      // warp's y box in shared memory (second tile, fetched with cp.async while the first was being written)
-      auto emit = [&](int t, bool y_smem) {
+      // every output column of tile t from the staged accumulator and the y rows held in registers
+      auto emit = [&](int t, bool) {
         const int trow = row_begin + t * TILE;
         const int nrows = min(TILE, row_end - trow);
         const long grow0 = job.out_row + trow;
@@ -633,7 +658,6 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           float4 yh, yv = yt[i];
           const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
-          if (y_smem) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yv.x), "=f"(yv.y), "=f"(yv.z), "=f"(yv.w) : "r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u));
           yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
           const bool live = wrow0 + r < nrows && !(a.flags & FLAG_NO_STORES);
           const long g = (grow0 + wrow0 + r) * (long)W + h * 32 + tc * 4;
@@ -681,50 +705,28 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       split_x(0);
       if (n_tiles > 1) split_x(1);
 
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-        const bool two = t0 + 1 < n_tiles;
-        if (has_y) {
-          if (two) {  // y rows of the pair's second tile -> y box (asynchronously; needed only after the first tile is written)
-            const int trow = row_begin + (t0 + 1) * TILE;
-            const int nrows = min(TILE, row_end - trow);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + tr;
-              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)W + h * 32 + tc * 4;
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-          }
-          const int trow = row_begin + t0 * TILE;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t & 1;
+        if (has_y) {  // y rows -> registers, requested before the accumulator is ready
+          const int trow = row_begin + t * TILE;
           const int nrows = min(TILE, row_end - trow);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {  // y rows of the first tile -> registers, requested before its accumulator is ready
+          for (int i = 0; i < 8; ++i) {
             const int r = min(q * 32 + i * 4 + tr, nrows - 1);
             yt[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + h * 32) + tc);
           }
         }
-        // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed both slots their next tiles
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t0, L - 1, 0);
-        mbar_wait(bars + BF, ph_f0);
-        ph_f0 ^= 1;
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t, L - 1, s);
+        mbar_wait(bars + BF + 8 * s, s ? ph_f1 : ph_f0);
+        if (s) ph_f1 ^= 1; else ph_f0 ^= 1;
         tc_fence_after();
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0, L - 1, 0);
-        park(0, t0);
-        if (t0 + 2 < n_tiles) split_x(t0 + 2);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
-        if (two) {
-          mbar_wait(bars + BF + 8, ph_f1);
-          ph_f1 ^= 1;
-          tc_fence_after();
-          if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0 + 1, L - 1, 1);
-          if (t0 + 3 < n_tiles) split_x(t0 + 3);  // slot 1's output sits in the spare accumulator until the stores below are done
-        }
-        // ---- then the stores
-        emit(t0, false);
-        if (two) {
-          park(1, t0 + 1);
-          asm volatile("cp.async.wait_all;" ::: "memory");
-          emit(t0 + 1, true);
-        }
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
+        // first what the layer pipeline waits for -- free the accumulator, feed the slot its next tile (the output-layer MMA of
+        // tile t is complete, nothing reads this slot's A operands any more) -- then the stores.  The slots run half a tile out
+        // of phase, so the other slot's accumulator is not due before these stores are out.
+        park(s, t);
+        if (t + 2 < n_tiles) split_x(t + 2);
+        emit(t, false);
       }
     }
     fence_proxy_async();  // this item's generic accesses to the x boxes / staging precede the next item's bulk copy and TMA loads
@@ -850,7 +852,8 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.bar_ofs = ofs; ofs += 128;
   ofs = gb::round_up(ofs, 1024);
   a.xbox_ofs = ofs; ofs += 4 * BOX_BYTES;            // two tile slots x two 32-column boxes
-  a.stage_ofs = ofs; ofs += OUT_WARPS * 2 * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box + a y box of the same shape
+  a.stage_ofs = ofs; ofs += OUT_WARPS * 2 * OBOX_BYTES;  // one 32-row x 32-column staging box per output warp; the rest only extends
+                                                         // the scratch area (x boxes + this) that receives a slot's parameter vector
   const size_t smem = (size_t)ofs;
   GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
 
@@ -868,7 +871,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_conf = out_conf;
   a.o_tots = out_total_scaled; a.o_totu = out_total_unscaled; a.o_totconf = out_total_conf;
   a.trace = g_trace; a.trace_cap = g_trace_cap;
-  if (const char* e = getenv("GB_TC_TRACE_FROM")) a.trace_from = atoi(e);  // debug trace window (scratch/dbg_trace.py)
+  if (const char* e = getenv("GB_TC_TRACE_FROM")) a.trace_from = atoi(e);
   if (const char* e = getenv("GB_TC_TRACE_HEAD")) a.trace_head = atoi(e);
 
   CUtensorMap mx;
