@@ -23,7 +23,7 @@ ACT_CODES = {"linear": 0, None: 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 EXPORTS = (
     "gb_abi_version", "gb_last_error", "gb_device_check", "gb_ffnet_param_count", "gb_ffnet_param_stride",
     "gb_ffae_infer_score", "gb_ffae_tc_supported", "gb_anomaly_score", "gb_minmax_fit", "gb_thresholds", "gb_smooth", "gb_affine_f64", "gb_ffae_fit_state_stride", "gb_ffae_fit",
-    "gb_lstm_param_count", "gb_lstm_param_stride", "gb_lstm_workspace_bytes", "gb_lstm_infer",
+    "gb_lstm_param_count", "gb_lstm_param_stride", "gb_lstm_workspace_bytes", "gb_lstm_infer", "gb_lstm_fit_workspace_bytes", "gb_lstm_fit",
 )
 
 
@@ -50,6 +50,11 @@ class GbLstmNet(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("n_features", C.c_int32), ("n_features_out", C.c_int32),
                 ("units", C.c_int32 * GB_MAX_LAYERS), ("act", C.c_int32 * GB_MAX_LAYERS), ("out_act", C.c_int32),
                 ("lookback", C.c_int32)]
+
+
+class GbLstmFitHParams(C.Structure):
+    _fields_ = [("epochs", C.c_int32), ("batch_size", C.c_int32), ("lookahead", C.c_int32), ("primer", C.c_int32),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
 
 
 class GordoB200Error(RuntimeError):
@@ -87,6 +92,10 @@ def _declare(lib):
     lib.gb_ffae_fit.argtypes = [C.POINTER(GbFFNet), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P,
                                 C.POINTER(GbFitHParams), _P, _P, _P]
     lib.gb_lstm_infer.argtypes = [C.POINTER(GbLstmNet), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]
+    lib.gb_lstm_fit_workspace_bytes.restype = C.c_size_t
+    lib.gb_lstm_fit_workspace_bytes.argtypes = [C.POINTER(GbLstmNet), C.c_int32]
+    lib.gb_lstm_fit.argtypes = [C.POINTER(GbLstmNet), _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(GbLstmFitHParams), _P, _P, _P, _P]
+    lib.gb_lstm_fit.restype = C.c_int
     for name in ("gb_device_check", "gb_ffae_infer_score", "gb_ffae_tc_supported", "gb_anomaly_score", "gb_minmax_fit", "gb_thresholds", "gb_smooth", "gb_ffae_fit", "gb_lstm_infer"):
         getattr(lib, name).restype = C.c_int
 

@@ -307,6 +307,50 @@ class LSTMEngine:
             host[s, : vec.size] = vec
         return torch.from_numpy(host).to(self.device)
 
+    def unpack_params(self, params):
+        """device [n_slots, stride] -> per slot ([(kernel, recurrent, bias) per layer], (Wd, bd)) as host arrays."""
+        host = params.detach().cpu().numpy()
+        out = []
+        for vec in host:
+            layers, ofs, i = [], 0, self.n_features
+            for u in self.units:
+                K = vec[ofs:ofs + i * 4 * u].reshape(i, 4 * u).copy(); ofs += i * 4 * u
+                U = vec[ofs:ofs + u * 4 * u].reshape(u, 4 * u).copy(); ofs += u * 4 * u
+                b = vec[ofs:ofs + 4 * u].copy(); ofs += 4 * u
+                layers.append((K, U, b))
+                i = u
+            Wd = vec[ofs:ofs + i * self.n_out].reshape(i, self.n_out).copy(); ofs += i * self.n_out
+            out.append((layers, (Wd, vec[ofs:ofs + self.n_out].copy())))
+        return out
+
+    def fit(self, params, jobs_dev, n_jobs, max_windows, x, y, epochs: int = 1, batch_size: int = 32, lookahead: int = 0,
+            primer: bool = True, adam: Optional[Dict[str, float]] = None, state=None):
+        """
+        Trains every job's slot in place by back-propagation through time (``jobs`` count windows; target of window j is
+        y[x_row + j + lookback - 1 + lookahead]).  Returns (loss [n_jobs, epochs], accuracy, (m, v, t)).
+        """
+        torch = _torch()
+        adam = adam or {}
+        hp = _cabi.GbLstmFitHParams()
+        hp.epochs, hp.batch_size, hp.lookahead, hp.primer = int(epochs), int(batch_size), int(lookahead), int(bool(primer))
+        hp.lr, hp.beta1 = float(adam.get("lr", 1e-3)), float(adam.get("beta1", 0.9))
+        hp.beta2, hp.eps = float(adam.get("beta2", 0.999)), float(adam.get("eps", 1e-7))
+        if state is None:
+            m = torch.zeros_like(params)
+            v = torch.zeros_like(params)
+            t = torch.zeros((params.shape[0],), dtype=torch.int32, device=self.device)
+        else:
+            m, v, t = state
+        ws_bytes = int(self.lib.gb_lstm_fit_workspace_bytes(C.byref(self.net), int(n_jobs)))
+        ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=self.device)
+        loss = torch.zeros((n_jobs, max(epochs, 1)), dtype=torch.float32, device=self.device)[:, :epochs]
+        acc = torch.zeros((n_jobs, max(epochs, 1)), dtype=torch.float32, device=self.device)[:, :epochs]
+        loss, acc = loss.contiguous(), acc.contiguous()
+        p = _cabi.ptr
+        _cabi.check(self.lib.gb_lstm_fit(C.byref(self.net), p(params), p(m), p(v), p(t), p(jobs_dev), int(n_jobs), int(max_windows), p(x), p(y),
+                                         C.byref(hp), p(ws), p(loss), p(acc), _stream_ptr()))
+        return loss, acc, (m, v, t)
+
     def infer(self, params, jobs_dev, n_jobs, max_windows, x, out_rows):
         """out[j] = net(x[j : j + lookback]) for every job's windows (jobs' n_rows counts windows)."""
         torch = _torch()

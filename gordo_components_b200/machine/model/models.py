@@ -379,18 +379,41 @@ class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin, metaclass=abc
 
     def fit(self, X, y, **kwargs):
         """
-        LSTM training (BPTT) has no B200 kernel yet: the network is built and initialised exactly as the reference's
-        primer fit does, then NotImplementedError is raised rather than silently training somewhere else.
+        models.py:557-616: the network is built and initialised, takes the reference's primer Adam step on the first window,
+        then ``epochs`` passes over the lookback windows in order (``shuffle=False``) in batches of ``self.batch_size``
+        (gb_lstm_fit, back-propagation through time on the GPU).
         """
+        from ... import engine
+
         X = self._validate_and_fix_size_of_X(_as_2d_values(X))
         y = _as_2d_values(y)
         if y.ndim == 1:
             y = y.reshape(-1, 1)
         self.initialize(X.shape[1], y.shape[1])
-        raise NotImplementedError(
-            "KerasLSTM*.fit: the LSTM training kernel is not built yet (round-1 scope is LSTM inference); "
-            "install weights with set_weights() -- there is deliberately no CPU/framework fallback"
-        )
+        spec = self.model.spec
+        fit_args = {**self.extract_supported_fit_args(self.kwargs), **kwargs}
+        epochs = int(fit_args.get("epochs", 1))
+        if fit_args.get("callbacks"):
+            logger.warning("callbacks %s are not supported by the B200 fit kernel and are ignored", fit_args["callbacks"])
+        batch_size = int(self.batch_size)
+        n_win = len(X) - self.lookback_window + 1 - self.lookahead
+        if n_win < 1:
+            raise ValueError("no training windows")
+        eng = self._engine()
+        dev = eng.device
+        xd, yd = engine.to_device_f32(X, dev), engine.to_device_f32(y, dev)
+        params = eng.pack_params([self.model.weights])
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [n_win], [0]), dev)
+        loss, acc, _ = eng.fit(params, jobs, 1, n_win, xd, yd, epochs=epochs, batch_size=batch_size, lookahead=self.lookahead,
+                               primer=True, adam=getattr(spec, "adam", None))
+        self.model.weights = eng.unpack_params(params)[0]
+        self.__dict__["_dev_cache"] = (self.model.weights, params)
+        history: Dict[str, list] = {"loss": [float(v) for v in loss[0].cpu().numpy()]}
+        if "accuracy" in getattr(spec, "metrics", ("accuracy",)):
+            history["accuracy"] = [float(v) for v in acc[0].cpu().numpy()]
+        self._history = History(history, {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n_win / batch_size))}, list(range(epochs)))
+        self.model.history = self._history
+        return self
 
     def predict(self, X, **kwargs) -> np.ndarray:
         """``[len(X) - lookback_window + 1 - lookahead, n_features_out]`` float32: row j is the net applied to X[j : j+lookback]."""

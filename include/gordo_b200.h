@@ -201,6 +201,27 @@ size_t gb_lstm_workspace_bytes(const gb_lstmnet* net, int32_t n_jobs, int32_t ma
 int gb_lstm_infer(const gb_lstmnet* net, const float* params, const gb_job* jobs, int32_t n_jobs,
                   int32_t max_rows, const float* x, float* out_model, void* workspace, void* stream);
 
+/* ---- K3-fit: LSTM training (back-propagation through time) ---------------------------------
+ * Replaces KerasLSTMBaseEstimator.fit (models.py:557-616): if `primer`, one Adam step on the single
+ * window 0 (the reference's `super().fit` on a batch of one, :585-597); then `epochs` passes over the
+ * windows in order (shuffle=False, :612-615) in batches of `batch_size` (last partial batch kept),
+ * loss = mean((net(window) - target)^2), Adam as in gb_ffae_fit.  Window j of a job = x rows
+ * [x_row + j, x_row + j + lookback), target = y row x_row + j + lookback - 1 + lookahead; jobs[].n_rows
+ * counts windows.  params / adam_m / adam_v: [n_slots][gb_lstm_param_stride], updated in place;
+ * adam_t: [n_slots] optimizer step counters (in/out).  out_loss / out_acc: [n_jobs][epochs].
+ * workspace: gb_lstm_fit_workspace_bytes(net, n_jobs) bytes of device scratch (saved gates/states of
+ * one batch per job).  One optimizer step is a sequence of launches over (tile, job) grids. */
+typedef struct gb_lstm_fit_hparams {
+  int32_t epochs, batch_size;   /* batch_size <= 32 */
+  int32_t lookahead;            /* 0 = KerasLSTMAutoEncoder, 1 = KerasLSTMForecast */
+  int32_t primer;               /* 1 = run the reference's primer step first */
+  float lr, beta1, beta2, eps;
+} gb_lstm_fit_hparams;
+size_t gb_lstm_fit_workspace_bytes(const gb_lstmnet* net, int32_t n_jobs);
+int gb_lstm_fit(const gb_lstmnet* net, float* params, float* adam_m, float* adam_v, int32_t* adam_t,
+                const gb_job* jobs, int32_t n_jobs, int32_t max_windows, const float* x, const float* y,
+                const gb_lstm_fit_hparams* hp, void* workspace, float* out_loss, float* out_acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

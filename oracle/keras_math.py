@@ -451,3 +451,139 @@ def lstm_predict(spec: LSTMSpec, weights, X: np.ndarray, lookahead: int = 0, bat
         win = np.lib.stride_tricks.sliding_window_view(X, (L, X.shape[1]))[js, 0]
         outs.append(lstm_forward_windows(spec, weights, win, dtype))
     return np.concatenate(outs, axis=0)
+
+
+# --------------------------------------------------------------------------------------
+# LSTM fit  (KerasLSTMBaseEstimator.fit, models.py:557-616: primer step on one window, then
+# Model.fit on the window generator with shuffle=False) -- back-propagation through time [3P keras]
+# --------------------------------------------------------------------------------------
+
+
+def lstm_loss_and_grads(spec: LSTMSpec, weights, windows: np.ndarray, targets: np.ndarray, dtype=np.float32):
+    """
+    MSE over all batch elements and its gradient for the stacked LSTM + Dense (no activity regulariser in lstm_model,
+    lstm_autoencoder.py:72-103).  Returns (loss, grads, yhat); grads mirrors ``weights``: ([(dK, dU, db)...], (dWd, dbd)).
+    """
+    layers, (Wd, bd) = weights
+    seq = np.asarray(windows, dtype=dtype)
+    tg = np.asarray(targets, dtype=dtype)
+    B, L, _ = seq.shape
+    saved = []
+    for (K, U, b), act in zip(layers, spec.acts):
+        u = U.shape[0]
+        K, U, b = K.astype(dtype), U.astype(dtype), b.astype(dtype)
+        h = np.zeros((B, u), dtype)
+        c = np.zeros((B, u), dtype)
+        ig, fg, gg, og, cs, hs = (np.empty((B, L, u), dtype) for _ in range(6))
+        for t in range(L):
+            z = seq[:, t] @ K + b + h @ U
+            ig[:, t] = _sigmoid(z[:, :u])
+            fg[:, t] = _sigmoid(z[:, u : 2 * u])
+            gg[:, t] = _act(act, z[:, 2 * u : 3 * u])
+            og[:, t] = _sigmoid(z[:, 3 * u :])
+            c = (fg[:, t] * c + ig[:, t] * gg[:, t]).astype(dtype)
+            h = (og[:, t] * _act(act, c)).astype(dtype)
+            cs[:, t], hs[:, t] = c, h
+        saved.append((seq, ig, fg, gg, og, cs, hs))
+        seq = hs
+    last = seq[:, -1]
+    yhat = _act(spec.out_func, last @ Wd.astype(dtype) + bd.astype(dtype)).astype(dtype)
+    diff = yhat - tg
+    loss = dtype(np.mean(diff**2))
+    dout = ((dtype(2.0) / dtype(diff.size)) * diff * _act_grad_from_output(spec.out_func, yhat)).astype(dtype)
+    g_dense = ((last.T @ dout).astype(dtype), dout.sum(axis=0).astype(dtype))
+    dh_seq = np.zeros_like(seq)
+    dh_seq[:, -1] = dout @ Wd.astype(dtype).T
+    g_layers = [None] * len(layers)
+    for li in range(len(layers) - 1, -1, -1):
+        K, U, b = (w.astype(dtype) for w in layers[li])
+        act = spec.acts[li]
+        xs, ig, fg, gg, og, cs, hs = saved[li]
+        u = U.shape[0]
+        dK, dU, db = np.zeros_like(K), np.zeros_like(U), np.zeros_like(b)
+        dx_seq = np.zeros_like(xs)
+        dh_next = np.zeros((B, u), dtype)
+        dc_next = np.zeros((B, u), dtype)
+        for t in range(L - 1, -1, -1):
+            dh = dh_seq[:, t] + dh_next
+            ac = _act(act, cs[:, t])
+            c_prev = cs[:, t - 1] if t > 0 else np.zeros((B, u), dtype)
+            h_prev = hs[:, t - 1] if t > 0 else np.zeros((B, u), dtype)
+            dc = dh * og[:, t] * _act_grad_from_output(act, ac) + dc_next
+            dz = np.concatenate(
+                [
+                    dc * gg[:, t] * ig[:, t] * (1 - ig[:, t]),
+                    dc * c_prev * fg[:, t] * (1 - fg[:, t]),
+                    dc * ig[:, t] * _act_grad_from_output(act, gg[:, t]),
+                    dh * ac * og[:, t] * (1 - og[:, t]),
+                ],
+                axis=1,
+            ).astype(dtype)
+            dK += xs[:, t].T @ dz
+            dU += h_prev.T @ dz
+            db += dz.sum(axis=0)
+            dx_seq[:, t] = dz @ K.T
+            dh_next = dz @ U.T
+            dc_next = dc * fg[:, t]
+        g_layers[li] = (dK.astype(dtype), dU.astype(dtype), db.astype(dtype))
+        dh_seq = dx_seq
+    return loss, (g_layers, g_dense), yhat
+
+
+def _lstm_flat(weights):
+    layers, dense = weights
+    return [a for lay in layers for a in lay] + list(dense)
+
+
+def _lstm_unflat(flat, n_layers):
+    return [tuple(flat[3 * i : 3 * i + 3]) for i in range(n_layers)], tuple(flat[3 * n_layers : 3 * n_layers + 2])
+
+
+def lstm_fit(spec: LSTMSpec, weights, X: np.ndarray, y: np.ndarray, epochs: int = 1, batch_size: int = 32, lookahead: int = 0,
+             lr=1e-3, b1=0.9, b2=0.999, eps=1e-7, dtype=np.float32):
+    """
+    models.py:557-616.  (1) primer: one Adam step on the single window X[:L] -> y[L-1+lookahead] (``super().fit`` with epochs=1 on
+    a batch of one); (2) ``epochs`` passes over the windows IN ORDER (shuffle=False) in batches of ``batch_size``, last partial
+    batch kept, the optimizer state carrying on from the primer step.  History = sample-weighted mean loss / accuracy per epoch.
+    Returns (weights, history).
+    """
+    X = np.asarray(X, dtype=dtype)
+    y = np.asarray(y, dtype=dtype)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    if y.ndim == 1:
+        y = y.reshape(-1, 1)
+    L = spec.lookback_window
+    starts, tgt = timeseries_windows(len(X), L, lookahead)
+    nl = len(spec.units)
+    flat = [np.asarray(a, dtype=dtype).copy() for a in _lstm_flat(weights)]
+    m = [np.zeros_like(a) for a in flat]
+    v = [np.zeros_like(a) for a in flat]
+    t_step = 0
+
+    def step(js):
+        nonlocal flat, t_step
+        win = np.stack([X[j : j + L] for j in js])
+        loss, grads, yhat = lstm_loss_and_grads(spec, _lstm_unflat(flat, nl), win, y[tgt[js]], dtype)
+        t_step += 1
+        alpha = dtype(lr * math.sqrt(1.0 - b2**t_step) / (1.0 - b1**t_step))
+        for k, g in enumerate(_lstm_flat(grads)):
+            m[k] += (g - m[k]) * dtype(1 - b1)
+            v[k] += (g * g - v[k]) * dtype(1 - b2)
+            flat[k] = (flat[k] - alpha * m[k] / (np.sqrt(v[k]) + dtype(eps))).astype(dtype)
+        return float(loss), categorical_accuracy(y[tgt[js]], yhat)
+
+    step(np.array([0]))  # primer
+    hist: Dict[str, list] = {"loss": [], "accuracy": []}
+    n = len(starts)
+    for _ in range(epochs):
+        ls = hs = 0.0
+        for s in range(0, n, batch_size):
+            js = starts[s : s + batch_size]
+            lo, ac = step(js)
+            ls += lo * len(js)
+            hs += ac * len(js)
+        hist["loss"].append(ls / n)
+        hist["accuracy"].append(hs / n)
+    hist["params"] = {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n / batch_size))}
+    return _lstm_unflat(flat, nl), hist

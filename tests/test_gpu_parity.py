@@ -460,8 +460,61 @@ def test_lstm_estimator_predict_shapes(engine, torch):
     assert len(X) - len(a.predict(X)) == 9
     with pytest.raises(ValueError):
         a.predict(np.random.random((10, 5)))
-    with pytest.raises(NotImplementedError):
-        a.fit(X, X)
+    a.fit(X, X, epochs=2)
+    assert a.get_metadata()["history"]["loss"][1] < a.get_metadata()["history"]["loss"][0]
+    assert a.get_metadata()["forecast_steps"] == 0 and len(X) - len(a.predict(X)) == 9
+
+
+@pytest.mark.parametrize("case", ["tiny", "tiled", "forecast", "gradients"])
+def test_lstm_fit_matches_oracle(engine, torch, case):
+    """gb_lstm_fit (BPTT, primer step + ordered batches, Adam) against the oracle's restatement of models.py:557-616 on
+    injected weights: the oracle's gradients are themselves pinned by finite differences in test_oracle_golden."""
+    from oracle import keras_math as km
+
+    if case == "tiny":
+        spec = km.lstm_model_spec(3, 3, lookback_window=4, encoding_dim=(5,), encoding_func=("tanh",), decoding_dim=(4,), decoding_func=("tanh",))
+        rows, epochs, B, la = [40], 2, 8, 0
+    elif case == "tiled":  # widths that cross the 16-unit / 32-row / 64-column tiles, two machines of different length, partial batches
+        spec = km.lstm_model_spec(20, 20, lookback_window=6, encoding_dim=(40, 24), encoding_func=("tanh", "tanh"), decoding_dim=(24, 40), decoding_func=("tanh", "tanh"))
+        rows, epochs, B, la = [107, 75], 2, 32, 0
+    elif case == "gradients":
+        # Adam's update is (nearly) invariant to the gradient's scale; with beta1 = beta2 = 0 and eps = 1 a step is
+        # -lr * g / (|g| + 1), so the trained weights expose the raw BPTT gradients
+        spec = km.lstm_model_spec(20, 20, lookback_window=6, encoding_dim=(40, 24), encoding_func=("tanh", "tanh"), decoding_dim=(24, 40), decoding_func=("tanh", "tanh"))
+        rows, epochs, B, la = [70], 1, 32, 0
+        adam = {"lr": 1.0, "beta1": 0.0, "beta2": 0.0, "eps": 1.0}
+    else:
+        spec = km.lstm_model_spec(4, 2, lookback_window=5, encoding_dim=(9,), encoding_func=("tanh",), decoding_dim=(7,), decoding_func=("sigmoid",), out_func="tanh")
+        rows, epochs, B, la = [60], 1, 16, 1
+    if case != "gradients":
+        adam = {"lr": 1e-3, "beta1": 0.9, "beta2": 0.999, "eps": 1e-7}
+    rng = np.random.default_rng(5)
+    eng = engine.LSTMEngine(spec.n_features, spec.units, spec.acts, spec.n_features_out, spec.out_func, spec.lookback_window)
+    Xs = [rng.random((n, spec.n_features)).astype(np.float32) for n in rows]
+    Ys = [rng.random((n, spec.n_features_out)).astype(np.float32) for n in rows]
+    ws = [km.init_lstm_weights(spec, np.random.default_rng(10 + i)) for i in range(len(rows))]
+    T = max(spec.n_features, spec.n_features_out)  # x and y share the row space; pad the narrower one
+    dev = eng.device
+    x = torch.from_numpy(np.concatenate(Xs)).to(dev)
+    y = torch.from_numpy(np.concatenate(Ys)).to(dev)
+    nwin = [n - spec.lookback_window + 1 - la for n in rows]
+    starts = np.concatenate([[0], np.cumsum(rows)[:-1]])
+    jobs = engine.jobs_to_device(engine.make_jobs(np.arange(len(rows)), nwin, starts), dev)
+    params = eng.pack_params(ws)
+    loss, acc, _ = eng.fit(params, jobs, len(rows), max(nwin), x, y, epochs=epochs, batch_size=B, lookahead=la, primer=True, adam=adam)
+    torch.cuda.synchronize()
+    got = eng.unpack_params(params)
+    for i in range(len(rows)):
+        want_w, hist = km.lstm_fit(spec, ws[i], Xs[i], Ys[i], epochs=epochs, batch_size=B, lookahead=la, lr=adam["lr"], b1=adam["beta1"],
+                                   b2=adam["beta2"], eps=adam["eps"])
+        close(loss[i].cpu().numpy(), np.array(hist["loss"]), rtol=5e-4, name=f"{case} loss history")
+        assert np.allclose(acc[i].cpu().numpy(), hist["accuracy"], atol=1.5 / nwin[i])
+        steps = 1 + epochs * int(np.ceil(nwin[i] / B))
+        for w0, gl, wl in zip(km._lstm_flat(ws[i]), km._lstm_flat(got[i]), km._lstm_flat(want_w)):
+            if case == "gradients":
+                close(gl - w0, wl - w0, mag=float(np.abs(wl - w0).max()), rtol=1e-3, name="accumulated raw gradients")
+            else:  # Adam moves a weight by ~lr per step whatever the gradient's size: compare the distance travelled
+                close(gl - w0, wl - w0, mag=adam["lr"] * steps, rtol=2e-2, name=f"{case} trained weights")
 
 
 @pytest.mark.parametrize("chain", ["minmax", "standard+minmax", "function"])

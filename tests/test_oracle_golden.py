@@ -215,3 +215,37 @@ def test_ff_grads_match_finite_differences():
             lp = km.ff_loss_and_grads(spec, w[:l] + [(Wp, w[l][1])] + w[l + 1:], xb, xb, dtype=np.float64)[0]
             lm = km.ff_loss_and_grads(spec, w[:l] + [(Wm, w[l][1])] + w[l + 1:], xb, xb, dtype=np.float64)[0]
             assert abs((lp - lm) / (2 * h) - grads[l][0][i, j]) < 1e-6
+
+
+def test_lstm_bptt_gradients_match_finite_differences():
+    """The oracle's back-propagation through time (the checker of gb_lstm_fit) against central differences in float64."""
+    from oracle import keras_math as km
+
+    spec = km.lstm_model_spec(3, 2, lookback_window=4, encoding_dim=(5,), encoding_func=("tanh",), decoding_dim=(4,), decoding_func=("sigmoid",), out_func="tanh")
+    rng = np.random.default_rng(0)
+    w = km.init_lstm_weights(spec, rng)
+    flat = [a.astype(np.float64) for a in km._lstm_flat(w)]
+    win, tg = rng.random((6, 4, 3)), rng.random((6, 2))
+    _, grads, _ = km.lstm_loss_and_grads(spec, km._lstm_unflat(flat, 2), win, tg, np.float64)
+    gflat = km._lstm_flat(grads)
+    for k, a in enumerate(flat):
+        for _ in range(5):
+            idx = tuple(rng.integers(0, s) for s in a.shape)
+            old, h = a[idx], 1e-6
+            a[idx] = old + h
+            lp = km.lstm_loss_and_grads(spec, km._lstm_unflat(flat, 2), win, tg, np.float64)[0]
+            a[idx] = old - h
+            lm = km.lstm_loss_and_grads(spec, km._lstm_unflat(flat, 2), win, tg, np.float64)[0]
+            a[idx] = old
+            fd = (lp - lm) / (2 * h)
+            assert abs(fd - gflat[k][idx]) <= 1e-5 * max(1e-3, abs(fd)), (k, idx, fd, gflat[k][idx])
+
+
+def test_lstm_fit_control_flow():
+    """models.py:557-616: primer step + ordered batches; the history has one entry per epoch and the loss falls."""
+    from oracle import keras_math as km
+
+    spec = km.lstm_model_spec(3, 3, lookback_window=4, encoding_dim=(5,), encoding_func=("tanh",), decoding_dim=(4,), decoding_func=("tanh",))
+    X = np.random.default_rng(2).random((40, 3)).astype(np.float32)
+    w, hist = km.lstm_fit(spec, km.init_lstm_weights(spec, np.random.default_rng(1)), X, X, epochs=3, batch_size=8)
+    assert len(hist["loss"]) == 3 and hist["loss"][2] < hist["loss"][0] and hist["params"]["steps"] == 5
