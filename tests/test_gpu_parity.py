@@ -465,6 +465,37 @@ def test_lstm_estimator_predict_shapes(engine, torch):
     assert a.get_metadata()["forecast_steps"] == 0 and len(X) - len(a.predict(X)) == 9
 
 
+@pytest.mark.parametrize("cls_name,offset", [("KerasLSTMAutoEncoder", 5), ("KerasLSTMForecast", 6)])
+def test_detector_with_lstm_base_estimator(engine, torch, cls_name, offset):
+    """tests/gordo/builder/test_builder.py:99-115 (model offsets) + test_anomaly_detectors.py with an LSTM base estimator:
+    cross_validate / fit / anomaly run end to end on the GPU; the frame is tail-aligned to the shorter model output."""
+    from gordo_components_b200.machine.model import models
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from oracle import anomaly_math as am
+    from oracle import keras_math as km
+
+    np.random.seed(1)
+    n, T, L = 120, 4, 6
+    t = np.linspace(0, 20, n)[:, None]
+    Xv = 0.5 + 0.4 * np.sin(t * np.linspace(0.5, 2, T)) + np.random.normal(0, 0.02, (n, T))
+    cols = [f"tag-{i}" for i in range(T)]
+    X = pd.DataFrame(Xv, columns=cols, index=pd.date_range("2019-01-01", periods=n, freq="10min", tz="UTC"))
+    det = DiffBasedAnomalyDetector(base_estimator=getattr(models, cls_name)(kind="lstm_hourglass", lookback_window=L, epochs=1, batch_size=16))
+    det.cross_validate(X=X, y=X)
+    assert len(det.feature_thresholds_) == T and np.isfinite(det.aggregate_threshold_)
+    det.fit(X, X)
+    frame = det.anomaly(X, X)
+    assert len(X) - len(frame) == offset
+    ae = det.base_estimator
+    spec = km.lstm_hourglass_spec(T, lookback_window=L)
+    pred = km.lstm_predict(spec, ae.model.weights, Xv.astype(np.float32), lookahead=ae.lookahead)
+    close(frame["model-output"].values, pred, rtol=2e-4, name="lstm detector model-output")
+    sc, mn = am.minmax_fit(Xv)
+    want = am.anomaly_arrays(pred, Xv, sc, mn, det.feature_thresholds_.values, det.aggregate_threshold_)
+    close(frame["tag-anomaly-unscaled"].values, want["tag-anomaly-unscaled"], rtol=2e-4, name="tag-anomaly-unscaled")
+    close(frame["total-anomaly-confidence"].values.ravel(), want["total-anomaly-confidence"], float(want["total-anomaly-confidence"].max()), rtol=2e-4, name="confidence")
+
+
 @pytest.mark.parametrize("case", ["tiny", "tiled", "forecast", "gradients"])
 def test_lstm_fit_matches_oracle(engine, torch, case):
     """gb_lstm_fit (BPTT, primer step + ordered batches, Adam) against the oracle's restatement of models.py:557-616 on
