@@ -583,6 +583,48 @@ def test_detector_with_scaler_pipeline(engine, torch, chain):
     close(frame["tag-anomaly-unscaled"].values, want["tag-anomaly-unscaled"], name="tag-anomaly-unscaled")
 
 
+def test_request_coalescer_equals_per_request_launches(engine, torch):
+    """serving.AnomalyCoalescer: 120 concurrent requests of 1..150 rows for random machines come back bit-identical to one
+    launch per request (rows are independent in the kernel), in far fewer launches."""
+    import threading
+
+    from gordo_components_b200 import fleet, serving
+    from oracle import keras_math as km
+
+    spec = km.ff_hourglass_spec(64)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    M = 40
+    g = torch.Generator(device=dev).manual_seed(3)
+    params = fleet.random_glorot_params(eng, M, g)
+    scale = torch.rand((M, 64), generator=g, device=dev) + 0.5
+    feat = torch.rand((M, 64), generator=g, device=dev) + 0.5
+    agg = torch.rand((M,), generator=g, device=dev) + 0.5
+    rng = np.random.default_rng(0)
+    reqs = [(int(rng.integers(0, M)), rng.random((int(rng.integers(1, 151)), 64)).astype(np.float32)) for _ in range(120)]
+    co = serving.AnomalyCoalescer(eng, params, scale, feat, agg, max_wait_ms=20.0)
+    futs = [None] * len(reqs)
+
+    def client(i):
+        futs[i] = co.submit(reqs[i][0], reqs[i][1], reqs[i][1] * 0.9)
+
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(len(reqs))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    results = [f.result(timeout=60) for f in futs]
+    assert co.batches < len(reqs) / 4 and co.requests == len(reqs)
+    with pytest.raises(ValueError):
+        co.submit(0, np.zeros((3, 5), np.float32), np.zeros((3, 5), np.float32))
+    co.close()
+    for (slot, X), got in zip(reqs, results):
+        n = len(X)
+        jobs = engine.jobs_to_device(engine.make_jobs([slot], [n], [0]), dev)
+        xd = torch.from_numpy(X).to(dev)
+        want = eng.infer_score(params, jobs, 1, n, xd, xd * 0.9 if False else torch.from_numpy(X * 0.9).to(dev), scale, feat, agg)
+        for k, v in got.items():
+            assert np.array_equal(v, want[k].cpu().numpy()), k
+
+
 def test_fleet_build_matches_per_machine_oracle(engine, torch):
     """build_fleet = CV folds + final fit + thresholds for all machines in one launch each; checked machine by machine against
     the oracle's fold geometry / scaler / threshold arithmetic applied to the weights the fleet trained."""
