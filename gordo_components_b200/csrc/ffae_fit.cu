@@ -11,6 +11,8 @@
 // shared memory for the backward pass, the next mini-batch is gathered with cp.async while the current one is
 // processed, and the Adam moments (opaque state, same padded layout) stream through L2.  Machines (and CV folds,
 // which are just more jobs) are independent, so the grid is simply one CTA per job.
+// A mini-batch larger than 32 rows is processed as chunks of 32 (one row per lane): the chunks' weight gradients are summed in
+// an L2-resident scratch image (second half of the opaque Adam-m state) and the optimizer runs with the last chunk.
 #include <cuda_pipeline.h>
 #include "gb_common.cuh"
 
@@ -115,12 +117,12 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
     if (a.hp.shuffle == 2) return a.perm[((long)job_id * a.hp.epochs + e) * a.max_rows + i];
     return (int)permute_index((uint32_t)i, (uint32_t)n, mix32(key_base + (uint32_t)e * 0x9e3779b9U));
   };
-  auto gather = [&](int buf, int e, int s) {
-    const int nb = min(B, n - s * B);
+  auto gather = [&](int buf, int e, int s, int c) {  // chunk c (32 rows) of mini-batch s of epoch e
+    const int nb = min(BR, min(B, n - s * B) - c * BR);
     float* xs = smem + a.xofs[buf];
     float* ys = smem + a.yofs[buf];
     for (int r = warp; r < nb; r += NWARPS) {
-      const int src = row_index(e, s * B + r);
+      const int src = row_index(e, s * B + c * BR + r);
       const float* xr = xbase + (long)src * n_in;
       const float* yr = ybase + (long)src * n_out;
       if ((n_in & 3) == 0) {
@@ -141,23 +143,29 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   int t_step = a.hp.step0;
   int cur = 0;
   __syncthreads();
-  gather(0, 0, 0);
+  gather(0, 0, 0, 0);
+  float* Gacc = Mg + a.wfloats;  // gradient sums of a multi-chunk mini-batch (same padded layout as the weights)
 
   for (int e = 0; e < a.hp.epochs; ++e) {
     float acc_sq = 0.f, acc_reg = 0.f, acc_hit = 0.f;
     for (int s = 0; s < steps; ++s) {
-      const int nb = min(B, n - s * B);
-      // ---- prefetch the next mini-batch, then wait for the current one ------------------------
-      int ne = e, ns = s + 1;
-      if (ns == steps) { ns = 0; ++ne; }
-      const bool more = ne < a.hp.epochs;
-      if (more) gather(cur ^ 1, ne, ns);
-      if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+      const int nbt = min(B, n - s * B);          // rows of this mini-batch
+      const int nchunks = (nbt + BR - 1) / BR;
       ++t_step;
       if (tid == 0) {
         const double t = (double)t_step;
         s_alpha = (float)((double)a.hp.lr * sqrt(1.0 - pow((double)a.hp.beta2, t)) / (1.0 - pow((double)a.hp.beta1, t)));
       }
+     for (int c = 0; c < nchunks; ++c) {
+      const int nb = min(BR, nbt - c * BR);        // rows of this chunk
+      const bool first_chunk = c == 0, last_chunk = c + 1 == nchunks;
+      // ---- prefetch the next chunk, then wait for the current one ------------------------
+      int ne = e, ns = s, nc = c + 1;
+      if (nc == nchunks) { nc = 0; ++ns; }
+      if (ns == steps) { ns = 0; ++ne; }
+      const bool more = ne < a.hp.epochs;
+      if (more) gather(cur ^ 1, ne, ns, nc);
+      if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
       __syncthreads();
 
       // ---- forward ---------------------------------------------------------------------------
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
         const int ip = a.apitch[l], op = a.apitch[l + 1];
         const float* Wl = sW + a.im.wofs[l];
         const float* bl = sW + a.im.bofs[l];
-        const float l1c = a.net.l1[l] * (a.hp.l1_div_batch ? 1.f : (float)nb);
+        const float l1c = a.net.l1[l] * (a.hp.l1_div_batch ? 1.f : (float)nbt);
         for (int task = warp; task < (Np >> 2); task += NWARPS) {
           const int n0 = task << 2;
           float4 acc = *reinterpret_cast<const float4*>(bl + n0);
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
         const float* yt = smem + a.yofs[cur];
         float* G = smem + a.dofs[0];
         const int NpL = a.im.np[L - 1];
-        const float gscale = 2.f / ((float)nb * (float)n_out);
+        const float gscale = 2.f / ((float)nbt * (float)n_out);
         for (int r = warp; r < BR; r += NWARPS) {
           for (int j = lane; j < NpL; j += 32) {
             float g = 0.f;
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
         float* Wl = sW + a.im.wofs[l];
         // A: dz = (G + l1*sign(a)) * act'(a)
         {
-          const float c = a.net.l1[l] / (a.hp.l1_div_batch ? (float)nb : 1.f);
+          const float c = a.net.l1[l] / (a.hp.l1_div_batch ? (float)nbt : 1.f);
           for (int r = warp; r < BR; r += NWARPS) {
             for (int j = lane; j < Np; j += 32) {
               float dz = 0.f;
@@ -305,7 +313,20 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
               g2.x = fmaf(av.z, d.x, g2.x); g2.y = fmaf(av.z, d.y, g2.y); g2.z = fmaf(av.z, d.z, g2.z); g2.w = fmaf(av.z, d.w, g2.w);
               g3.x = fmaf(av.w, d.x, g3.x); g3.y = fmaf(av.w, d.y, g3.y); g3.z = fmaf(av.w, d.z, g3.z); g3.w = fmaf(av.w, d.w, g3.w);
             }
-            const float4 gs[4] = {g0, g1, g2, g3};
+            float4 gs[4] = {g0, g1, g2, g3};
+            if (nchunks > 1) {  // multi-chunk mini-batch: sum the chunks' gradients in the L2 scratch image; Adam with the last chunk
+              float* Gl = Gacc + a.im.wofs[l];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4* gp = reinterpret_cast<float4*>(Gl + (k0 + i) * Np + n0);
+                if (!first_chunk) {
+                  const float4 o = *gp;
+                  gs[i].x += o.x; gs[i].y += o.y; gs[i].z += o.z; gs[i].w += o.w;
+                }
+                if (!last_chunk) *gp = gs[i];
+              }
+              if (!last_chunk) continue;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int off = (k0 + i) * Np + n0;
@@ -325,6 +346,10 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
             float g = 0.f;
             for (int r = 0; r < BR; ++r) g += D[r * a.dpitch + j];
             const int off = a.im.bofs[l] + j;
+            if (nchunks > 1) {
+              if (!first_chunk) g += Gacc[off];
+              if (!last_chunk) { Gacc[off] = g; continue; }
+            }
             float w = sW[off], m = Mg[off], v = Vg[off];
             adam_update(w, g, m, v, alpha, omb1, omb2, eps);
             sW[off] = w; Mg[off] = m; Vg[off] = v;
@@ -334,6 +359,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
       }
       __syncthreads();
       cur ^= 1;
+     }  // chunks
     }
     // ---- epoch statistics (keras History: sample-weighted mean of the per-batch total loss) -------------
     float v0 = acc_sq, v1 = acc_reg, v2 = acc_hit;
@@ -378,7 +404,7 @@ extern "C" {
 
 size_t gb_ffae_fit_state_stride(const gb_ffnet* net) {
   if (gb::validate_ffnet(net) != GB_OK) return 0;
-  return (size_t)gb::round_up(gb::make_ff_image(net, 4).total, 4);
+  return 2 * (size_t)gb::round_up(gb::make_ff_image(net, 4).total, 4);  // moments + gradient scratch of multi-chunk mini-batches
 }
 
 int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v, const gb_job* jobs, int32_t n_jobs,
@@ -389,8 +415,7 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
   GB_REQUIRE(params && adam_m && adam_v && jobs && x && y && hp && out_loss, GB_E_ARG,
              "params/adam_m/adam_v/jobs/x/y/hp/out_loss must be non-NULL");
   GB_REQUIRE(hp->epochs >= 1, GB_E_ARG, "epochs=%d must be >= 1", hp->epochs);
-  GB_REQUIRE(hp->batch_size >= 1 && hp->batch_size <= BR, GB_E_SHAPE,
-             "batch_size=%d: this kernel keeps one mini-batch row per lane (1..%d)", hp->batch_size, BR);
+  GB_REQUIRE(hp->batch_size >= 1, GB_E_ARG, "batch_size=%d must be >= 1", hp->batch_size);
   GB_REQUIRE(hp->shuffle >= 0 && hp->shuffle <= 2, GB_E_ARG, "shuffle=%d unknown", hp->shuffle);
   GB_REQUIRE(hp->shuffle != 2 || perm, GB_E_ARG, "shuffle=2 needs perm");
   GB_REQUIRE(gb::aligned16(params) && gb::aligned16(adam_m) && gb::aligned16(adam_v) && gb::aligned16(x) &&
