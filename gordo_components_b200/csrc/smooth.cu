@@ -99,7 +99,71 @@ __global__ void affine_f64_kernel(const gb_job* __restrict__ jobs, const double*
   }
 }
 
+// q-quantile of the non-NaN values of one column of one job (pandas Series.quantile, interpolation="linear"):
+// compacted into shared memory, padded with +inf to a power of two, bitonic sort, linear interpolation at (n-1)*q.
+constexpr int Q_THREADS = 1024;
+__global__ void __launch_bounds__(Q_THREADS) quantile_kernel(const gb_job* __restrict__ jobs, const float* __restrict__ arr, int n_cols, float q,
+                                                             float* __restrict__ out, int cap) {
+  extern __shared__ float sv[];
+  __shared__ int s_n;
+  const gb_job job = jobs[blockIdx.y];
+  const int col = blockIdx.x, tid = threadIdx.x;
+  const float* src = arr + (long)job.out_row * n_cols + col;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int r = tid; r < job.n_rows; r += Q_THREADS) {
+    const float v = src[(long)r * n_cols];
+    if (v == v) sv[atomicAdd(&s_n, 1)] = v;  // order is irrelevant before a sort
+  }
+  __syncthreads();
+  const int n = s_n;
+  int p2 = 1;
+  while (p2 < n) p2 <<= 1;
+  for (int i = n + tid; i < p2; i += Q_THREADS) sv[i] = __int_as_float(0x7f800000);
+  __syncthreads();
+  for (int k = 2; k <= p2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < p2; i += Q_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = sv[i], b = sv[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { sv[i] = b; sv[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  if (tid == 0) {
+    float res = __int_as_float(0x7fc00000);  // all-NaN / empty column -> NaN, as pandas
+    if (n > 0) {
+      const double pos = (double)(n - 1) * (double)q;
+      const int lo = (int)floor(pos), hi = min(lo + 1, n - 1);
+      const double frac = pos - (double)lo;
+      res = (float)((double)sv[lo] + ((double)sv[hi] - (double)sv[lo]) * frac);
+    }
+    out[(long)blockIdx.y * n_cols + col] = res;
+  }
+  (void)cap;
+}
+
 }  // namespace
+
+extern "C" int gb_quantile(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* arr, int32_t n_cols, float q, float* out,
+                           void* stream) {
+  GB_REQUIRE(jobs && arr && out, GB_E_ARG, "jobs/arr/out must be non-NULL");
+  GB_REQUIRE(n_cols >= 1 && n_cols <= 65535 && max_rows >= 0, GB_E_ARG, "n_cols=%d max_rows=%d", n_cols, max_rows);
+  GB_REQUIRE(q >= 0.f && q <= 1.f, GB_E_ARG, "percentiles should all be in the interval [0, 1], got %g", (double)q);
+  GB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535, GB_E_ARG, "bad n_jobs");
+  if (n_jobs == 0) return GB_OK;
+  int cap = 1;
+  while (cap < max_rows) cap <<= 1;
+  const size_t smem = (size_t)cap * sizeof(float);
+  GB_REQUIRE(smem <= 200 * 1024, GB_E_SMEM, "quantile over %d rows per job does not fit in shared memory (limit 32768 rows)", max_rows);
+  GB_CUDA_CHECK(cudaFuncSetAttribute(quantile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  quantile_kernel<<<dim3(n_cols, n_jobs), Q_THREADS, smem, (cudaStream_t)stream>>>(jobs, arr, n_cols, q, out, cap);
+  GB_CUDA_CHECK(cudaGetLastError());
+  return GB_OK;
+}
 
 extern "C" int gb_affine_f64(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const double* x, int32_t n_cols, const double* a,
                              const double* b, float* out, void* stream) {

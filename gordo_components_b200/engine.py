@@ -251,6 +251,17 @@ def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_t
     return res
 
 
+def quantile(jobs_dev, n_jobs, max_rows, arr, q: float):
+    """pandas ``.quantile(q)`` (linear interpolation, NaNs skipped) of every column of ``arr`` per job -> [n_jobs, n_cols]."""
+    torch = _torch()
+    lib = _cabi.load_library()
+    a2 = arr if arr.dim() == 2 else arr.reshape(-1, 1)
+    out = torch.empty((int(n_jobs), a2.shape[1]), dtype=torch.float32, device=a2.device)
+    p = _cabi.ptr
+    _cabi.check(lib.gb_quantile(p(jobs_dev), int(n_jobs), int(max_rows), p(a2), int(a2.shape[1]), float(q), p(out), _stream_ptr()))
+    return out
+
+
 def affine_f64(jobs_dev, n_jobs, max_rows, x64, a, b, out_rows=None):
     """Per-feature ``x * a[slot] + b[slot]`` in float64 on the device, rounded once to float32 (sklearn scalers' transform)."""
     torch = _torch()

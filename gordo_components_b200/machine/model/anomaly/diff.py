@@ -369,3 +369,89 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         extra = pd.DataFrame(np.concatenate(blocks, axis=1) if blocks else np.empty((len(data), 0)), index=data.index,
                              columns=pd.MultiIndex.from_tuples(cols))
         return pd.concat([data, extra], axis=1)
+
+
+class DiffBasedKFCVAnomalyDetector(DiffBasedAnomalyDetector):
+    """
+    diff.py:461-635: thresholds are a percentile of the *smoothed* validation errors gathered over K-fold cross-validation
+    predictions (every row is predicted by the fold model that did not see it), instead of the rolling-min/max of the last
+    TimeSeriesSplit fold.  ``anomaly`` is inherited.  Error columns, smoothing and the percentile run on the GPU
+    (gb_anomaly_score / gb_ffae_infer_score, gb_smooth, gb_quantile).
+    """
+
+    def __init__(
+        self,
+        base_estimator: BaseEstimator = KerasAutoEncoder(kind="feedforward_hourglass"),
+        scaler: TransformerMixin = MinMaxScaler(),
+        require_thresholds: bool = True,
+        shuffle: bool = True,
+        window: int = 144,
+        smoothing_method: str = "smm",
+        threshold_percentile: float = 0.99,
+    ):
+        self.base_estimator = base_estimator
+        self.scaler = scaler
+        self.require_thresholds = require_thresholds
+        self.window = window
+        self.shuffle = shuffle
+        self.smoothing_method = smoothing_method
+        self.threshold_percentile = threshold_percentile
+
+    def get_params(self, deep=True):
+        return {
+            "base_estimator": self.base_estimator, "scaler": self.scaler, "window": self.window, "smoothing_method": self.smoothing_method,
+            "shuffle": self.shuffle, "threshold_percentile": self.threshold_percentile,
+        }
+
+    def get_metadata(self):
+        metadata = dict()
+        if hasattr(self, "feature_thresholds_"):
+            metadata["feature-thresholds"] = self.feature_thresholds_.tolist()
+        if hasattr(self, "aggregate_threshold_"):
+            metadata["aggregate-threshold"] = self.aggregate_threshold_
+        if isinstance(self.base_estimator, GordoBase):
+            metadata.update(self.base_estimator.get_metadata())
+        else:
+            metadata.update({
+                "scaler": str(self.scaler), "base_estimator": str(self.base_estimator), "shuffle": self.shuffle, "window": self.window,
+                "smoothing-method": self.smoothing_method, "threshold-percentile": self.threshold_percentile,
+            })
+        return metadata
+
+    def cross_validate(self, *, X, y, cv=None, **kwargs):
+        from sklearn.model_selection import KFold
+
+        from .... import engine
+
+        cv = cv if cv is not None else KFold(n_splits=5, shuffle=True, random_state=0)
+        kwargs.update(dict(return_estimator=True, cv=cv))
+        cv_output = sk_cross_validate(self, X=X, y=y, **kwargs)
+
+        yv = _values(y)
+        n, t = yv.shape
+        columns = list(y.columns) if hasattr(y, "columns") else list(range(t))
+        abs_err = np.zeros((n, t), dtype=np.float32)
+        val_mse = np.full((n,), np.nan, dtype=np.float32)
+        for (_, test_idxs), fold in zip(kwargs["cv"].split(X, y), cv_output["estimator"]):
+            X_test = X.iloc[test_idxs] if isinstance(X, pd.DataFrame) else X[test_idxs]
+            y_test = y.iloc[test_idxs] if isinstance(y, pd.DataFrame) else y[test_idxs]
+            res = self._score(fold, X_test, y_test, fold.scaler, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
+            if len(res["model-output"]) != len(test_idxs):
+                raise ValueError("K-fold thresholds need a base estimator that predicts one row per input row")
+            abs_err[test_idxs] = res["tag-anomaly-unscaled"]
+            val_mse[test_idxs] = res["total-anomaly-scaled"]
+
+        dev = engine.cuda_device()
+        torch = engine._torch()
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+        q = float(self.threshold_percentile)
+
+        def threshold(metric: np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(metric, dtype=np.float32)).to(dev)
+            if self.window is not None and self.smoothing_method is not None:
+                a = engine.smooth(jobs, 1, a, int(self.window), self.smoothing_method)
+            return engine.quantile(jobs, 1, n, a, q)[0].cpu().numpy().astype(np.float64)
+
+        self.aggregate_threshold_ = float(threshold(val_mse)[0])
+        self.feature_thresholds_ = pd.Series(threshold(abs_err), index=columns)
+        return cv_output

@@ -139,6 +139,12 @@ int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const fl
 int gb_smooth(const gb_job* jobs, int32_t n_jobs, const float* arr, int32_t n_cols, int32_t window, int32_t method,
               float* out, void* stream);
 
+/* ---- K9: percentile thresholds of DiffBasedKFCVAnomalyDetector (diff.py:623-635: smoothed validation metric
+ * .quantile(threshold_percentile)).  out[job][c] = q-quantile (linear interpolation, NaNs skipped -- pandas
+ * semantics) of column c of rows [out_row, out_row+n_rows) of arr [rows][n_cols]; at most 32768 rows per job. */
+int gb_quantile(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* arr, int32_t n_cols, float q,
+                float* out, void* stream);
+
 /* ---- K8: per-feature affine pre-transform (sklearn MinMaxScaler/StandardScaler/... .transform in front of the
  * network inside a Pipeline: gordo serializer pipelines, e.g. examples/config_crd.yaml "sklearn.preprocessing.MinMaxScaler")
  *   out[out_row+r][c] = (float)(x[x_row+r][c] * a[slot][c] + b[slot][c]), computed in double like sklearn and rounded once,

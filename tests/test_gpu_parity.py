@@ -583,6 +583,63 @@ def test_detector_with_scaler_pipeline(engine, torch, chain):
     close(frame["tag-anomaly-unscaled"].values, want["tag-anomaly-unscaled"], name="tag-anomaly-unscaled")
 
 
+@pytest.mark.parametrize("n_rows,window,method,q", [(300, 12, "smm", 0.99), (300, 144, "sma", 0.9), (1000, 6, "ewma", 0.5)])
+def test_kfcv_detector_thresholds(engine, torch, n_rows, window, method, q):
+    """DiffBasedKFCVAnomalyDetector (diff.py:461-635; reference test test_anomaly_detectors.py:374-487): percentile of the
+    smoothed K-fold validation errors.  Thresholds are re-derived with pandas from the fold models the detector trained."""
+    from sklearn.model_selection import KFold
+
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedKFCVAnomalyDetector
+    from gordo_components_b200.machine.model.models import KerasAutoEncoder
+    from oracle import anomaly_math as am
+    from oracle import keras_math as km
+
+    np.random.seed(3)
+    T = 6
+    t = np.linspace(0, 30, n_rows)[:, None]
+    Xv = 0.5 + 0.4 * np.sin(t * np.linspace(0.5, 2, T)) + np.random.normal(0, 0.03, (n_rows, T))
+    cols = [f"tag-{i}" for i in range(T)]
+    X = pd.DataFrame(Xv, columns=cols, index=pd.date_range("2019-01-01", periods=n_rows, freq="10min", tz="UTC"))
+    det = DiffBasedKFCVAnomalyDetector(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass", epochs=2), window=window,
+                                       smoothing_method=method, threshold_percentile=q)
+    assert det.get_params() == dict(base_estimator=det.base_estimator, scaler=det.scaler, window=window, smoothing_method=method, shuffle=True,
+                                    threshold_percentile=q)
+    with pytest.raises(AttributeError):
+        det.fit(X, X).anomaly(X, X)
+    cvo = det.cross_validate(X=X, y=X)
+    spec = km.ff_hourglass_spec(T)
+    abs_err = np.zeros((n_rows, T))
+    mse = np.zeros(n_rows)
+    for (tr, te), fold in zip(KFold(n_splits=5, shuffle=True, random_state=0).split(X, X), cvo["estimator"]):
+        pred = km.ff_forward(spec, fold.base_estimator.model.weights, Xv[te], np.float64)
+        abs_err[te] = np.abs(pred - Xv[te])
+        mse[te] = (((pred - Xv[te]) * fold.scaler.scale_) ** 2).mean(axis=1)
+    want_feat = pd.DataFrame(am.smoothing(abs_err, window, method)).quantile(q).values
+    want_agg = pd.Series(am.smoothing(mse, window, method)).quantile(q)
+    close(det.feature_thresholds_.values, want_feat, rtol=2e-3, mag=1e-4, name="KFCV feature thresholds")
+    close(det.aggregate_threshold_, want_agg, rtol=2e-3, mag=1e-6, name="KFCV aggregate threshold")
+    md = det.get_metadata()
+    assert not np.isnan(md["feature-thresholds"]).any() and not np.isnan(md["aggregate-threshold"])
+    det.fit(X, X)
+    frame = det.anomaly(X, X)
+    assert "smooth-total-anomaly-scaled" in frame.columns.get_level_values(0) and "total-anomaly-confidence" in frame.columns.get_level_values(0)
+
+
+def test_quantile_kernel_matches_pandas(engine, torch):
+    rng = np.random.default_rng(0)
+    dev = engine.cuda_device()
+    for n, cols in [(1, 3), (2, 1), (777, 5), (4096, 2), (10000, 3)]:
+        a = rng.normal(size=(n, cols)).astype(np.float32)
+        a[rng.random(a.shape) < 0.1] = np.nan
+        if n > 100:
+            a[:, 0] = np.nan  # an all-NaN column stays NaN
+        jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
+        for q in (0.0, 0.37, 0.99, 1.0):
+            got = engine.quantile(jobs, 1, n, torch.from_numpy(a).to(dev), q)[0].cpu().numpy()
+            want = pd.DataFrame(a.astype(np.float64)).quantile(q).values
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-7, equal_nan=True), (n, q, got, want)
+
+
 def test_request_coalescer_equals_per_request_launches(engine, torch):
     """serving.AnomalyCoalescer: 120 concurrent requests of 1..150 rows for random machines come back bit-identical to one
     launch per request (rows are independent in the kernel), in far fewer launches."""

@@ -227,6 +227,24 @@ def test_detector_protocol():
         DiffBasedAnomalyDetector(base_estimator=base, require_thresholds=True).anomaly(frame, frame)
 
 
+def test_kfcv_detector_protocol():
+    """test_anomaly_detectors.py:403-424, 675-732: constructor defaults, get_params, metadata keys, clone / pickle."""
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedKFCVAnomalyDetector
+
+    base = KerasAutoEncoder(kind="feedforward_hourglass")
+    sc = MinMaxScaler()
+    d = DiffBasedKFCVAnomalyDetector(base_estimator=base, scaler=sc)
+    assert isinstance(d, DiffBasedAnomalyDetector) and isinstance(d, AnomalyDetectorBase)
+    assert d.get_params() == dict(base_estimator=base, scaler=sc, window=144, smoothing_method="smm", shuffle=True, threshold_percentile=0.99)
+    assert "feature-thresholds" not in d.get_metadata()
+    c = clone(d)
+    assert c.threshold_percentile == 0.99 and c.base_estimator is not base
+    pickle.loads(pickle.dumps(d))
+    frame = pd.DataFrame(np.zeros((3, 3)))
+    with pytest.raises(AttributeError):
+        d.anomaly(frame, frame)
+
+
 def test_scaler_multiplier():
     from sklearn.preprocessing import QuantileTransformer, RobustScaler
 
