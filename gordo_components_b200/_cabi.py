@@ -23,7 +23,7 @@ ACT_CODES = {"linear": 0, None: 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 EXPORTS = (
     "gb_abi_version", "gb_last_error", "gb_device_check", "gb_ffnet_param_count", "gb_ffnet_param_stride",
     "gb_ffae_infer_score", "gb_ffae_tc_supported", "gb_anomaly_score", "gb_minmax_fit", "gb_thresholds", "gb_smooth", "gb_quantile", "gb_affine_f64", "gb_ffae_fit_state_stride", "gb_ffae_fit",
-    "gb_lstm_param_count", "gb_lstm_param_stride", "gb_lstm_workspace_bytes", "gb_lstm_infer", "gb_lstm_fit_workspace_bytes", "gb_lstm_fit",
+    "gb_lstm_param_count", "gb_lstm_param_stride", "gb_lstm_workspace_bytes", "gb_lstm_infer", "gb_lstm_tc_supported", "gb_lstm_tc_workspace_bytes", "gb_lstm_infer_tc", "gb_lstm_fit_workspace_bytes", "gb_lstm_fit",
 )
 
 
@@ -94,6 +94,12 @@ def _declare(lib):
     lib.gb_ffae_fit.argtypes = [C.POINTER(GbFFNet), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P,
                                 C.POINTER(GbFitHParams), _P, _P, _P]
     lib.gb_lstm_infer.argtypes = [C.POINTER(GbLstmNet), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]
+    lib.gb_lstm_tc_supported.argtypes = [C.POINTER(GbLstmNet)]
+    lib.gb_lstm_tc_supported.restype = C.c_int
+    lib.gb_lstm_tc_workspace_bytes.argtypes = [C.POINTER(GbLstmNet), C.c_int32, C.c_int32, C.c_int32, C.c_int64]
+    lib.gb_lstm_tc_workspace_bytes.restype = C.c_size_t
+    lib.gb_lstm_infer_tc.argtypes = [C.POINTER(GbLstmNet), _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P]
+    lib.gb_lstm_infer_tc.restype = C.c_int
     lib.gb_lstm_fit_workspace_bytes.restype = C.c_size_t
     lib.gb_lstm_fit_workspace_bytes.argtypes = [C.POINTER(GbLstmNet), C.c_int32]
     lib.gb_lstm_fit.argtypes = [C.POINTER(GbLstmNet), _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(GbLstmFitHParams), _P, _P, _P, _P]

@@ -1,0 +1,486 @@
+// K3, variant 2: LSTM autoencoder prediction on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), machine-batched.
+//
+// Replaces KerasLSTMBaseEstimator.predict (gordo/machine/model/models.py:618-660) for the stacks of
+// factories/lstm_autoencoder.py:72-103 whose layer widths are multiples of 64 (lstm_symmetric's 256/128/64 defaults --
+// BASELINE configs[3]); other stacks take lstm_infer.cu.  Windows are index arithmetic, never materialised (:713-793).
+//
+// 335 MFLOP per 144 x 128 window is tensor-core work.  One launch advances EVERY window of EVERY job by one (layer,
+// timestep): a CTA owns a tile of 128 windows x 64 units and computes the four gate pre-activations
+//      z[128, 4 x 64] = [h_below,t | h_own,t-1] (128 x K)  .  [K; U]^T (K x 256)
+// as tcgen05.mma (M=128, N=256, K=16 per instruction) with both operands brought to shared memory by TMA (SWIZZLE_128B
+// K-major boxes, two-stage ring), accumulates in TMEM, and finishes the cell in the epilogue: gates, c_t, h_t, with h_t
+// written straight back as the next launches' A operand.  The recurrent state of all windows lives in HBM (h as an FP16
+// pair, c in fp32): per timestep that is a few GB of traffic against tens of TFLOP of contraction.
+//
+// Numerics (1e-4 parity): h in (-1, 1) and the weights are split into FP16 pairs (a = a1 + a2, 22 significant bits) and
+// every product is formed as a2*w1 + a1*w2 + a1*w1 with fp32 accumulation -- the scheme of ffae_infer_tc.cu's layers >= 1.
+// The raw input x (any magnitude) never enters an FP16 operand: its projection x.K0 + b0 is computed once per ROW (not
+// per window) in fp32 on the CUDA cores and added in layer 0's epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "gb_common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;            // windows per CTA
+constexpr int UB = 64;               // units per CTA
+constexpr int NCOL = 4 * UB;         // gate columns per CTA (accumulator width in TMEM)
+constexpr int KC = 64;               // K elements per pipeline chunk (one 128-byte swizzle row of FP16)
+constexpr int STAGES = 2;
+constexpr int A_BOX = TILE * 128;    // bytes: 128 rows x 64 FP16
+constexpr int B_BOX = NCOL * 128;    // bytes: 256 rows x 64 FP16
+constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_BOX;
+constexpr int NTHREADS = 192;        // warps 0-3: epilogue (one thread = one window), warp 4: TMA producer, warp 5: MMA issuer
+
+struct TcLayerArgs {
+  int u, kc_below, kc_own;           // units; K chunks coming from the layer below / from this layer's own h
+  int act, is_first;
+  int tiles_per_job, t, lookback;
+  const gb_job* jobs;
+  const float* bias;                 // [n_slots][4u] reordered (layers >= 1; layer 0's bias lives in xk)
+  const float* xk;                   // layer 0: [x rows][4u] reordered input projection
+  long xk_rows;
+  float* c;                          // [rows][u]
+  __half *h_out_hi, *h_out_lo;       // [rows][u]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], FP16 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); the K step inside the swizzle
+// row is taken by advancing the start address (32 bytes per K=16 FP16 step)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {  // D fp32, A/B FP16, both K-major, M = 128
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float sigm(float z) { return 1.f / (1.f + expf(-z)); }
+
+// ------------------------------------------------------------------------------------------------ one (layer, timestep) for all windows
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_below_hi, const __grid_constant__ CUtensorMap m_below_lo,
+                    const __grid_constant__ CUtensorMap m_own_hi, const __grid_constant__ CUtensorMap m_own_lo,
+                    const __grid_constant__ CUtensorMap m_w_hi, const __grid_constant__ CUtensorMap m_w_lo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) unsigned long long s_bar[2 * STAGES + 1];
+  __shared__ float s_bias[NCOL];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, ub = blockIdx.y;
+  const int job_id = tile / a.tiles_per_job, tj = tile - job_id * a.tiles_per_job;
+  const gb_job job = a.jobs[job_id];
+  if (tj * TILE >= job.n_rows) return;  // uniform: nothing of this tile is a real window
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[STAGES]), bar_done = smem_u32(&s_bar[2 * STAGES]);
+  const int u = a.u;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(NCOL) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (!a.is_first)
+    for (int i = tid; i < NCOL; i += NTHREADS) s_bias[i] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int n_chunks = a.kc_below + a.kc_own;
+  const int row0 = tile * TILE;                       // first row of this tile in the state arrays
+  const int wrow0 = job.slot * 4 * u + ub * NCOL;      // first row of this unit block in the weight images
+
+  if (warp == 4) {
+    // ============================== TMA producer
+    if (lane == 0) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % STAGES, it = c / STAGES;
+        if (it > 0) mbar_wait(bar_empty + 8 * s, (it - 1) & 1);
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        const bool below = c < a.kc_below;
+        const int acol = (below ? c : c - a.kc_below) * KC;
+        tma_load_2d(st, below ? &m_below_hi : &m_own_hi, acol, row0, bar_full + 8 * s);
+        tma_load_2d(st + A_BOX, below ? &m_below_lo : &m_own_lo, acol, row0, bar_full + 8 * s);
+        tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0, bar_full + 8 * s);
+        tma_load_2d(st + 2 * A_BOX + B_BOX, &m_w_lo, c * KC, wrow0, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer
+    const uint32_t idesc = make_idesc_f16(NCOL);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c % STAGES, it = c / STAGES;
+      mbar_wait(bar_full + 8 * s, it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_BOX);
+        const uint64_t b_hi = make_desc_sw128(st + 2 * A_BOX), b_lo = make_desc_sw128(st + 2 * A_BOX + B_BOX);
+#pragma unroll
+        for (int ks = 0; ks < KC / 16; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K step, in 16-byte units of the address field
+          mma_f16_ss(tmem, a_lo + adv, b_hi + adv, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+          mma_f16_ss(tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+          mma_f16_ss(tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+        }
+        mma_commit(bar_empty + 8 * s);
+        if (c + 1 == n_chunks) mma_commit(bar_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================== epilogue: gates, cell, h (one thread = one window)
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int r = tid;  // 0..127
+    const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
+    const long row = (long)row0 + r;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* xk = nullptr;
+    if (a.is_first) {
+      const long xr = job.x_row + min(w, job.n_rows - 1) + a.t;
+      xk = a.xk + min(xr, a.xk_rows - 1) * (long)(4 * u) + ub * NCOL;
+    }
+    float* crow = a.c + row * u + ub * UB;
+    __half* hh = a.h_out_hi + row * u + ub * UB;
+    __half* hl = a.h_out_lo + row * u + ub * UB;
+#pragma unroll 1
+    for (int j0 = 0; j0 < UB; j0 += 8) {
+      float z[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0, z[g]);
+      tmem_wait_ld();
+      float add[4][8];
+      if (a.is_first) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0)), q = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0 + 4));
+          add[g][0] = p.x; add[g][1] = p.y; add[g][2] = p.z; add[g][3] = p.w; add[g][4] = q.x; add[g][5] = q.y; add[g][6] = q.z; add[g][7] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) add[g][i] = s_bias[g * UB + j0 + i];
+      }
+      float cprev[8];
+      {
+        const float4 p = *reinterpret_cast<const float4*>(crow + j0), q = *reinterpret_cast<const float4*>(crow + j0 + 4);
+        cprev[0] = p.x; cprev[1] = p.y; cprev[2] = p.z; cprev[3] = p.w; cprev[4] = q.x; cprev[5] = q.y; cprev[6] = q.z; cprev[7] = q.w;
+      }
+      float cn[8];
+      __align__(16) __half h1[8], h2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ig = sigm(z[0][i] + add[0][i]), fg = sigm(z[1][i] + add[1][i]);
+        const float gg = gb::apply_act(a.act, z[2][i] + add[2][i]), og = sigm(z[3][i] + add[3][i]);
+        cn[i] = fmaf(fg, a.t == 0 ? 0.f : cprev[i], ig * gg);
+        const float h = og * gb::apply_act(a.act, cn[i]);
+        h1[i] = __float2half_rn(h);
+        h2[i] = __float2half_rn(h - __half2float(h1[i]));
+      }
+      *reinterpret_cast<float4*>(crow + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      *reinterpret_cast<float4*>(crow + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
+      *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NCOL) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ preparation kernels (fp32 CUDA cores)
+// reordered gate column n' = ub*256 + g*64 + j  <->  keras column g*u + ub*64 + j
+__device__ __forceinline__ int keras_col(int np, int u) {
+  const int ub = np >> 8, g = (np >> 6) & 3, j = np & 63;
+  return g * u + ub * UB + j;
+}
+
+// weight images of one layer: rows n' (4u per slot), K contiguous: [below part padded to 64 | own part], FP16 pair
+__global__ void lstm_tc_weights_kernel(const float* __restrict__ params, long pstride, long kofs, int in, int u, int kp_below, int kp, int use_below,
+                                       __half* __restrict__ w_hi, __half* __restrict__ w_lo, float* __restrict__ bias) {
+  const int slot = blockIdx.y;
+  const float* P = params + (long)slot * pstride + kofs;  // kernel [in][4u], recurrent [u][4u], bias [4u]
+  const int u4 = 4 * u;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)u4 * kp; i += (long)gridDim.x * blockDim.x) {
+    const int np = (int)(i / kp), k = (int)(i - (long)np * kp);
+    const int col = keras_col(np, u);
+    float v = 0.f;
+    if (k < kp_below) {
+      if (use_below && k < in) v = P[(long)k * u4 + col];
+    } else if (k - kp_below < u) {
+      v = P[(long)(in + k - kp_below) * u4 + col];
+    }
+    const __half h = __float2half_rn(v);
+    w_hi[((long)slot * u4 + np) * kp + k] = h;
+    w_lo[((long)slot * u4 + np) * kp + k] = __float2half_rn(v - __half2float(h));
+  }
+  if (blockIdx.x == 0)
+    for (int np = threadIdx.x; np < u4; np += blockDim.x) bias[(long)slot * u4 + np] = P[(long)(in + u) * u4 + keras_col(np, u)];
+}
+
+// layer 0 input projection per ROW: xk[row][n'] = x[row] . K0[:, col(n')] + b0[col(n')]; grid (ceil(rows/32), 4u/64, jobs)
+__global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restrict__ jobs, const float* __restrict__ x, int F, int u, int lookback,
+                                                         const float* __restrict__ params, long pstride, float* __restrict__ xk) {
+  const gb_job job = jobs[blockIdx.z];
+  const int n_x = job.n_rows + lookback - 1;  // x rows this job's windows touch
+  const int r0 = blockIdx.x * 32;
+  if (r0 >= n_x) return;
+  const float* P = params + (long)job.slot * pstride;  // layer 0: kernel [F][4u] first
+  const int u4 = 4 * u, c0 = blockIdx.y * 64;
+  __shared__ float sA[32][33];
+  __shared__ float sW[32][65];
+  const int tid = threadIdx.x, col = tid & 63, rg = tid >> 6;
+  const int kc = keras_col(c0 + col, u);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < F; k0 += 32) {
+    for (int i = tid; i < 32 * 32; i += 256) {
+      const int b = i >> 5, k = k0 + (i & 31);
+      sA[b][i & 31] = (r0 + b < n_x && k < F) ? __ldg(x + (job.x_row + r0 + b) * (long)F + k) : 0.f;
+    }
+    for (int i = tid; i < 32 * 64; i += 256) {
+      const int kk = i >> 6, c = i & 63, k = k0 + kk;
+      sW[kk][c] = k < F ? __ldg(P + (long)k * u4 + keras_col(c0 + c, u)) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const float w = sW[kk][col];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(sA[rg + 4 * i][kk], w, acc[i]);
+    }
+    __syncthreads();
+  }
+  const float b = __ldg(P + (long)(F + u) * u4 + kc);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + rg + 4 * i;
+    if (r < n_x) xk[(job.x_row + r) * (long)u4 + c0 + col] = acc[i] + b;
+  }
+}
+
+// Dense head on the last layer's final h: out[w][o] = act(sum_k h[w][k] Wd[k][o] + bd[o]); grid (tiles, jobs)
+__global__ void __launch_bounds__(128) lstm_tc_head_kernel(const gb_job* __restrict__ jobs, int tiles_per_job, const __half* __restrict__ h_hi,
+                                                           const __half* __restrict__ h_lo, int u, int n_out, int out_act, const float* __restrict__ params,
+                                                           long pstride, long dofs, float* __restrict__ out) {
+  const gb_job job = jobs[blockIdx.y];
+  const int w = blockIdx.x * TILE + threadIdx.x;
+  if (w >= job.n_rows) return;
+  const long row = ((long)blockIdx.y * tiles_per_job + blockIdx.x) * TILE + threadIdx.x;
+  const float* Wd = params + (long)job.slot * pstride + dofs;
+  const float* bd = Wd + (long)u * n_out;
+  for (int o = 0; o < n_out; ++o) {
+    float acc = __ldg(bd + o);
+    for (int k = 0; k < u; ++k) acc = fmaf(__half2float(h_hi[row * u + k]) + __half2float(h_lo[row * u + k]), __ldg(Wd + (long)k * n_out + o), acc);
+    out[(job.out_row + w) * (long)n_out + o] = gb::apply_act(out_act, acc);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  return fn = reinterpret_cast<EncodeTiledFn>(p);
+}
+// [rows][cols] FP16 row-major, box = 64 columns x box_rows rows, SWIZZLE_128B
+int make_map_f16(CUtensorMap* map, const void* base, long rows, long cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  GB_REQUIRE(fn != nullptr, GB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+  cuuint32_t box[2] = {KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_REQUIRE(r == CUDA_SUCCESS, GB_E_CUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
+  return GB_OK;
+}
+
+struct Plan {
+  int nl, F, n_out, L;
+  int u[GB_MAX_LAYERS], in[GB_MAX_LAYERS], kp_below[GB_MAX_LAYERS], kp[GB_MAX_LAYERS];
+  long kofs[GB_MAX_LAYERS], dofs;
+  // workspace offsets (bytes)
+  size_t w_hi[GB_MAX_LAYERS], w_lo[GB_MAX_LAYERS], bias[GB_MAX_LAYERS], h_hi[GB_MAX_LAYERS][2], h_lo[GB_MAX_LAYERS][2], c[GB_MAX_LAYERS], xk, total;
+  size_t state_begin, state_end;
+};
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+void make_plan(const gb_lstmnet* net, int n_slots, long rows_pad, long x_rows, Plan* p) {
+  p->nl = net->n_layers; p->F = net->n_features; p->n_out = net->n_features_out; p->L = net->lookback;
+  long pofs = 0;
+  int in = net->n_features;
+  size_t ofs = 0;
+  for (int l = 0; l < p->nl; ++l) {
+    const int u = net->units[l];
+    p->u[l] = u; p->in[l] = in;
+    p->kofs[l] = pofs;
+    pofs += 4L * u * (in + u + 1);
+    p->kp_below[l] = l == 0 ? 0 : gb::round_up(in, KC);
+    p->kp[l] = p->kp_below[l] + u;
+    p->w_hi[l] = ofs; ofs = align256(ofs + (size_t)n_slots * 4 * u * p->kp[l] * sizeof(__half));
+    p->w_lo[l] = ofs; ofs = align256(ofs + (size_t)n_slots * 4 * u * p->kp[l] * sizeof(__half));
+    p->bias[l] = ofs; ofs = align256(ofs + (size_t)n_slots * 4 * u * sizeof(float));
+    in = u;
+  }
+  p->dofs = pofs;
+  p->xk = ofs; ofs = align256(ofs + (size_t)x_rows * 4 * net->units[0] * sizeof(float));
+  p->state_begin = ofs;
+  for (int l = 0; l < p->nl; ++l) {
+    const size_t hb = (size_t)rows_pad * p->u[l] * sizeof(__half);
+    for (int b = 0; b < 2; ++b) {
+      p->h_hi[l][b] = ofs; ofs = align256(ofs + hb);
+      p->h_lo[l][b] = ofs; ofs = align256(ofs + hb);
+    }
+    p->c[l] = ofs; ofs = align256(ofs + (size_t)rows_pad * p->u[l] * sizeof(float));
+  }
+  p->state_end = ofs;
+  p->total = ofs;
+}
+
+}  // namespace
+
+extern "C" int gb_lstm_tc_supported(const gb_lstmnet* net) {
+  GB_REQUIRE(net != nullptr, GB_E_ARG, "net is NULL");
+  GB_REQUIRE(net->n_layers >= 1 && net->n_layers <= GB_MAX_LAYERS, GB_E_SHAPE, "n_layers=%d outside [1,%d]", net->n_layers, GB_MAX_LAYERS);
+  for (int l = 0; l < net->n_layers; ++l)
+    GB_REQUIRE(net->units[l] >= UB && net->units[l] % UB == 0 && net->units[l] <= 512, GB_E_SHAPE,
+               "tcgen05 LSTM variant needs layer widths that are multiples of %d (<= 512), units[%d]=%d", UB, l, net->units[l]);
+  GB_REQUIRE(net->n_features >= 1 && net->n_features <= 512 && net->n_features_out >= 1 && net->n_features_out <= 512, GB_E_SHAPE, "bad feature counts");
+  GB_REQUIRE(net->lookback >= 1, GB_E_ARG, "lookback=%d must be >= 1", net->lookback);
+  return GB_OK;
+}
+
+// x_rows: rows of the x array (the input projection is indexed by absolute x row)
+extern "C" size_t gb_lstm_tc_workspace_bytes(const gb_lstmnet* net, int32_t n_slots, int32_t n_jobs, int32_t max_windows, int64_t x_rows) {
+  if (gb_lstm_tc_supported(net) != GB_OK || n_jobs < 0 || max_windows < 0 || n_slots < 0) return 0;
+  Plan p;
+  const long tiles_per_job = (max_windows + TILE - 1) / TILE;
+  make_plan(net, n_slots, (long)n_jobs * tiles_per_job * TILE, x_rows, &p);
+  return p.total;
+}
+
+extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int32_t n_slots, const gb_job* jobs, int32_t n_jobs, int32_t max_windows,
+                                const float* x, int64_t x_rows, float* out_model, void* workspace, void* stream) {
+  int rc = gb_lstm_tc_supported(net);
+  if (rc != GB_OK) return rc;
+  GB_REQUIRE(params && jobs && x && out_model && workspace, GB_E_ARG, "params/jobs/x/out_model/workspace must be non-NULL");
+  GB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && max_windows >= 0 && n_slots >= 1 && x_rows >= 1, GB_E_ARG, "bad n_jobs/max_windows/n_slots/x_rows");
+  GB_REQUIRE(gb::aligned16(workspace), GB_E_ALIGN, "workspace must be 16-byte aligned");
+  if (n_jobs == 0 || max_windows == 0) return GB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_per_job = (max_windows + TILE - 1) / TILE;
+  const long rows_pad = (long)n_jobs * tiles_per_job * TILE;
+  Plan p;
+  make_plan(net, n_slots, rows_pad, x_rows, &p);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const long pstride = (long)gb_lstm_param_stride(net);
+
+  // ---- operands that do not depend on the timestep
+  for (int l = 0; l < p.nl; ++l)
+    lstm_tc_weights_kernel<<<dim3(64, n_slots), 256, 0, st>>>(params, pstride, p.kofs[l], p.in[l], p.u[l], p.kp_below[l], p.kp[l], l > 0,
+                                                               reinterpret_cast<__half*>(ws + p.w_hi[l]), reinterpret_cast<__half*>(ws + p.w_lo[l]),
+                                                               reinterpret_cast<float*>(ws + p.bias[l]));
+  const int xr_max = max_windows + p.L - 1;
+  lstm_tc_xk_kernel<<<dim3((xr_max + 31) / 32, 4 * p.u[0] / 64, n_jobs), 256, 0, st>>>(jobs, x, p.F, p.u[0], p.L, params, pstride,
+                                                                                       reinterpret_cast<float*>(ws + p.xk));
+  GB_CUDA_CHECK(cudaMemsetAsync(ws + p.state_begin, 0, p.state_end - p.state_begin, st));
+  GB_CUDA_CHECK(cudaGetLastError());
+
+  CUtensorMap m_h[GB_MAX_LAYERS][2][2], m_w[GB_MAX_LAYERS][2];
+  for (int l = 0; l < p.nl; ++l) {
+    for (int b = 0; b < 2; ++b) {
+      if ((rc = make_map_f16(&m_h[l][b][0], ws + p.h_hi[l][b], rows_pad, p.u[l], TILE)) != GB_OK) return rc;
+      if ((rc = make_map_f16(&m_h[l][b][1], ws + p.h_lo[l][b], rows_pad, p.u[l], TILE)) != GB_OK) return rc;
+    }
+    if ((rc = make_map_f16(&m_w[l][0], ws + p.w_hi[l], (long)n_slots * 4 * p.u[l], p.kp[l], NCOL)) != GB_OK) return rc;
+    if ((rc = make_map_f16(&m_w[l][1], ws + p.w_lo[l], (long)n_slots * 4 * p.u[l], p.kp[l], NCOL)) != GB_OK) return rc;
+  }
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  // ---- the recurrence: h of (layer, t) is written to buffer t & 1 and read from buffer (t - 1) & 1 (zero at t = 0)
+  for (int t = 0; t < p.L; ++t) {
+    const int wr = t & 1, rd = wr ^ 1;
+    for (int l = 0; l < p.nl; ++l) {
+      TcLayerArgs a{};
+      a.u = p.u[l]; a.kc_below = p.kp_below[l] / KC; a.kc_own = p.u[l] / KC; a.act = net->act[l]; a.is_first = l == 0;
+      a.tiles_per_job = tiles_per_job; a.t = t; a.lookback = p.L; a.jobs = jobs;
+      a.bias = reinterpret_cast<const float*>(ws + p.bias[l]);
+      a.xk = reinterpret_cast<const float*>(ws + p.xk); a.xk_rows = x_rows;
+      a.c = reinterpret_cast<float*>(ws + p.c[l]);
+      a.h_out_hi = reinterpret_cast<__half*>(ws + p.h_hi[l][wr]);
+      a.h_out_lo = reinterpret_cast<__half*>(ws + p.h_lo[l][wr]);
+      const int lb = l > 0 ? l - 1 : 0;
+      lstm_tc_step_kernel<<<dim3(n_jobs * tiles_per_job, p.u[l] / UB), NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1],
+                                                                                             m_w[l][0], m_w[l][1]);
+    }
+  }
+  const int top = p.nl - 1, fin = (p.L - 1) & 1;
+  lstm_tc_head_kernel<<<dim3(tiles_per_job, n_jobs), TILE, 0, st>>>(jobs, tiles_per_job, reinterpret_cast<const __half*>(ws + p.h_hi[top][fin]),
+                                                                     reinterpret_cast<const __half*>(ws + p.h_lo[top][fin]), p.u[top], p.n_out, net->out_act,
+                                                                     params, pstride, p.dofs, out_model);
+  GB_CUDA_CHECK(cudaGetLastError());
+  return GB_OK;
+}

@@ -362,11 +362,26 @@ class LSTMEngine:
                                          C.byref(hp), p(ws), p(loss), p(acc), _stream_ptr()))
         return loss, acc, (m, v, t)
 
-    def infer(self, params, jobs_dev, n_jobs, max_windows, x, out_rows):
-        """out[j] = net(x[j : j + lookback]) for every job's windows (jobs' n_rows counts windows)."""
+    @property
+    def tc_supported(self) -> bool:
+        return self.lib.gb_lstm_tc_supported(C.byref(self.net)) == 0
+
+    def infer(self, params, jobs_dev, n_jobs, max_windows, x, out_rows, variant: int = 0):
+        """
+        out[j] = net(x[j : j + lookback]) for every job's windows (jobs' n_rows counts windows).
+        variant 0 = tcgen05 kernel when the layer widths allow it, 1 = fp32 CUDA-core kernel, 2 = tcgen05 (error if unsupported).
+        """
         torch = _torch()
         out = torch.empty((int(out_rows), self.n_out), dtype=torch.float32, device=self.device)
         p = _cabi.ptr
+        if variant == 2 or (variant == 0 and self.tc_supported):
+            ws_bytes = int(self.lib.gb_lstm_tc_workspace_bytes(C.byref(self.net), int(params.shape[0]), int(n_jobs), int(max_windows), int(x.shape[0])))
+            if ws_bytes == 0:
+                _cabi.check(self.lib.gb_lstm_tc_supported(C.byref(self.net)))
+            ws = torch.empty((ws_bytes + 255,), dtype=torch.uint8, device=self.device)
+            _cabi.check(self.lib.gb_lstm_infer_tc(C.byref(self.net), p(params), int(params.shape[0]), p(jobs_dev), int(n_jobs), int(max_windows), p(x),
+                                                  int(x.shape[0]), p(out), p(ws), _stream_ptr()))
+            return out
         _cabi.check(self.lib.gb_lstm_infer(C.byref(self.net), p(params), p(jobs_dev), int(n_jobs), int(max_windows), p(x), p(out), None, _stream_ptr()))
         return out
 

@@ -207,6 +207,15 @@ size_t gb_lstm_workspace_bytes(const gb_lstmnet* net, int32_t n_jobs, int32_t ma
 int gb_lstm_infer(const gb_lstmnet* net, const float* params, const gb_job* jobs, int32_t n_jobs,
                   int32_t max_rows, const float* x, float* out_model, void* workspace, void* stream);
 
+/* ---- K3 on tcgen05: stacks whose layer widths are multiples of 64 (lstm_symmetric's 256/128/64).  One launch per
+ * (layer, timestep) advances every window of every job: [h_below,t | h_own,t-1] . [K; U]^T on the tensor cores
+ * (FP16-pair split operands, fp32 accumulation in TMEM), LSTM cell in the epilogue, recurrent state in `workspace`
+ * (gb_lstm_tc_workspace_bytes; x_rows = rows of the x array, n_slots = rows of params). */
+int gb_lstm_tc_supported(const gb_lstmnet* net);
+size_t gb_lstm_tc_workspace_bytes(const gb_lstmnet* net, int32_t n_slots, int32_t n_jobs, int32_t max_windows, int64_t x_rows);
+int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int32_t n_slots, const gb_job* jobs, int32_t n_jobs,
+                     int32_t max_windows, const float* x, int64_t x_rows, float* out_model, void* workspace, void* stream);
+
 /* ---- K3-fit: LSTM training (back-propagation through time) ---------------------------------
  * Replaces KerasLSTMBaseEstimator.fit (models.py:557-616): if `primer`, one Adam step on the single
  * window 0 (the reference's `super().fit` on a batch of one, :585-597); then `epochs` passes over the

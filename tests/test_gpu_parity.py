@@ -340,6 +340,38 @@ def test_lstm_infer_matches_oracle(engine, torch, F, units, lookback):
         close(out[m * nwin:(m + 1) * nwin], want, 1.0, name="lstm output")
 
 
+@pytest.mark.parametrize("F,units,lookback,rows,scale", [(16, [64, 64], 5, [140, 300], 1.0), (128, [256, 128, 64, 64, 128, 256], 20, [57, 190], 1.0),
+                                                          (7, [128], 9, [400], 1000.0)])
+def test_lstm_infer_tcgen05_matches_oracle(engine, torch, F, units, lookback, rows, scale):
+    """gb_lstm_infer_tc: FP16-pair split operands on the tensor cores, state in HBM, one launch per (layer, timestep).
+    Jobs of different lengths (tiles with padding rows), machines sharing the launch, raw inputs of large magnitude (the
+    input projection stays fp32), and the CUDA-core kernel as a second witness."""
+    from oracle import keras_math as km
+
+    spec = km.LSTMSpec(F, units, ["tanh"] * len(units), F, "linear", lookback)
+    M = len(rows)
+    rng = np.random.default_rng(9)
+    ws = [km.init_lstm_weights(spec, np.random.default_rng(40 + m)) for m in range(M)]
+    if scale != 1.0:  # keep the pre-activations sane for huge inputs: shrink the input kernel instead of the data
+        ws = [([(K / scale if i == 0 else K, U, b) for i, (K, U, b) in enumerate(layers)], dense) for layers, dense in ws]
+    Xs = [(rng.random((n, F)) * scale).astype(np.float32) for n in rows]
+    eng = engine.LSTMEngine(F, units, spec.acts, F, "linear", lookback)
+    assert eng.tc_supported
+    dev = eng.device
+    nwin = [n - lookback + 1 for n in rows]
+    starts = np.concatenate([[0], np.cumsum(rows)[:-1]])
+    outs = np.concatenate([[0], np.cumsum(nwin)[:-1]])
+    jobs = engine.jobs_to_device(engine.make_jobs(np.arange(M), nwin, starts, outs), dev)
+    x = torch.from_numpy(np.concatenate(Xs)).to(dev)
+    params = eng.pack_params(ws)
+    got_tc = eng.infer(params, jobs, M, max(nwin), x, sum(nwin), variant=2).cpu().numpy()
+    got_fma = eng.infer(params, jobs, M, max(nwin), x, sum(nwin), variant=1).cpu().numpy()
+    for m in range(M):
+        want = km.lstm_predict(spec, ws[m], Xs[m], dtype=np.float64)
+        close(got_tc[outs[m]:outs[m] + nwin[m]], want, 1.0, name="tcgen05 lstm output")
+        close(got_fma[outs[m]:outs[m] + nwin[m]], want, 1.0, name="fp32 lstm output")
+
+
 # ------------------------------------------------------------------------------------------------ estimator API end to end
 def test_detector_end_to_end_like_reference_tests(engine, torch):
     """tests/gordo/machine/model/anomaly/test_anomaly_detectors.py:28-120 with our KerasAutoEncoder as base estimator."""
