@@ -101,7 +101,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float sigm(float z) { return 1.f / (1.f + expf(-z)); }
+// sigmoid / tanh through ex2.approx + rcp.approx (~2e-7 absolute error, exact limits): the epilogue evaluates five of them per
+// (window, unit) and is otherwise the longest phase of a CTA
+__device__ __forceinline__ float sigm(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return r;
+}
+__device__ __forceinline__ float fast_tanh(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(2.8853900817779268f * z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+__device__ __forceinline__ float cell_act(int act, float z) { return act == GB_ACT_TANH ? fast_tanh(z) : gb::apply_act(act, z); }
 
 // ------------------------------------------------------------------------------------------------ one (layer, timestep) for all windows
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -113,7 +127,8 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
   __shared__ __align__(8) unsigned long long s_bar[2 * STAGES + 1];
   __shared__ float s_bias[NCOL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, ub = blockIdx.y;
+  // the unit blocks of one window tile are neighbours in launch order: they read the same A operand, which then comes from L2
+  const int nub = a.u / UB, tile = blockIdx.x / nub, ub = blockIdx.x - tile * nub;
   const int job_id = tile / a.tiles_per_job, tj = tile - job_id * a.tiles_per_job;
   const gb_job job = a.jobs[job_id];
   if (tj * TILE >= job.n_rows) return;  // uniform: nothing of this tile is a real window
@@ -183,8 +198,9 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     }
   } else {
     // ============================== epilogue: gates, cell, h (one thread = one window)
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
+    // Everything that does not depend on the accumulator is requested while the MMAs run (c_{t-1} of all 64 units, the
+    // first input-projection slice), and inside the loop the next slice's TMEM / global loads are in flight while the
+    // current one is evaluated: per-thread row accesses have no coalescing to hide their latency behind.
     const int r = tid;  // 0..127
     const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
     const long row = (long)row0 + r;
@@ -197,38 +213,53 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     float* crow = a.c + row * u + ub * UB;
     __half* hh = a.h_out_hi + row * u + ub * UB;
     __half* hl = a.h_out_lo + row * u + ub * UB;
-#pragma unroll 1
-    for (int j0 = 0; j0 < UB; j0 += 8) {
-      float z[4][8];
+    float4 cp[UB / 4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0, z[g]);
-      tmem_wait_ld();
-      float add[4][8];
+    for (int i = 0; i < UB / 4; ++i) cp[i] = a.t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(crow + 4 * i);
+    float4 ad[2][8];  // [buffer][gate * 2 + half]: the additive term of 8 units x 4 gates
+    auto load_add = [&](int buf, int j0) {
       if (a.is_first) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float4 p = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0)), q = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0 + 4));
-          add[g][0] = p.x; add[g][1] = p.y; add[g][2] = p.z; add[g][3] = p.w; add[g][4] = q.x; add[g][5] = q.y; add[g][6] = q.z; add[g][7] = q.w;
+          ad[buf][2 * g] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0));
+          ad[buf][2 * g + 1] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0 + 4));
         }
       } else {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+        for (int g = 0; g < 4; ++g) {
+          ad[buf][2 * g] = *reinterpret_cast<const float4*>(s_bias + g * UB + j0);
+          ad[buf][2 * g + 1] = *reinterpret_cast<const float4*>(s_bias + g * UB + j0 + 4);
+        }
+      }
+    };
+    load_add(0, 0);
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    float z[2][4][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) add[g][i] = s_bias[g * UB + j0 + i];
+    for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB, z[0][g]);
+#pragma unroll
+    for (int it = 0; it < UB / 8; ++it) {
+      const int j0 = it * 8, cur = it & 1;
+      tmem_wait_ld();
+      if (it + 1 < UB / 8) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0 + 8, z[cur ^ 1][g]);
+        load_add(cur ^ 1, j0 + 8);
       }
-      float cprev[8];
-      {
-        const float4 p = *reinterpret_cast<const float4*>(crow + j0), q = *reinterpret_cast<const float4*>(crow + j0 + 4);
-        cprev[0] = p.x; cprev[1] = p.y; cprev[2] = p.z; cprev[3] = p.w; cprev[4] = q.x; cprev[5] = q.y; cprev[6] = q.z; cprev[7] = q.w;
-      }
+      const float cprev[8] = {cp[2 * it].x, cp[2 * it].y, cp[2 * it].z, cp[2 * it].w, cp[2 * it + 1].x, cp[2 * it + 1].y, cp[2 * it + 1].z, cp[2 * it + 1].w};
       float cn[8];
       __align__(16) __half h1[8], h2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float ig = sigm(z[0][i] + add[0][i]), fg = sigm(z[1][i] + add[1][i]);
-        const float gg = gb::apply_act(a.act, z[2][i] + add[2][i]), og = sigm(z[3][i] + add[3][i]);
-        cn[i] = fmaf(fg, a.t == 0 ? 0.f : cprev[i], ig * gg);
-        const float h = og * gb::apply_act(a.act, cn[i]);
+        const float4 a0 = ad[cur][0 + (i >> 2)], a1 = ad[cur][2 + (i >> 2)], a2 = ad[cur][4 + (i >> 2)], a3 = ad[cur][6 + (i >> 2)];
+        const int e = i & 3;
+        const float b0 = e == 0 ? a0.x : e == 1 ? a0.y : e == 2 ? a0.z : a0.w, b1 = e == 0 ? a1.x : e == 1 ? a1.y : e == 2 ? a1.z : a1.w;
+        const float b2 = e == 0 ? a2.x : e == 1 ? a2.y : e == 2 ? a2.z : a2.w, b3 = e == 0 ? a3.x : e == 1 ? a3.y : e == 2 ? a3.z : a3.w;
+        const float ig = sigm(z[cur][0][i] + b0), fg = sigm(z[cur][1][i] + b1);
+        const float gg = cell_act(a.act, z[cur][2][i] + b2), og = sigm(z[cur][3][i] + b3);
+        cn[i] = fmaf(fg, cprev[i], ig * gg);
+        const float h = og * cell_act(a.act, cn[i]);
         h1[i] = __float2half_rn(h);
         h2[i] = __float2half_rn(h - __half2float(h1[i]));
       }
@@ -473,7 +504,7 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
       a.h_out_hi = reinterpret_cast<__half*>(ws + p.h_hi[l][wr]);
       a.h_out_lo = reinterpret_cast<__half*>(ws + p.h_lo[l][wr]);
       const int lb = l > 0 ? l - 1 : 0;
-      lstm_tc_step_kernel<<<dim3(n_jobs * tiles_per_job, p.u[l] / UB), NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1],
+      lstm_tc_step_kernel<<<dim3(n_jobs * tiles_per_job * (p.u[l] / UB)), NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1],
                                                                                              m_w[l][0], m_w[l][1]);
     }
   }
