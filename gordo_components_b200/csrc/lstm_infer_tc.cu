@@ -35,7 +35,7 @@ constexpr int NTHREADS = 192;        // warps 0-3: epilogue (one thread = one wi
 struct TcLayerArgs {
   int u, kc_below, kc_own;           // units; K chunks coming from the layer below / from this layer's own h
   int act, is_first;
-  int tiles_per_job, t, lookback;
+  int tiles_per_job, t, lookback, n_items;
   const gb_job* jobs;
   const float* bias;                 // [n_slots][4u] reordered (layers >= 1; layer 0's bias lives in xk)
   const float* xk;                   // layer 0: [x rows][4u] reordered input projection
@@ -118,160 +118,207 @@ __device__ __forceinline__ float fast_tanh(float z) {
 __device__ __forceinline__ float cell_act(int act, float z) { return act == GB_ACT_TANH ? fast_tanh(z) : gb::apply_act(act, z); }
 
 // ------------------------------------------------------------------------------------------------ one (layer, timestep) for all windows
+// Persistent: gridDim.x CTAs walk the work items (window tile, unit block); the accumulator is double-buffered in TMEM (2 x 256
+// columns), so the MMAs of item i+1 run while the epilogue warps finish the cell of item i; the TMA ring runs ahead across items.
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_below_hi, const __grid_constant__ CUtensorMap m_below_lo,
                     const __grid_constant__ CUtensorMap m_own_hi, const __grid_constant__ CUtensorMap m_own_lo,
                     const __grid_constant__ CUtensorMap m_w_hi, const __grid_constant__ CUtensorMap m_w_lo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) unsigned long long s_bar[2 * STAGES + 1];
-  __shared__ float s_bias[NCOL];
+  __shared__ __align__(8) unsigned long long s_bar[2 * STAGES + 4];
+  __shared__ __align__(16) float s_bias[2][NCOL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // the unit blocks of one window tile are neighbours in launch order: they read the same A operand, which then comes from L2
-  const int nub = a.u / UB, tile = blockIdx.x / nub, ub = blockIdx.x - tile * nub;
-  const int job_id = tile / a.tiles_per_job, tj = tile - job_id * a.tiles_per_job;
-  const gb_job job = a.jobs[job_id];
-  if (tj * TILE >= job.n_rows) return;  // uniform: nothing of this tile is a real window
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[STAGES]), bar_done = smem_u32(&s_bar[2 * STAGES]);
+  const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[STAGES]), bar_done = smem_u32(&s_bar[2 * STAGES]),
+                 bar_free = smem_u32(&s_bar[2 * STAGES + 2]);
   const int u = a.u;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_done, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_done + 8 * b, 1);
+      mbar_init(bar_free + 8 * b, 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(NCOL) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * NCOL) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (!a.is_first)
-    for (int i = tid; i < NCOL; i += NTHREADS) s_bias[i] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   const int n_chunks = a.kc_below + a.kc_own;
-  const int row0 = tile * TILE;                       // first row of this tile in the state arrays
-  const int wrow0 = job.slot * 4 * u + ub * NCOL;      // first row of this unit block in the weight images
+  const int nub = u / UB;
+  // work item -> (tile, ub): the unit blocks of one window tile are neighbours, so CTAs running side by side read the same A
+  // operand and it comes from L2.  Items whose tile holds no real window are skipped by every role alike.
+  auto item_info = [&](int item, int& tile, int& ub, gb_job& job, int& tj) -> bool {
+    tile = item / nub;
+    ub = item - tile * nub;
+    const int job_id = tile / a.tiles_per_job;
+    tj = tile - job_id * a.tiles_per_job;
+    job = a.jobs[job_id];
+    return tj * TILE < job.n_rows;
+  };
 
   if (warp == 4) {
     // ============================== TMA producer
     if (lane == 0) {
-      for (int c = 0; c < n_chunks; ++c) {
-        const int s = c % STAGES, it = c / STAGES;
-        if (it > 0) mbar_wait(bar_empty + 8 * s, (it - 1) & 1);
-        const uint32_t st = sbase + s * STAGE_BYTES;
-        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-        const bool below = c < a.kc_below;
-        const int acol = (below ? c : c - a.kc_below) * KC;
-        tma_load_2d(st, below ? &m_below_hi : &m_own_hi, acol, row0, bar_full + 8 * s);
-        tma_load_2d(st + A_BOX, below ? &m_below_lo : &m_own_lo, acol, row0, bar_full + 8 * s);
-        tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0, bar_full + 8 * s);
-        tma_load_2d(st + 2 * A_BOX + B_BOX, &m_w_lo, c * KC, wrow0, bar_full + 8 * s);
+      int cc = 0;  // chunks issued so far (ring position)
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int tile, ub, tj;
+        gb_job job;
+        if (!item_info(item, tile, ub, job, tj)) continue;
+        const int row0 = tile * TILE, wrow0 = job.slot * 4 * u + ub * NCOL;
+        for (int c = 0; c < n_chunks; ++c, ++cc) {
+          const int s = cc % STAGES, round = cc / STAGES;
+          if (round > 0) mbar_wait(bar_empty + 8 * s, (round - 1) & 1);
+          const uint32_t st = sbase + s * STAGE_BYTES;
+          mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          const bool below = c < a.kc_below;
+          const int acol = (below ? c : c - a.kc_below) * KC;
+          tma_load_2d(st, below ? &m_below_hi : &m_own_hi, acol, row0, bar_full + 8 * s);
+          tma_load_2d(st + A_BOX, below ? &m_below_lo : &m_own_lo, acol, row0, bar_full + 8 * s);
+          tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0, bar_full + 8 * s);
+          tma_load_2d(st + 2 * A_BOX + B_BOX, &m_w_lo, c * KC, wrow0, bar_full + 8 * s);
+        }
       }
     }
   } else if (warp == 5) {
     // ============================== MMA issuer
     const uint32_t idesc = make_idesc_f16(NCOL);
-    for (int c = 0; c < n_chunks; ++c) {
-      const int s = c % STAGES, it = c / STAGES;
-      mbar_wait(bar_full + 8 * s, it & 1);
+    int cc = 0, n = 0;  // chunks consumed, items started
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      int tile, ub, tj;
+      gb_job job;
+      if (!item_info(item, tile, ub, job, tj)) continue;
+      const int buf = n & 1;
+      if (n >= 2) mbar_wait(bar_free + 8 * buf, ((n >> 1) - 1) & 1);  // the epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = sbase + s * STAGE_BYTES;
-        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_BOX);
-        const uint64_t b_hi = make_desc_sw128(st + 2 * A_BOX), b_lo = make_desc_sw128(st + 2 * A_BOX + B_BOX);
+      const uint32_t dcol = tmem + buf * NCOL;
+      for (int c = 0; c < n_chunks; ++c, ++cc) {
+        const int s = cc % STAGES, round = cc / STAGES;
+        mbar_wait(bar_full + 8 * s, round & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = sbase + s * STAGE_BYTES;
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_BOX);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * A_BOX), b_lo = make_desc_sw128(st + 2 * A_BOX + B_BOX);
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K step, in 16-byte units of the address field
-          mma_f16_ss(tmem, a_lo + adv, b_hi + adv, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-          mma_f16_ss(tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-          mma_f16_ss(tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K step, in 16-byte units of the address field
+            mma_f16_ss(dcol, a_lo + adv, b_hi + adv, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            mma_f16_ss(dcol, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_f16_ss(dcol, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          mma_commit(bar_empty + 8 * s);
+          if (c + 1 == n_chunks) mma_commit(bar_done + 8 * buf);
         }
-        mma_commit(bar_empty + 8 * s);
-        if (c + 1 == n_chunks) mma_commit(bar_done);
+        __syncwarp();
       }
-      __syncwarp();
+      ++n;
     }
   } else {
     // ============================== epilogue: gates, cell, h (one thread = one window)
     // Everything that does not depend on the accumulator is requested while the MMAs run (c_{t-1} of all 64 units, the
     // first input-projection slice), and inside the loop the next slice's TMEM / global loads are in flight while the
     // current one is evaluated: per-thread row accesses have no coalescing to hide their latency behind.
-    const int r = tid;  // 0..127
-    const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
-    const long row = (long)row0 + r;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    const float* xk = nullptr;
-    if (a.is_first) {
-      const long xr = job.x_row + min(w, job.n_rows - 1) + a.t;
-      xk = a.xk + min(xr, a.xk_rows - 1) * (long)(4 * u) + ub * NCOL;
-    }
-    float* crow = a.c + row * u + ub * UB;
-    __half* hh = a.h_out_hi + row * u + ub * UB;
-    __half* hl = a.h_out_lo + row * u + ub * UB;
-    float4 cp[UB / 4];
-#pragma unroll
-    for (int i = 0; i < UB / 4; ++i) cp[i] = a.t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(crow + 4 * i);
-    float4 ad[2][8];  // [buffer][gate * 2 + half]: the additive term of 8 units x 4 gates
-    auto load_add = [&](int buf, int j0) {
+    int n = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      int tile, ub, tj;
+      gb_job job;
+      if (!item_info(item, tile, ub, job, tj)) continue;
+      const int buf = n & 1;
+      const int r = tid;  // 0..127
+      const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
+      const long row = (long)tile * TILE + r;
+      const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)(warp * 32) << 16);
+      const float* xk = nullptr;
+      float* sb = s_bias[buf];
       if (a.is_first) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          ad[buf][2 * g] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0));
-          ad[buf][2 * g + 1] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0 + 4));
-        }
+        const long xr = job.x_row + min(w, job.n_rows - 1) + a.t;
+        xk = a.xk + min(xr, a.xk_rows - 1) * (long)(4 * u) + ub * NCOL;
       } else {
+        // this buffer's previous user (item n-2) finished reading it before the 128-thread barrier of item n-1
+        const float* bsrc = a.bias + (long)job.slot * 4 * u + ub * NCOL;
+        sb[r] = __ldg(bsrc + r);
+        sb[r + TILE] = __ldg(bsrc + r + TILE);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      float* crow = a.c + row * u + ub * UB;
+      __half* hh = a.h_out_hi + row * u + ub * UB;
+      __half* hl = a.h_out_lo + row * u + ub * UB;
+      float4 cp[UB / 4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          ad[buf][2 * g] = *reinterpret_cast<const float4*>(s_bias + g * UB + j0);
-          ad[buf][2 * g + 1] = *reinterpret_cast<const float4*>(s_bias + g * UB + j0 + 4);
+      for (int i = 0; i < UB / 4; ++i) cp[i] = a.t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(crow + 4 * i);
+      float4 ad[2][8];  // [buffer][gate * 2 + half]: the additive term of 8 units x 4 gates
+      auto load_add = [&](int b2, int j0) {
+        if (a.is_first) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            ad[b2][2 * g] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0));
+            ad[b2][2 * g + 1] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0 + 4));
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            ad[b2][2 * g] = *reinterpret_cast<const float4*>(sb + g * UB + j0);
+            ad[b2][2 * g + 1] = *reinterpret_cast<const float4*>(sb + g * UB + j0 + 4);
+          }
         }
+      };
+      load_add(0, 0);
+      mbar_wait(bar_done + 8 * buf, (n >> 1) & 1);
+      tc_fence_after();
+      float z[2][4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB, z[0][g]);
+#pragma unroll
+      for (int it = 0; it < UB / 8; ++it) {
+        const int j0 = it * 8, cur = it & 1;
+        tmem_wait_ld();
+        if (it + 1 < UB / 8) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0 + 8, z[cur ^ 1][g]);
+          load_add(cur ^ 1, j0 + 8);
+        } else {
+          tc_fence_before();  // last slice of the accumulator is in registers: hand the buffer back to the MMA warp
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * buf) : "memory");
+          }
+        }
+        const float cprev[8] = {cp[2 * it].x, cp[2 * it].y, cp[2 * it].z, cp[2 * it].w, cp[2 * it + 1].x, cp[2 * it + 1].y, cp[2 * it + 1].z, cp[2 * it + 1].w};
+        float cn[8];
+        __align__(16) __half h1[8], h2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a0 = ad[cur][0 + (i >> 2)], a1 = ad[cur][2 + (i >> 2)], a2 = ad[cur][4 + (i >> 2)], a3 = ad[cur][6 + (i >> 2)];
+          const int e = i & 3;
+          const float b0 = e == 0 ? a0.x : e == 1 ? a0.y : e == 2 ? a0.z : a0.w, b1 = e == 0 ? a1.x : e == 1 ? a1.y : e == 2 ? a1.z : a1.w;
+          const float b2 = e == 0 ? a2.x : e == 1 ? a2.y : e == 2 ? a2.z : a2.w, b3 = e == 0 ? a3.x : e == 1 ? a3.y : e == 2 ? a3.z : a3.w;
+          const float ig = sigm(z[cur][0][i] + b0), fg = sigm(z[cur][1][i] + b1);
+          const float gg = cell_act(a.act, z[cur][2][i] + b2), og = sigm(z[cur][3][i] + b3);
+          cn[i] = fmaf(fg, cprev[i], ig * gg);
+          const float h = og * cell_act(a.act, cn[i]);
+          h1[i] = __float2half_rn(h);
+          h2[i] = __float2half_rn(h - __half2float(h1[i]));
+        }
+        *reinterpret_cast<float4*>(crow + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(crow + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
+        *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
       }
-    };
-    load_add(0, 0);
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    float z[2][4][8];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB, z[0][g]);
-#pragma unroll
-    for (int it = 0; it < UB / 8; ++it) {
-      const int j0 = it * 8, cur = it & 1;
-      tmem_wait_ld();
-      if (it + 1 < UB / 8) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0 + 8, z[cur ^ 1][g]);
-        load_add(cur ^ 1, j0 + 8);
-      }
-      const float cprev[8] = {cp[2 * it].x, cp[2 * it].y, cp[2 * it].z, cp[2 * it].w, cp[2 * it + 1].x, cp[2 * it + 1].y, cp[2 * it + 1].z, cp[2 * it + 1].w};
-      float cn[8];
-      __align__(16) __half h1[8], h2[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 a0 = ad[cur][0 + (i >> 2)], a1 = ad[cur][2 + (i >> 2)], a2 = ad[cur][4 + (i >> 2)], a3 = ad[cur][6 + (i >> 2)];
-        const int e = i & 3;
-        const float b0 = e == 0 ? a0.x : e == 1 ? a0.y : e == 2 ? a0.z : a0.w, b1 = e == 0 ? a1.x : e == 1 ? a1.y : e == 2 ? a1.z : a1.w;
-        const float b2 = e == 0 ? a2.x : e == 1 ? a2.y : e == 2 ? a2.z : a2.w, b3 = e == 0 ? a3.x : e == 1 ? a3.y : e == 2 ? a3.z : a3.w;
-        const float ig = sigm(z[cur][0][i] + b0), fg = sigm(z[cur][1][i] + b1);
-        const float gg = cell_act(a.act, z[cur][2][i] + b2), og = sigm(z[cur][3][i] + b3);
-        cn[i] = fmaf(fg, cprev[i], ig * gg);
-        const float h = og * cell_act(a.act, cn[i]);
-        h1[i] = __float2half_rn(h);
-        h2[i] = __float2half_rn(h - __half2float(h1[i]));
-      }
-      *reinterpret_cast<float4*>(crow + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-      *reinterpret_cast<float4*>(crow + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-      *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
-      *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
+      ++n;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NCOL) : "memory");
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ preparation kernels (fp32 CUDA cores)
@@ -489,6 +536,9 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
     if ((rc = make_map_f16(&m_w[l][1], ws + p.w_lo[l], (long)n_slots * 4 * p.u[l], p.kp[l], NCOL)) != GB_OK) return rc;
   }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  int dev = 0, sms = 148;
+  GB_CUDA_CHECK(cudaGetDevice(&dev));
+  GB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   // ---- the recurrence: h of (layer, t) is written to buffer t & 1 and read from buffer (t - 1) & 1 (zero at t = 0)
@@ -504,8 +554,9 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
       a.h_out_hi = reinterpret_cast<__half*>(ws + p.h_hi[l][wr]);
       a.h_out_lo = reinterpret_cast<__half*>(ws + p.h_lo[l][wr]);
       const int lb = l > 0 ? l - 1 : 0;
-      lstm_tc_step_kernel<<<dim3(n_jobs * tiles_per_job * (p.u[l] / UB)), NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1],
-                                                                                             m_w[l][0], m_w[l][1]);
+      a.n_items = n_jobs * tiles_per_job * (p.u[l] / UB);
+      const int grid = a.n_items < sms ? a.n_items : sms;
+      lstm_tc_step_kernel<<<grid, NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1], m_w[l][0], m_w[l][1]);
     }
   }
   const int top = p.nl - 1, fin = (p.L - 1) & 1;
