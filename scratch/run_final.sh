@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tail -6 > gpurun_out/pytest_full8.log; tail -3 gpurun_out/pytest_full8.log
-timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench8_tc.json 2>gpurun_out/bench8_tc.err; python -c "import json; d=json.load(open('gpurun_out/bench8_tc.json')); print(d['value'], d['ms_per_step'], d['roofline'], d['e2e']['value'], d['clocks'])"; tail -2 gpurun_out/bench8_tc.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ffae_tc -s 3 -c 1 -o gpurun_out/prof_tc_v12 python bench.py --steps 2 --warmup 3 --e2e-steps 1 --machines 300 > gpurun_out/ncu_full8.log 2>&1; tail -1 gpurun_out/ncu_full8.log
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ffae|minmax|roll|anomaly" -c 60 --csv --log-file gpurun_out/launches_v12.csv python bench.py --steps 3 --warmup 3 --e2e-steps 1 > gpurun_out/ncu_launch8.log 2>&1; tail -3 gpurun_out/launches_v12.csv
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tail -6 > gpurun_out/pytest_full9.log; tail -3 gpurun_out/pytest_full9.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench9_tc.json 2>gpurun_out/bench9_tc.err; python -c "import json; d=json.load(open('gpurun_out/bench9_tc.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['clocks'])"; tail -2 gpurun_out/bench9_tc.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench9_ref.json 2>gpurun_out/bench9_ref.err; python -c "import json; d=json.load(open('gpurun_out/bench9_ref.json')); print('ref', d['value'], d['cpu_baseline']['cores'])"

@@ -672,6 +672,43 @@ def test_quantile_kernel_matches_pandas(engine, torch):
             assert np.allclose(got, want, rtol=1e-6, atol=1e-7, equal_nan=True), (n, q, got, want)
 
 
+def test_error_paths_raise_like_the_reference(engine, torch):
+    """Status codes surface as the exceptions the reference raises in the same situations (ValueError for bad shapes /
+    arguments), never as a silent fallback."""
+    from gordo_components_b200 import _cabi
+    from oracle import keras_math as km
+
+    dev = engine.cuda_device()
+    # LSTM: widths outside the tcgen05 kernel must be refused when that kernel is demanded, and served by the fp32 kernel otherwise
+    spec = km.lstm_model_spec(5, 5, lookback_window=3, encoding_dim=(7,), encoding_func=("tanh",), decoding_dim=(7,), decoding_func=("tanh",))
+    eng = engine.LSTMEngine(5, spec.units, spec.acts, 5, "linear", 3)
+    assert not eng.tc_supported
+    params = eng.pack_params([km.init_lstm_weights(spec, np.random.default_rng(0))])
+    x = torch.rand((20, 5), device=dev)
+    jobs = engine.jobs_to_device(engine.make_jobs([0], [18], [0]), dev)
+    with pytest.raises(ValueError):
+        eng.infer(params, jobs, 1, 18, x, 18, variant=2)
+    assert eng.infer(params, jobs, 1, 18, x, 18).shape == (18, 5)
+    with pytest.raises(ValueError):  # batches above 32 windows are not supported by gb_lstm_fit
+        eng.fit(params, jobs, 1, 18, x, x, epochs=1, batch_size=64)
+    # quantile: more rows than fit in shared memory
+    big = torch.zeros((40000, 1), device=dev)
+    with pytest.raises((ValueError, _cabi.GordoB200Error)):
+        engine.quantile(engine.jobs_to_device(engine.make_jobs([0], [40000], [0]), dev), 1, 40000, big, 0.5)
+    # fused kernel: the tcgen05 variant refuses architectures it does not cover
+    ff = km.ff_hourglass_spec(10)
+    e2 = engine.FFEngine(ff.dims, ff.acts, ff.l1)
+    p2 = e2.pack_params([km.init_ff_weights(ff, np.random.default_rng(0))])
+    x2 = torch.rand((64, 10), device=dev)
+    j2 = engine.jobs_to_device(engine.make_jobs([0], [64], [0]), dev)
+    with pytest.raises(ValueError):
+        e2.infer_score(p2, j2, 1, 64, x2, x2, variant=2)
+    with pytest.raises(ValueError):  # confidence requested without thresholds
+        _cabi.check(e2.lib.gb_ffae_infer_score(_cabi.C.byref(e2.net), _cabi.ptr(p2), _cabi.ptr(j2), 1, 64, 64, 64, _cabi.ptr(x2), _cabi.ptr(x2), None,
+                                               None, None, _cabi.ptr(torch.empty((64, 10), device=dev)), None, None, None, None,
+                                               _cabi.ptr(torch.empty((64, 10), device=dev)), None, 0, None))
+
+
 def test_request_coalescer_equals_per_request_launches(engine, torch):
     """serving.AnomalyCoalescer: 120 concurrent requests of 1..150 rows for random machines come back bit-identical to one
     launch per request (rows are independent in the kernel), in far fewer launches."""
