@@ -45,7 +45,8 @@ struct FitArgs {
   const float *x, *y;
   float* ws;
   float *loss_sum, *hit_sum;  // [n_jobs]
-  int win0, bsz;              // this step: first window, nominal batch size
+  const int* step;            // device: {first window, nominal batch size} of the optimizer step being replayed (the launch
+                              // sequence of one step is captured once as a CUDA graph; only these two numbers change)
   float lr, b1, b2, eps;
 };
 
@@ -56,7 +57,7 @@ __device__ __forceinline__ int job_batch(const gb_job& job, int win0, int bsz) {
 // grid (ceil(u/16), n_jobs), 256 threads: 16 units x 4 gates = 64 gate columns x up to 32 batch rows.
 __global__ void __launch_bounds__(256) lstm_fwd_kernel(const FitArgs a, int l, int t) {
   const gb_job job = a.jobs[blockIdx.y];
-  const int nb = job_batch(job, a.win0, a.bsz);
+  const int nb = job_batch(job, a.step[0], a.step[1]);
   if (nb == 0) return;
   const Lay ly = a.lay[l];
   const int u = ly.u, in = ly.in, KK = in + u, u4 = 4 * u;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const FitArgs a, int l, i
       const int b = i >> 5, k = k0 + (i & 31);
       float v = 0.f;
       if (b < nb && k < KK) {
-        if (k < in) v = l == 0 ? __ldg(a.x + (job.x_row + a.win0 + b + t) * (long)a.F + k) : below[b * in + k];
+        if (k < in) v = l == 0 ? __ldg(a.x + (job.x_row + a.step[0] + b + t) * (long)a.F + k) : below[b * in + k];
         else v = t > 0 ? hprev[b * u + (k - in)] : 0.f;
       }
       sA[b][i & 31] = v;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const FitArgs a, int l, i
 // grid n_jobs, 256 threads.  Dynamic smem: h [B][u], dout [B][T_out], yhat [B][T_out].
 __global__ void __launch_bounds__(256) lstm_head_kernel(const FitArgs a) {
   const gb_job job = a.jobs[blockIdx.x];
-  const int nb = job_batch(job, a.win0, a.bsz);
+  const int nb = job_batch(job, a.step[0], a.step[1]);
   if (nb == 0) return;
   extern __shared__ float sm[];
   const Lay top = a.lay[a.n_layers - 1];
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256) lstm_head_kernel(const FitArgs a) {
     float z = __ldg(P + (long)u * T + o);
     for (int k = 0; k < u; ++k) z = fmaf(sh[b * u + k], __ldg(P + (long)k * T + o), z);
     const float yh = gb::apply_act(a.out_act, z);
-    const float tgt = __ldg(a.y + (job.x_row + a.win0 + b + a.L - 1 + a.lookahead) * (long)T + o);
+    const float tgt = __ldg(a.y + (job.x_row + a.step[0] + b + a.L - 1 + a.lookahead) * (long)T + o);
     const float d = yh - tgt;
     lsum += d * d;
     sy[i] = yh;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) lstm_head_kernel(const FitArgs a) {
   if (tid == 0) a.loss_sum[blockIdx.x] += red[0] / (float)(nb * T) * (float)nb;
   // accuracy (metrics=["accuracy"] on 2-D float targets: argmax match; width 1: thresholded match)
   if (tid < nb) {
-    const float* tg = a.y + (job.x_row + a.win0 + tid + a.L - 1 + a.lookahead) * (long)T;
+    const float* tg = a.y + (job.x_row + a.step[0] + tid + a.L - 1 + a.lookahead) * (long)T;
     float hit;
     if (T == 1) {
       hit = ((sy[tid] > 0.5f ? 1.f : 0.f) == __ldg(tg)) ? 1.f : 0.f;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) lstm_head_kernel(const FitArgs a) {
 // grid (ceil(MAXB*u/256), n_jobs).  Overwrites the saved gates of (l, t) with dz, updates dc_next.
 __global__ void __launch_bounds__(256) lstm_bwd_gates_kernel(const FitArgs a, int l, int t) {
   const gb_job job = a.jobs[blockIdx.y];
-  const int nb = job_batch(job, a.win0, a.bsz);
+  const int nb = job_batch(job, a.step[0], a.step[1]);
   if (nb == 0) return;
   const Lay ly = a.lay[l];
   const int u = ly.u, u4 = 4 * u;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_gates_kernel(const FitArgs a, in
 // grid (ceil(cols/64), n_jobs) over the columns that are needed (layer 0 has no dx), 256 threads.
 __global__ void __launch_bounds__(256) lstm_bwd_input_kernel(const FitArgs a, int l, int t) {
   const gb_job job = a.jobs[blockIdx.y];
-  const int nb = job_batch(job, a.win0, a.bsz);
+  const int nb = job_batch(job, a.step[0], a.step[1]);
   if (nb == 0) return;
   const Lay ly = a.lay[l];
   const int u = ly.u, in = ly.in, KK = in + u, u4 = 4 * u;
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_input_kernel(const FitArgs a, in
 // grid (ceil(4u/64), ceil((in+u)/32), n_jobs), 256 threads: tile of 32 rows k x 64 columns c, reduction over (t, b).
 __global__ void __launch_bounds__(256) lstm_wgrad_kernel(const FitArgs a, int l) {
   const gb_job job = a.jobs[blockIdx.z];
-  const int nb = job_batch(job, a.win0, a.bsz);
+  const int nb = job_batch(job, a.step[0], a.step[1]);
   if (nb == 0) return;
   const Lay ly = a.lay[l];
   const int u = ly.u, in = ly.in, KK = in + u, u4 = 4 * u;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(256) lstm_wgrad_kernel(const FitArgs a, int l)
       const int b = i >> 5, k = k0 + (i & 31);
       float v = 0.f;
       if (b < nb && k < KK) {
-        if (k < in) v = l == 0 ? __ldg(a.x + (job.x_row + a.win0 + b + t) * (long)a.F + k) : below[b * in + k];
+        if (k < in) v = l == 0 ? __ldg(a.x + (job.x_row + a.step[0] + b + t) * (long)a.F + k) : below[b * in + k];
         else v = t > 0 ? hprev[b * u + (k - in)] : 0.f;
       }
       sA[b][i & 31] = v;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256) lstm_wgrad_kernel(const FitArgs a, int l)
 // ---------------------------------------------------------------------------------------------- Adam
 __global__ void __launch_bounds__(256) lstm_adam_kernel(const FitArgs a, long n_params) {
   const gb_job job = a.jobs[blockIdx.y];
-  if (job_batch(job, a.win0, a.bsz) == 0) return;
+  if (job_batch(job, a.step[0], a.step[1]) == 0) return;
   const int t = a.adam_t[job.slot] + 1;
   const float alpha = (float)((double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
   const float* G = a.ws + (long)blockIdx.y * a.ws_stride + a.gofs;
@@ -356,7 +357,11 @@ __global__ void __launch_bounds__(256) lstm_adam_kernel(const FitArgs a, long n_
 }
 __global__ void lstm_bump_kernel(const FitArgs a, int n_jobs) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n_jobs && job_batch(a.jobs[j], a.win0, a.bsz) > 0) a.adam_t[a.jobs[j].slot] += 1;
+  if (j < n_jobs && job_batch(a.jobs[j], a.step[0], a.step[1]) > 0) a.adam_t[a.jobs[j].slot] += 1;
+}
+__global__ void lstm_set_step_kernel(int* step, int win0, int bsz) {
+  step[0] = win0;
+  step[1] = bsz;
 }
 // epoch bookkeeping: history[job][epoch] = sums / n_windows; sums reset
 __global__ void lstm_epoch_kernel(const gb_job* jobs, int n_jobs, float* loss_sum, float* hit_sum, float* out_loss, float* out_acc, int epoch, int epochs) {
@@ -415,7 +420,7 @@ extern "C" {
 size_t gb_lstm_fit_workspace_bytes(const gb_lstmnet* net, int32_t n_jobs) {
   if (validate(net) != GB_OK || n_jobs < 0) return 0;
   FitArgs a{};
-  return (size_t)(layout(net, &a) * (long)n_jobs + 2L * n_jobs) * sizeof(float);
+  return (size_t)(layout(net, &a) * (long)n_jobs + 2L * n_jobs + 4) * sizeof(float);
 }
 
 int gb_lstm_fit(const gb_lstmnet* net, float* params, float* adam_m, float* adam_v, int32_t* adam_t, const gb_job* jobs, int32_t n_jobs,
@@ -447,8 +452,24 @@ int gb_lstm_fit(const gb_lstmnet* net, float* params, float* adam_m, float* adam
   GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
   const int jb = (n_jobs + 127) / 128;
 
-  auto step = [&](int win0, int bsz) -> int {
-    a.win0 = win0; a.bsz = bsz;
+  int* d_step = reinterpret_cast<int*>(a.hit_sum + n_jobs);
+  a.step = d_step;
+  // One optimizer step is ~2 600 small launches (18 per timestep): captured once as a CUDA graph and replayed per step, the
+  // step's (first window, batch size) being read from device memory -- launch overhead was >90 % of a step for few machines.
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t cap = nullptr;  // the caller's stream may be the legacy default stream, which cannot capture
+  GB_CUDA_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  {
+    const cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) {
+      cudaStreamDestroy(cap);
+      gb::set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce));
+      return GB_E_CUDA;
+    }
+  }
+  {
+    cudaStream_t st = cap;  // everything in this block is recorded, not run
     for (int t = 0; t < a.L; ++t)
       for (int l = 0; l < a.n_layers; ++l) lstm_fwd_kernel<<<dim3((a.lay[l].u + 15) / 16, n_jobs), 256, 0, st>>>(a, l, t);
     lstm_head_kernel<<<n_jobs, 256, head_smem, st>>>(a);
@@ -465,7 +486,30 @@ int gb_lstm_fit(const gb_lstmnet* net, float* params, float* adam_m, float* adam
     }
     lstm_adam_kernel<<<dim3((unsigned)((n_params + 256 * 8 - 1) / (256 * 8)), n_jobs), 256, 0, st>>>(a, n_params);
     lstm_bump_kernel<<<jb, 128, 0, st>>>(a, n_jobs);
-    GB_CUDA_CHECK(cudaGetLastError());
+  }
+  {
+    const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+    cudaStreamDestroy(cap);
+    if (ce != cudaSuccess || graph == nullptr) {
+      gb::set_error("capturing the LSTM optimizer step failed: %s", cudaGetErrorString(ce));
+      return GB_E_CUDA;
+    }
+  }
+  {
+    const cudaError_t ce = cudaGraphInstantiate(&gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      gb::set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      return GB_E_CUDA;
+    }
+  }
+  auto step = [&](int win0, int bsz) -> int {
+    lstm_set_step_kernel<<<1, 1, 0, st>>>(d_step, win0, bsz);
+    const cudaError_t ce = cudaGraphLaunch(gexec, st);
+    if (ce != cudaSuccess) {
+      gb::set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(ce));
+      return GB_E_CUDA;
+    }
     return GB_OK;
   };
 
@@ -479,6 +523,7 @@ int gb_lstm_fit(const gb_lstmnet* net, float* params, float* adam_m, float* adam
       if ((rc = step(w, hp->batch_size)) != GB_OK) return rc;
     lstm_epoch_kernel<<<jb, 128, 0, st>>>(jobs, n_jobs, a.loss_sum, a.hit_sum, out_loss, out_acc, e, hp->epochs);
   }
+  cudaGraphExecDestroy(gexec);  // the enqueued replays keep what they need
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }
