@@ -30,7 +30,8 @@ constexpr int STAGES = 2;
 constexpr int A_BOX = TILE * 128;    // bytes: 128 rows x 64 FP16
 constexpr int B_BOX = NCOL * 128;    // bytes: 256 rows x 64 FP16
 constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_BOX;
-constexpr int NTHREADS = 192;        // warps 0-3: epilogue (one thread = one window), warp 4: TMA producer, warp 5: MMA issuer
+constexpr int EPI_WARPS = 8;         // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which 32 of the 64 units
+constexpr int NTHREADS = (EPI_WARPS + 2) * 32;  // + warp 8: TMA producer, warp 9: MMA issuer
 
 struct TcLayerArgs {
   int u, kc_below, kc_own;           // units; K chunks coming from the layer below / from this layer's own h
@@ -140,11 +141,11 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_done + 8 * b, 1);
-      mbar_init(bar_free + 8 * b, 4);  // one arrival per epilogue warp
+      mbar_init(bar_free + 8 * b, EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * NCOL) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -165,7 +166,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     return tj * TILE < job.n_rows;
   };
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // ============================== TMA producer
     if (lane == 0) {
       int cc = 0;  // chunks issued so far (ring position)
@@ -188,7 +189,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     // ============================== MMA issuer
     const uint32_t idesc = make_idesc_f16(NCOL);
     int cc = 0, n = 0;  // chunks consumed, items started
@@ -233,28 +234,30 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       gb_job job;
       if (!item_info(item, tile, ub, job, tj)) continue;
       const int buf = n & 1;
-      const int r = tid;  // 0..127
+      const int r = tid & (TILE - 1), uh = warp >> 2;      // window row 0..127; this warp's half of the 64 units
       const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
       const long row = (long)tile * TILE + r;
-      const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)(warp * 32) << 16);
+      const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + uh * (UB / 2);
       const float* xk = nullptr;
       float* sb = s_bias[buf];
       if (a.is_first) {
         const long xr = job.x_row + min(w, job.n_rows - 1) + a.t;
         xk = a.xk + min(xr, a.xk_rows - 1) * (long)(4 * u) + ub * NCOL;
       } else {
-        // this buffer's previous user (item n-2) finished reading it before the 128-thread barrier of item n-1
+        // this buffer's previous user (item n-2) finished reading it before the epilogue-wide barrier of item n-1
         const float* bsrc = a.bias + (long)job.slot * 4 * u + ub * NCOL;
-        sb[r] = __ldg(bsrc + r);
-        sb[r + TILE] = __ldg(bsrc + r + TILE);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        sb[tid] = __ldg(bsrc + tid);  // 256 epilogue threads, 256 gate columns
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      float* crow = a.c + row * u + ub * UB;
-      __half* hh = a.h_out_hi + row * u + ub * UB;
-      __half* hl = a.h_out_lo + row * u + ub * UB;
-      float4 cp[UB / 4];
+      constexpr int UH = UB / 2;  // units per epilogue thread
+      float* crow = a.c + row * u + ub * UB + uh * UH;
+      __half* hh = a.h_out_hi + row * u + ub * UB + uh * UH;
+      __half* hl = a.h_out_lo + row * u + ub * UB + uh * UH;
+      if (xk) xk += uh * UH;
+      sb += uh * UH;
+      float4 cp[UH / 4];
 #pragma unroll
-      for (int i = 0; i < UB / 4; ++i) cp[i] = a.t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(crow + 4 * i);
+      for (int i = 0; i < UH / 4; ++i) cp[i] = a.t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(crow + 4 * i);
       float4 ad[2][8];  // [buffer][gate * 2 + half]: the additive term of 8 units x 4 gates
       auto load_add = [&](int b2, int j0) {
         if (a.is_first) {
@@ -278,10 +281,10 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB, z[0][g]);
 #pragma unroll
-      for (int it = 0; it < UB / 8; ++it) {
+      for (int it = 0; it < UH / 8; ++it) {
         const int j0 = it * 8, cur = it & 1;
         tmem_wait_ld();
-        if (it + 1 < UB / 8) {
+        if (it + 1 < UH / 8) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0 + 8, z[cur ^ 1][g]);
           load_add(cur ^ 1, j0 + 8);
@@ -318,7 +321,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
+  if (warp == EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ preparation kernels (fp32 CUDA cores)
