@@ -250,14 +250,16 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       constexpr int UH = UB / 2;  // units per epilogue thread
-      float* crow = a.c + row * u + ub * UB + uh * UH;
+      // c is stored tile-blocked, [tile][unit][128 windows]: consecutive threads (windows) touch consecutive floats and an item's
+      // slice is one contiguous 32 KB block (a row-major layout costs a 32-byte sector per thread and access)
+      float* ccol = a.c + ((long)tile * u + ub * UB + uh * UH) * TILE + r;  // unit j of this window: ccol[j * TILE]
       __half* hh = a.h_out_hi + row * u + ub * UB + uh * UH;
       __half* hl = a.h_out_lo + row * u + ub * UB + uh * UH;
       if (xk) xk += uh * UH;
       sb += uh * UH;
-      float4 cp[UH / 4];
+      float cp[UH];
 #pragma unroll
-      for (int i = 0; i < UH / 4; ++i) cp[i] = a.t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(crow + 4 * i);
+      for (int i = 0; i < UH; ++i) cp[i] = a.t == 0 ? 0.f : ccol[i * TILE];
       float4 ad[2][8];  // [buffer][gate * 2 + half]: the additive term of 8 units x 4 gates
       auto load_add = [&](int b2, int j0) {
         if (a.is_first) {
@@ -295,7 +297,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * buf) : "memory");
           }
         }
-        const float cprev[8] = {cp[2 * it].x, cp[2 * it].y, cp[2 * it].z, cp[2 * it].w, cp[2 * it + 1].x, cp[2 * it + 1].y, cp[2 * it + 1].z, cp[2 * it + 1].w};
+        const float* cprev = cp + j0;
         float cn[8];
         __align__(16) __half h1[8], h2[8];
 #pragma unroll
@@ -311,8 +313,8 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
           h1[i] = __float2half_rn(h);
           h2[i] = __float2half_rn(h - __half2float(h1[i]));
         }
-        *reinterpret_cast<float4*>(crow + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(crow + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ccol[(j0 + i) * TILE] = cn[i];
         *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
         *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
       }
