@@ -39,7 +39,7 @@ struct TcLayerArgs {
   int tiles_per_job, t, lookback, n_items;
   const gb_job* jobs;
   const float* bias;                 // [n_slots][4u] reordered (layers >= 1; layer 0's bias lives in xk)
-  const float* xk;                   // layer 0: [x rows][4u] reordered input projection
+  const float* xk;                   // layer 0: input projection, row-blocked [x row / 128][4u reordered][128]
   long xk_rows;
   float* c;                          // [rows][u]
   __half *h_out_hi, *h_out_lo;       // [rows][u]
@@ -240,9 +240,9 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + uh * (UB / 2);
       const float* xk = nullptr;
       float* sb = s_bias[buf];
-      if (a.is_first) {
-        const long xr = job.x_row + min(w, job.n_rows - 1) + a.t;
-        xk = a.xk + min(xr, a.xk_rows - 1) * (long)(4 * u) + ub * NCOL;
+      if (a.is_first) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
+        const long xr = min(job.x_row + min(w, job.n_rows - 1) + a.t, a.xk_rows - 1);
+        xk = a.xk + ((xr >> 7) * (long)(4 * u) + ub * NCOL) * TILE + (xr & (TILE - 1));
       } else {
         // this buffer's previous user (item n-2) finished reading it before the epilogue-wide barrier of item n-1
         const float* bsrc = a.bias + (long)job.slot * 4 * u + ub * NCOL;
@@ -255,7 +255,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       float* ccol = a.c + ((long)tile * u + ub * UB + uh * UH) * TILE + r;  // unit j of this window: ccol[j * TILE]
       __half* hh = a.h_out_hi + row * u + ub * UB + uh * UH;
       __half* hl = a.h_out_lo + row * u + ub * UB + uh * UH;
-      if (xk) xk += uh * UH;
+      if (xk) xk += uh * UH * TILE;
       sb += uh * UH;
       float cp[UH];
 #pragma unroll
@@ -265,8 +265,9 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         if (a.is_first) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            ad[b2][2 * g] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0));
-            ad[b2][2 * g + 1] = __ldg(reinterpret_cast<const float4*>(xk + g * UB + j0 + 4));
+            const float* q = xk + (g * UB + j0) * TILE;
+            ad[b2][2 * g] = make_float4(__ldg(q), __ldg(q + TILE), __ldg(q + 2 * TILE), __ldg(q + 3 * TILE));
+            ad[b2][2 * g + 1] = make_float4(__ldg(q + 4 * TILE), __ldg(q + 5 * TILE), __ldg(q + 6 * TILE), __ldg(q + 7 * TILE));
           }
         } else {
 #pragma unroll
@@ -391,10 +392,16 @@ __global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restric
     __syncthreads();
   }
   const float b = __ldg(P + (long)(F + u) * u4 + kc);
+  // out: row-blocked [row / 128][4u][128]; staged through shared memory so that lanes run along rows (128-byte segments)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + rg + 4 * i;
-    if (r < n_x) xk[(job.x_row + r) * (long)u4 + c0 + col] = acc[i] + b;
+  for (int i = 0; i < 8; ++i) sW[rg + 4 * i][col] = acc[i] + b;  // sW reused as [32 rows][64 columns]
+  __syncthreads();
+  for (int i = tid; i < 64 * 32; i += 256) {
+    const int c = i >> 5, rr = i & 31, r = r0 + rr;
+    if (r < n_x) {
+      const long xr = job.x_row + r;
+      xk[((xr >> 7) * (long)u4 + c0 + c) * TILE + (xr & (TILE - 1))] = sW[rr][c];
+    }
   }
 }
 
@@ -468,7 +475,7 @@ void make_plan(const gb_lstmnet* net, int n_slots, long rows_pad, long x_rows, P
     in = u;
   }
   p->dofs = pofs;
-  p->xk = ofs; ofs = align256(ofs + (size_t)x_rows * 4 * net->units[0] * sizeof(float));
+  p->xk = ofs; ofs = align256(ofs + (size_t)((x_rows + TILE - 1) / TILE * TILE) * 4 * net->units[0] * sizeof(float));
   p->state_begin = ofs;
   for (int l = 0; l < p->nl; ++l) {
     const size_t hb = (size_t)rows_pad * p->u[l] * sizeof(__half);
