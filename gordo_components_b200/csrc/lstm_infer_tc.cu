@@ -30,7 +30,9 @@ constexpr int STAGES = 2;
 constexpr int A_BOX = TILE * 128;    // bytes: 128 rows x 64 FP16
 constexpr int B_BOX = NCOL * 128;    // bytes: 256 rows x 64 FP16
 constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_BOX;
-constexpr int EPI_WARPS = 8;         // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which 32 of the 64 units
+constexpr int EPI_WARPS = 16;        // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which UH of the 64 units
+constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread
+constexpr int SL = 4;                // units per software-pipeline slice (registers: 576 threads leave 112 each)
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;  // + warp 8: TMA producer, warp 9: MMA issuer
 
 struct TcLayerArgs {
@@ -100,6 +102,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+  if (N == 8) tmem_ld8(taddr, v); else tmem_ld4(taddr, v);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // sigmoid / tanh through ex2.approx + rcp.approx (~2e-7 absolute error, exact limits): the epilogue evaluates five of them per
@@ -234,63 +243,50 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       gb_job job;
       if (!item_info(item, tile, ub, job, tj)) continue;
       const int buf = n & 1;
-      const int r = tid & (TILE - 1), uh = warp >> 2;      // window row 0..127; this warp's half of the 64 units
+      const int r = tid & (TILE - 1), uh = warp >> 2;      // window row 0..127; which UH of the 64 units this warp evaluates
       const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
       const long row = (long)tile * TILE + r;
-      const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + uh * (UB / 2);
+      const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + uh * UH;
       const float* xk = nullptr;
       float* sb = s_bias[buf];
       if (a.is_first) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
         const long xr = min(job.x_row + min(w, job.n_rows - 1) + a.t, a.xk_rows - 1);
-        xk = a.xk + ((xr >> 7) * (long)(4 * u) + ub * NCOL) * TILE + (xr & (TILE - 1));
+        xk = a.xk + ((xr >> 7) * (long)(4 * u) + ub * NCOL + uh * UH) * TILE + (xr & (TILE - 1));
       } else {
         // this buffer's previous user (item n-2) finished reading it before the epilogue-wide barrier of item n-1
-        const float* bsrc = a.bias + (long)job.slot * 4 * u + ub * NCOL;
-        sb[tid] = __ldg(bsrc + tid);  // 256 epilogue threads, 256 gate columns
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < NCOL) sb[tid] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + tid);
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
-      constexpr int UH = UB / 2;  // units per epilogue thread
       // c is stored tile-blocked, [tile][unit][128 windows]: consecutive threads (windows) touch consecutive floats and an item's
       // slice is one contiguous 32 KB block (a row-major layout costs a 32-byte sector per thread and access)
       float* ccol = a.c + ((long)tile * u + ub * UB + uh * UH) * TILE + r;  // unit j of this window: ccol[j * TILE]
       __half* hh = a.h_out_hi + row * u + ub * UB + uh * UH;
       __half* hl = a.h_out_lo + row * u + ub * UB + uh * UH;
-      if (xk) xk += uh * UH * TILE;
       sb += uh * UH;
       float cp[UH];
 #pragma unroll
       for (int i = 0; i < UH; ++i) cp[i] = a.t == 0 ? 0.f : ccol[i * TILE];
-      float4 ad[2][8];  // [buffer][gate * 2 + half]: the additive term of 8 units x 4 gates
+      float ad[2][4][SL];  // [buffer][gate][unit]: the additive term (bias, or layer 0's input projection incl. bias)
       auto load_add = [&](int b2, int j0) {
-        if (a.is_first) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float* q = xk + (g * UB + j0) * TILE;
-            ad[b2][2 * g] = make_float4(__ldg(q), __ldg(q + TILE), __ldg(q + 2 * TILE), __ldg(q + 3 * TILE));
-            ad[b2][2 * g + 1] = make_float4(__ldg(q + 4 * TILE), __ldg(q + 5 * TILE), __ldg(q + 6 * TILE), __ldg(q + 7 * TILE));
-          }
-        } else {
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            ad[b2][2 * g] = *reinterpret_cast<const float4*>(sb + g * UB + j0);
-            ad[b2][2 * g + 1] = *reinterpret_cast<const float4*>(sb + g * UB + j0 + 4);
-          }
-        }
+          for (int i = 0; i < SL; ++i) ad[b2][g][i] = a.is_first ? __ldg(xk + (g * UB + j0 + i) * TILE) : sb[g * UB + j0 + i];
       };
       load_add(0, 0);
       mbar_wait(bar_done + 8 * buf, (n >> 1) & 1);
       tc_fence_after();
-      float z[2][4][8];
+      float z[2][4][SL];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB, z[0][g]);
+      for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB, z[0][g]);
 #pragma unroll
-      for (int it = 0; it < UH / 8; ++it) {
-        const int j0 = it * 8, cur = it & 1;
+      for (int it = 0; it < UH / SL; ++it) {
+        const int j0 = it * SL, cur = it & 1;
         tmem_wait_ld();
-        if (it + 1 < UH / 8) {
+        if (it + 1 < UH / SL) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(lane_base + g * UB + j0 + 8, z[cur ^ 1][g]);
-          load_add(cur ^ 1, j0 + 8);
+          for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB + j0 + SL, z[cur ^ 1][g]);
+          load_add(cur ^ 1, j0 + SL);
         } else {
           tc_fence_before();  // last slice of the accumulator is in registers: hand the buffer back to the MMA warp
           __syncwarp();
@@ -298,26 +294,26 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * buf) : "memory");
           }
         }
-        const float* cprev = cp + j0;
-        float cn[8];
-        __align__(16) __half h1[8], h2[8];
+        float cn[SL];
+        __align__(8) __half h1[SL], h2[SL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 a0 = ad[cur][0 + (i >> 2)], a1 = ad[cur][2 + (i >> 2)], a2 = ad[cur][4 + (i >> 2)], a3 = ad[cur][6 + (i >> 2)];
-          const int e = i & 3;
-          const float b0 = e == 0 ? a0.x : e == 1 ? a0.y : e == 2 ? a0.z : a0.w, b1 = e == 0 ? a1.x : e == 1 ? a1.y : e == 2 ? a1.z : a1.w;
-          const float b2 = e == 0 ? a2.x : e == 1 ? a2.y : e == 2 ? a2.z : a2.w, b3 = e == 0 ? a3.x : e == 1 ? a3.y : e == 2 ? a3.z : a3.w;
-          const float ig = sigm(z[cur][0][i] + b0), fg = sigm(z[cur][1][i] + b1);
-          const float gg = cell_act(a.act, z[cur][2][i] + b2), og = sigm(z[cur][3][i] + b3);
-          cn[i] = fmaf(fg, cprev[i], ig * gg);
+        for (int i = 0; i < SL; ++i) {
+          const float ig = sigm(z[cur][0][i] + ad[cur][0][i]), fg = sigm(z[cur][1][i] + ad[cur][1][i]);
+          const float gg = cell_act(a.act, z[cur][2][i] + ad[cur][2][i]), og = sigm(z[cur][3][i] + ad[cur][3][i]);
+          cn[i] = fmaf(fg, cp[j0 + i], ig * gg);
           const float h = og * cell_act(a.act, cn[i]);
           h1[i] = __float2half_rn(h);
           h2[i] = __float2half_rn(h - __half2float(h1[i]));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ccol[(j0 + i) * TILE] = cn[i];
-        *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
-        *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
+        for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
+        if (SL == 8) {
+          *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
+          *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
+        } else {
+          *reinterpret_cast<uint2*>(hh + j0) = *reinterpret_cast<const uint2*>(h1);
+          *reinterpret_cast<uint2*>(hl + j0) = *reinterpret_cast<const uint2*>(h2);
+        }
       }
       ++n;
     }
