@@ -277,6 +277,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       mbar_wait(bar_done + 8 * buf, (n >> 1) & 1);
       tc_fence_after();
       float z[2][4][SL];
+      uint32_t hp1[UH / 2], hp2[UH / 2];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB, z[0][g]);
 #pragma unroll
@@ -307,13 +308,16 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         }
 #pragma unroll
         for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
-        if (SL == 8) {
-          *reinterpret_cast<uint4*>(hh + j0) = *reinterpret_cast<const uint4*>(h1);
-          *reinterpret_cast<uint4*>(hl + j0) = *reinterpret_cast<const uint4*>(h2);
-        } else {
-          *reinterpret_cast<uint2*>(hh + j0) = *reinterpret_cast<const uint2*>(h1);
-          *reinterpret_cast<uint2*>(hl + j0) = *reinterpret_cast<const uint2*>(h2);
+#pragma unroll
+        for (int i = 0; i < SL / 2; ++i) {  // keep the packed halves: a thread's UH units are one full 32-byte sector per image
+          hp1[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(h1 + 2 * i);
+          hp2[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(h2 + 2 * i);
         }
+      }
+#pragma unroll
+      for (int i = 0; i < UH / 8; ++i) {
+        *reinterpret_cast<uint4*>(hh + 8 * i) = make_uint4(hp1[4 * i], hp1[4 * i + 1], hp1[4 * i + 2], hp1[4 * i + 3]);
+        *reinterpret_cast<uint4*>(hl + 8 * i) = make_uint4(hp2[4 * i], hp2[4 * i + 1], hp2[4 * i + 2], hp2[4 * i + 3]);
       }
       ++n;
     }
