@@ -174,7 +174,8 @@ typedef struct gb_fit_hparams {
 size_t gb_ffae_fit_state_stride(const gb_ffnet* net);
 
 /* params: [n_slots][param_stride], updated in place.  adam_m / adam_v: [n_slots][state_stride], updated in place
- * (all zero for a fresh fit).  batch_size <= 32 in this version (one mini-batch row per lane).
+ * (all zero for a fresh fit).  Mini-batches above 32 rows are processed as 32-row chunks whose gradients are summed
+ * before the optimizer step (the state arrays carry the scratch for that).
  * perm: [n_jobs][epochs][max_rows] int32 row indices relative to the job (shuffle == 2), else NULL.
  * out_loss / out_acc: [n_jobs][epochs] per-epoch sample-weighted mean loss / categorical accuracy
  * (keras History.history["loss"], ["accuracy"], models.py:339-357). */
