@@ -181,3 +181,19 @@ def base_frame(tags, model_input, model_output, target_tag_list=None, index=None
         second = names if values.shape[1] == len(names) else [str(i) for i in range(values.shape[1])]
         parts.append(pd.DataFrame(values, index=idx, columns=pd.MultiIndex.from_tuples([(name, s) for s in second])))
     return pd.concat(parts, axis=1)
+
+
+# ------------------------------------------------------------------ DiffBasedKFCVAnomalyDetector (diff.py:461-635)
+
+
+def kfcv_thresholds(abs_err: np.ndarray, scaled_mse: np.ndarray, window: Optional[int], smoothing_method: Optional[str], percentile: float):
+    """
+    diff.py:623-635: thresholds = percentile (pandas ``quantile``: linear interpolation, NaNs skipped) of the smoothed validation
+    metric, where every row's metric comes from the K-fold model that did not train on it (:598-615).
+    Returns (feature_thresholds [T], aggregate_threshold).
+    """
+    def thr(metric):
+        m = smoothing(metric, window, smoothing_method) if (window is not None and smoothing_method is not None) else np.asarray(metric, dtype=np.float64)
+        return pd.DataFrame(m).quantile(percentile).values
+
+    return thr(np.asarray(abs_err, dtype=np.float64)), float(thr(np.asarray(scaled_mse, dtype=np.float64).reshape(-1, 1))[0])

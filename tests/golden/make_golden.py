@@ -134,8 +134,30 @@ def anomaly_fixture(name, n_rows, n_tags, window, method, datetime_index, base="
     print(name, "ok", frame.shape)
 
 
+def kfcv_fixture(name, n_rows, n_tags, window, method, q, seed):
+    """DiffBasedKFCVAnomalyDetector (diff.py:461-635) from the reference itself, LinearRegression base estimator."""
+    rng = np.random.default_rng(seed)
+    cols = [f"tag-{i}" for i in range(n_tags)]
+    index = pd.date_range("2019-01-01", periods=n_rows, freq="10min", tz="UTC")
+    X = pd.DataFrame(rng.random((n_rows, n_tags)), columns=cols, index=index)
+    y = pd.DataFrame(rng.random((n_rows, n_tags)) * np.arange(1, n_tags + 1), columns=cols, index=index)
+    det = ref.DiffBasedKFCVAnomalyDetector(base_estimator=MultiOutputRegressor(LinearRegression()), scaler=MinMaxScaler(), window=window,
+                                           smoothing_method=method, threshold_percentile=q)
+    det.cross_validate(X=X, y=y)
+    det.fit(X, y)
+    frame = det.anomaly(X, y, frequency=pd.Timedelta("10min"))
+    save = dict(X=X.values, y=y.values, window=window, method=str(method), q=q, feature_thresholds=np.asarray(det.feature_thresholds_, dtype=np.float64),
+                aggregate_threshold=np.float64(det.aggregate_threshold_), columns_level0=np.array(list(dict.fromkeys(frame.columns.get_level_values(0)))))
+    for top in ("total-anomaly-confidence", "anomaly-confidence", "smooth-total-anomaly-scaled", "smooth-tag-anomaly-unscaled"):
+        save[f"frame_{top}"] = np.asarray(frame[top], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **save)
+    print(name, "ok", frame.shape)
+
+
 if __name__ == "__main__":
     dims_fixture()
+    kfcv_fixture("kfcv_smm", 300, 3, 12, "smm", 0.99, seed=6)
+    kfcv_fixture("kfcv_ewma", 400, 4, 24, "ewma", 0.9, seed=7)
     anomaly_fixture("anomaly_plain", 300, 3, None, None, False)
     anomaly_fixture("anomaly_smm", 300, 3, 12, "smm", True, seed=1)
     anomaly_fixture("anomaly_sma", 200, 4, 12, "sma", True, seed=2)

@@ -657,6 +657,35 @@ def test_kfcv_detector_thresholds(engine, torch, n_rows, window, method, q):
     assert "smooth-total-anomaly-scaled" in frame.columns.get_level_values(0) and "total-anomaly-confidence" in frame.columns.get_level_values(0)
 
 
+@pytest.mark.parametrize("case", ["kfcv_smm", "kfcv_ewma"])
+def test_kfcv_detector_against_reference_generated_fixture(engine, torch, case):
+    """Thresholds and frame columns of the reference's own DiffBasedKFCVAnomalyDetector (tests/golden/make_golden.py ran it
+    from /root/reference with a LinearRegression base estimator) against ours with the same base estimator."""
+    from sklearn.linear_model import LinearRegression
+    from sklearn.multioutput import MultiOutputRegressor
+    from sklearn.preprocessing import MinMaxScaler
+
+    from gordo_components_b200.machine.model.anomaly.diff import DiffBasedKFCVAnomalyDetector
+
+    g = np.load(os.path.join(GOLDEN, f"{case}.npz"), allow_pickle=False)
+    Xv, yv = np.ascontiguousarray(g["X"]), np.ascontiguousarray(g["y"])
+    cols = [f"tag-{i}" for i in range(Xv.shape[1])]
+    idx = pd.date_range("2019-01-01", periods=len(Xv), freq="10min", tz="UTC")
+    X, y = pd.DataFrame(Xv, columns=cols, index=idx), pd.DataFrame(yv, columns=cols, index=idx)
+    det = DiffBasedKFCVAnomalyDetector(base_estimator=MultiOutputRegressor(LinearRegression()), scaler=MinMaxScaler(), window=int(g["window"]),
+                                       smoothing_method=str(g["method"]), threshold_percentile=float(g["q"]))
+    det.cross_validate(X=X, y=y)
+    close(det.feature_thresholds_.values, g["feature_thresholds"], rtol=1e-5, mag=float(np.abs(g["feature_thresholds"]).max()), name="feature thresholds")
+    close(det.aggregate_threshold_, float(g["aggregate_threshold"]), rtol=1e-5, mag=float(g["aggregate_threshold"]), name="aggregate threshold")
+    det.fit(X, y)
+    frame = det.anomaly(X, y, frequency=pd.Timedelta("10min"))
+    assert list(dict.fromkeys(frame.columns.get_level_values(0))) == [str(c) for c in g["columns_level0"]]
+    for top in ("total-anomaly-confidence", "anomaly-confidence", "smooth-total-anomaly-scaled", "smooth-tag-anomaly-unscaled"):
+        want = g[f"frame_{top}"]
+        got = np.asarray(frame[top], dtype=np.float64).reshape(want.shape)
+        close(got, want, rtol=2e-5, mag=float(np.nanmax(np.abs(want))), name=top)
+
+
 def test_quantile_kernel_matches_pandas(engine, torch):
     rng = np.random.default_rng(0)
     dev = engine.cuda_device()

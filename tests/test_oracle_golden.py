@@ -249,3 +249,28 @@ def test_lstm_fit_control_flow():
     X = np.random.default_rng(2).random((40, 3)).astype(np.float32)
     w, hist = km.lstm_fit(spec, km.init_lstm_weights(spec, np.random.default_rng(1)), X, X, epochs=3, batch_size=8)
     assert len(hist["loss"]) == 3 and hist["loss"][2] < hist["loss"][0] and hist["params"]["steps"] == 5
+
+
+@pytest.mark.parametrize("case", ["kfcv_smm", "kfcv_ewma"])
+def test_oracle_kfcv_thresholds_match_reference_fixture(case):
+    """oracle/anomaly_math.kfcv_thresholds against the reference's own DiffBasedKFCVAnomalyDetector (fixture generated by
+    tests/golden/make_golden.py from /root/reference): K-fold predictions of a LinearRegression, fold scalers, smoothing, percentile."""
+    from sklearn.linear_model import LinearRegression
+    from sklearn.model_selection import KFold
+    from sklearn.multioutput import MultiOutputRegressor
+    from sklearn.utils import shuffle as sk_shuffle
+
+    from oracle import anomaly_math as am
+
+    g = np.load(os.path.join(GOLDEN, f"{case}.npz"), allow_pickle=False)
+    X, y = np.ascontiguousarray(g["X"]), np.ascontiguousarray(g["y"])
+    abs_err, mse = np.zeros_like(y), np.zeros(len(y))
+    for tr, te in KFold(n_splits=5, shuffle=True, random_state=0).split(X, y):
+        Xs, ys = sk_shuffle(X[tr], y[tr], random_state=0)  # the KFCV detector shuffles in fit by default (diff.py:469)
+        pred = MultiOutputRegressor(LinearRegression()).fit(Xs, ys).predict(X[te])
+        scale, mn = am.minmax_fit(y[tr])
+        abs_err[te] = np.abs(pred - y[te])
+        mse[te] = ((am.minmax_transform(pred, scale, mn) - am.minmax_transform(y[te], scale, mn)) ** 2).mean(axis=1)
+    feat, agg = am.kfcv_thresholds(abs_err, mse, int(g["window"]), str(g["method"]), float(g["q"]))
+    np.testing.assert_allclose(feat, g["feature_thresholds"], rtol=1e-9)
+    np.testing.assert_allclose(agg, float(g["aggregate_threshold"]), rtol=1e-9)
