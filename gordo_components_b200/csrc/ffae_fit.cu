@@ -76,6 +76,10 @@ __device__ __forceinline__ void adam_update(float& w, float g, float& m, float& 
   w -= __fdividef(alpha * m, sq + eps);
 }
 
+// WG = false: the slot's padded weight image lives in shared memory for the whole fit (every 64-tag stack).  WG = true: the image does
+// not fit beside the activations (e.g. the 128-tag hourglass, 245 KB) and lives in the slot's L2-resident state area instead; the
+// code is the same, the loads become global.
+template <bool WG>
 __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float s_red[3][NWARPS];
@@ -88,13 +92,15 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.net.n_layers, n_in = a.n_in, n_out = a.n_out;
   const int B = a.hp.batch_size;
-  float* sW = smem;
   float* P = a.params + (long)job.slot * a.pstride;
   float* Mg = a.adam_m + (long)job.slot * a.sstride;
+  float* sW = WG ? Mg + 2 * a.wfloats : smem;
   float* Vg = a.adam_v + (long)job.slot * a.sstride;
 
   // ---- weights -> padded smem image; zero every staging buffer ------------------------------------
   for (int i = tid; i < a.smem_floats; i += THREADS) smem[i] = 0.f;
+  if (WG)
+    for (int i = tid; i < a.wfloats; i += THREADS) sW[i] = 0.f;  // the padding of the image must read as zero
   __syncthreads();
   for (int l = 0; l < L; ++l) {
     const int K = a.net.dims[l], N = a.net.dims[l + 1], Np = a.im.np[l];
@@ -404,7 +410,7 @@ extern "C" {
 
 size_t gb_ffae_fit_state_stride(const gb_ffnet* net) {
   if (gb::validate_ffnet(net) != GB_OK) return 0;
-  return 2 * (size_t)gb::round_up(gb::make_ff_image(net, 4).total, 4);  // moments + gradient scratch of multi-chunk mini-batches
+  return 3 * (size_t)gb::round_up(gb::make_ff_image(net, 4).total, 4);  // moments + gradient scratch of multi-chunk mini-batches + weight image of wide stacks
 }
 
 int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v, const gb_job* jobs, int32_t n_jobs,
@@ -433,26 +439,37 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
   a.max_rows = max_rows;
   a.pstride = (long)gb_ffnet_param_stride(net);
   a.sstride = (long)gb_ffae_fit_state_stride(net);
-  int ofs = gb::round_up(a.im.total, 4);
-  a.wfloats = ofs;
-  a.apitch[0] = odd_pitch(a.im.kp[0]);
-  for (int l = 1; l <= L; ++l) {
-    a.apitch[l] = odd_pitch(a.im.np[l - 1]);
-    a.aofs[l] = ofs;
-    ofs += BR * a.apitch[l];
+  a.wfloats = gb::round_up(a.im.total, 4);
+  size_t smem = 0;
+  bool w_global = false;
+  for (int pass = 0; pass < 2; ++pass) {  // first with the weight image in shared memory; if that does not fit, with the image in L2
+    int ofs = w_global ? 0 : a.wfloats;
+    a.apitch[0] = odd_pitch(a.im.kp[0]);
+    for (int l = 1; l <= L; ++l) {
+      a.apitch[l] = odd_pitch(a.im.np[l - 1]);
+      a.aofs[l] = ofs;
+      ofs += BR * a.apitch[l];
+    }
+    for (int b = 0; b < 2; ++b) { a.xofs[b] = ofs; ofs += BR * a.apitch[0]; }
+    a.ypitch = odd_pitch(gb::round_up(a.n_out, 4));
+    for (int b = 0; b < 2; ++b) { a.yofs[b] = ofs; ofs += BR * a.ypitch; }
+    a.dpitch = odd_pitch(a.im.max_np);
+    for (int b = 0; b < 2; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
+    a.smem_floats = ofs;
+    smem = (size_t)ofs * sizeof(float);
+    if (smem <= 227 * 1024) break;
+    w_global = true;
   }
-  for (int b = 0; b < 2; ++b) { a.xofs[b] = ofs; ofs += BR * a.apitch[0]; }
-  a.ypitch = odd_pitch(gb::round_up(a.n_out, 4));
-  for (int b = 0; b < 2; ++b) { a.yofs[b] = ofs; ofs += BR * a.ypitch; }
-  a.dpitch = odd_pitch(a.im.max_np);
-  for (int b = 0; b < 2; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
-  a.smem_floats = ofs;
-  const size_t smem = (size_t)ofs * sizeof(float);
-  GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory for a resident fit", smem);
+  GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory for the activations of one mini-batch chunk", smem);
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.jobs = jobs; a.x = x; a.y = y; a.perm = perm;
   a.out_loss = out_loss; a.out_acc = out_acc;
-  GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ffae_fit_kernel<<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
+  if (w_global) {
+    GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ffae_fit_kernel<true><<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ffae_fit_kernel<false><<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
+  }
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }

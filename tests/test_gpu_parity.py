@@ -255,7 +255,7 @@ def test_detector_with_window_like_reference_tests(engine, torch):
 
 
 # ------------------------------------------------------------------------------------------------ K2
-@pytest.mark.parametrize("T,batch", [(8, 32), (64, 32), (10, 7), (64, 128), (8, 50), (64, 33)])  # > 32: gradient sums over 32-row chunks
+@pytest.mark.parametrize("T,batch", [(8, 32), (64, 32), (10, 7), (64, 128), (8, 50), (64, 33), (128, 32), (128, 48)])  # batch > 32: gradient sums over 32-row chunks; 128 tags: weight image in L2
 def test_ffae_fit_matches_oracle_adam(engine, torch, T, batch):
     """Same initial weights + same visiting order => same weights/loss as the oracle's Keras-style Adam loop."""
     from oracle import keras_math as km
