@@ -77,6 +77,79 @@ def _as_2d_values(a):
     return np.asarray(a)
 
 
+class EarlyStopping:
+    """
+    The one Keras callback gordo's model definitions use (``tensorflow.keras.callbacks.EarlyStopping``: monitor, min_delta,
+    patience, mode, baseline, restore_best_weights, start_from_epoch), restated from keras 3.3.3 [3P]
+    ``keras/src/callbacks/early_stopping.py`` -- epochs are kernel launches here, so the callback is host-side bookkeeping
+    between them.  ``update(epoch, logs, get_weights)`` returns True when training must stop.
+    """
+
+    def __init__(self, monitor="val_loss", min_delta=0, patience=0, verbose=0, mode="auto", baseline=None, restore_best_weights=False,
+                 start_from_epoch=0):
+        self.monitor, self.patience, self.verbose, self.baseline = monitor, int(patience), verbose, baseline
+        self.min_delta = abs(float(min_delta))
+        self.restore_best_weights, self.start_from_epoch = bool(restore_best_weights), int(start_from_epoch)
+        if mode not in ("auto", "min", "max"):
+            mode = "auto"
+        if mode == "auto":  # keras: accuracy-like metrics are maximised, everything else minimised
+            mode = "max" if any(k in monitor for k in ("acc", "accuracy", "auc")) else "min"
+        self.mode = mode
+        self.reset()
+
+    def reset(self):
+        self.wait, self.stopped_epoch, self.best_epoch = 0, 0, 0
+        self.best = float("inf") if self.mode == "min" else -float("inf")
+        self.best_weights = None
+
+    def _is_improvement(self, value, reference):
+        return value + self.min_delta < reference if self.mode == "min" else value - self.min_delta > reference
+
+    def update(self, epoch: int, logs: Dict[str, float], get_weights: Callable) -> bool:
+        current = logs.get(self.monitor)
+        if current is None or epoch < self.start_from_epoch:
+            if current is None:
+                logger.warning("Early stopping conditioned on metric `%s` which is not available. Available metrics are: %s",
+                               self.monitor, ",".join(logs))
+            return False
+        if self.restore_best_weights and self.best_weights is None:
+            self.best_weights, self.best_epoch = get_weights(), epoch
+        self.wait += 1
+        if self._is_improvement(current, self.best):
+            self.best, self.best_epoch = current, epoch
+            if self.restore_best_weights:
+                self.best_weights = get_weights()
+            if self.baseline is None or self._is_improvement(current, self.baseline):
+                self.wait = 0
+            return False
+        if self.wait >= self.patience and epoch > 0:
+            self.stopped_epoch = epoch
+            return True
+        return False
+
+
+def build_callbacks(definitions) -> list:
+    """
+    ``callbacks`` of a model definition -- ``[{"tensorflow.keras.callbacks.EarlyStopping": {...}}]`` as gordo's serializer
+    receives them (gordo/serializer/from_definition.py:337-372) or already-built objects -- to the callbacks this fit loop
+    understands.  Anything but EarlyStopping is reported and skipped.
+    """
+    out = []
+    for cb in definitions or []:
+        if isinstance(cb, EarlyStopping):
+            out.append(cb)
+        elif isinstance(cb, dict) and len(cb) == 1 and str(next(iter(cb))).split(".")[-1] == "EarlyStopping":
+            out.append(EarlyStopping(**(next(iter(cb.values())) or {})))
+        elif isinstance(cb, str) and cb.split(".")[-1] == "EarlyStopping":
+            out.append(EarlyStopping())
+        elif type(cb).__name__ == "EarlyStopping":  # a real keras object handed over by the caller
+            out.append(EarlyStopping(**{k: getattr(cb, k) for k in ("monitor", "min_delta", "patience", "baseline", "restore_best_weights",
+                                                                    "start_from_epoch") if hasattr(cb, k)}))
+        else:
+            logger.warning("callback %s is not supported by the B200 fit loop and is ignored", cb)
+    return out
+
+
 class KerasBaseEstimator(BaseEstimator, GordoBase):
     # keyword arguments of the model definition that steer fitting rather than the architecture
     supported_fit_args = [
@@ -255,8 +328,9 @@ class KerasBaseEstimator(BaseEstimator, GordoBase):
         batch_size = int(fit_args.get("batch_size") or 32)
         shuffle = bool(fit_args.get("shuffle", True))
         vsplit = float(fit_args.get("validation_split") or 0.0)
-        if fit_args.get("callbacks"):
-            logger.warning("callbacks %s are not supported by the B200 fit kernel and are ignored", fit_args["callbacks"])
+        callbacks = build_callbacks(fit_args.get("callbacks"))
+        for cb in callbacks:
+            cb.reset()
         n_train = len(X)
         if 0.0 < vsplit < 1.0:  # keras holds out the *tail* before shuffling
             n_train = int(math.floor(len(X) * (1.0 - vsplit)))
@@ -272,29 +346,50 @@ class KerasBaseEstimator(BaseEstimator, GordoBase):
         history: Dict[str, list] = {"loss": []}
         if "accuracy" in spec.metrics:
             history["accuracy"] = []
-        if n_train < len(X):
-            history["val_loss"] = []
-            vjobs = engine.jobs_to_device(engine.make_jobs([0], [len(X) - n_train], [n_train]), dev)
+        n_val = len(X) - n_train
+        if n_val or callbacks:
+            # one launch per epoch: the validation loss and the callbacks live between epochs
+            if n_val:
+                history["val_loss"] = []
+                if "accuracy" in history:
+                    history["val_accuracy"] = []
+                vjobs = engine.jobs_to_device(engine.make_jobs([0], [n_val], [n_train]), dev)
+                vbatch = int(fit_args.get("validation_batch_size") or batch_size)
             state, step0 = None, 0
             steps = int(math.ceil(n_train / batch_size))
+            frozen = dict(spec.adam, lr=0.0)
             for e in range(epochs):
                 loss, acc, state = eng.fit(params, jobs, 1, n_train, xd, yd, epochs=1, batch_size=batch_size, shuffle=shuffle,
                                            adam=spec.adam, seed=seed + e, state=state, step0=step0)
                 step0 += steps
-                history["loss"].append(float(loss[0, 0]))
+                logs = {"loss": float(loss[0, 0])}
                 if "accuracy" in history:
-                    history["accuracy"].append(float(acc[0, 0]))
-                res = eng.infer_score(params, vjobs, 1, len(X) - n_train, xd, yd, want=("total-anomaly-unscaled",))
-                history["val_loss"].append(float(res["total-anomaly-unscaled"][n_train:].mean()))
+                    logs["accuracy"] = float(acc[0, 0])
+                if n_val:
+                    # keras evaluates the *total* loss (MSE + activity regularisation) on the held-out tail in batches: the fit
+                    # kernel with a zero learning rate on a throw-away optimizer state computes exactly that and moves nothing
+                    vl, va, _ = eng.fit(params, vjobs, 1, n_val, xd, yd, epochs=1, batch_size=vbatch, shuffle=False, adam=frozen)
+                    logs["val_loss"] = float(vl[0, 0])
+                    if "accuracy" in history:
+                        logs["val_accuracy"] = float(va[0, 0])
+                for k, v in logs.items():
+                    history[k].append(v)
+                if any([cb.update(e, logs, lambda: params.clone()) for cb in callbacks]):
+                    break
+            for cb in callbacks:  # keras restores at train end whether or not training stopped early
+                if cb.restore_best_weights and cb.best_weights is not None:
+                    params = cb.best_weights
+            epochs_run = len(history["loss"])
         else:
             loss, acc, _ = eng.fit(params, jobs, 1, n_train, xd, yd, epochs=epochs, batch_size=batch_size, shuffle=shuffle,
                                    adam=spec.adam, seed=seed)
             history["loss"] = [float(v) for v in loss[0].cpu().numpy()]
             if "accuracy" in history:
                 history["accuracy"] = [float(v) for v in acc[0].cpu().numpy()]
+            epochs_run = epochs
         self.model.weights = eng.unpack_params(params)[0]
         self.__dict__["_dev_cache"] = (self.model.weights, params)
-        self._history = History(history, {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n_train / batch_size))}, list(range(epochs)))
+        self._history = History(history, {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n_train / batch_size))}, list(range(epochs_run)))
         self.model.history = self._history
         return self
 

@@ -478,6 +478,29 @@ def test_estimator_validation_split_and_score(engine, torch):
     np.testing.assert_array_equal(a, b)
 
 
+def test_estimator_early_stopping_like_the_example_config(engine, torch):
+    """test_anomaly_detectors.py:520-534 / test_model.py:341-361: epochs=1000 with EarlyStopping(val_loss, patience, restore_best_weights)
+    stops long before, val_loss is the total loss (MSE + activity L1) on the held-out tail, and the best weights come back."""
+    from gordo_components_b200.machine.model.models import KerasAutoEncoder
+    from oracle import keras_math as km
+
+    np.random.seed(5)
+    t = np.linspace(0, 20, 400)[:, None]
+    X = (0.5 + 0.4 * np.sin(t * np.linspace(0.5, 2, 6)) + np.random.normal(0, 0.05, (400, 6))).astype(np.float32)
+    m = KerasAutoEncoder(kind="feedforward_hourglass", batch_size=128, epochs=1000, validation_split=0.1, compression_factor=0.5, encoding_layers=1,
+                         callbacks=[{"tensorflow.keras.callbacks.EarlyStopping": {"monitor": "val_loss", "patience": 3, "restore_best_weights": True}}])
+    m.fit(X, X)
+    h = m.get_metadata()["history"]
+    n = len(h["loss"])
+    assert 4 <= n < 1000 and len(h["val_loss"]) == n and h["params"]["epochs"] == 1000
+    best = int(np.argmin(h["val_loss"]))
+    assert n - 1 - best == 3  # stopped `patience` epochs after the best one
+    # the restored weights reproduce the best epoch's validation loss (oracle: total loss on the tail, one batch of 40 rows)
+    spec = km.ff_hourglass_spec(6, encoding_layers=1)
+    total, _mse, _g, _yh = km.ff_loss_and_grads(spec, m.model.weights, X[360:], X[360:], np.float64)
+    close(float(total), h["val_loss"][best], rtol=2e-4, mag=0.0, name="restored best weights / val_loss semantics")
+
+
 def test_lstm_estimator_predict_shapes(engine, torch):
     """tests/gordo/machine/model/test_model.py:324-338 and tests/gordo/builder/test_builder.py:99-115 (offsets)."""
     from gordo_components_b200.machine.model.models import KerasLSTMAutoEncoder, KerasLSTMForecast

@@ -245,6 +245,35 @@ def test_kfcv_detector_protocol():
         d.anomaly(frame, frame)
 
 
+def test_early_stopping_state_machine():
+    """keras 3.3.3 EarlyStopping semantics [3P] (the callback of gordo's model definitions, test_model.py:341-361,
+    test_anomaly_detectors.py:531-534), restated for the per-epoch launch loop."""
+    from gordo_components_b200.machine.model.models import EarlyStopping, build_callbacks
+
+    (cb,) = build_callbacks([{"tensorflow.keras.callbacks.EarlyStopping": {"monitor": "val_loss", "patience": 2, "restore_best_weights": True}}])
+    assert cb.monitor == "val_loss" and cb.patience == 2 and cb.mode == "min"
+    w = [None]
+    stops = []
+    for e, v in enumerate([1.0, 0.8, 0.9, 0.85, 0.95]):
+        w[0] = e
+        stops.append(cb.update(e, {"val_loss": v}, lambda: w[0]))
+        if stops[-1]:
+            break
+    assert stops == [False, False, False, True] and cb.best == 0.8 and cb.best_weights == 1 and cb.stopped_epoch == 3
+    # min_delta: an improvement smaller than it does not count; patience 0 stops at the first non-improving epoch after epoch 0
+    cb = EarlyStopping(monitor="loss", min_delta=0.1, patience=0)
+    assert [cb.update(e, {"loss": v}, lambda: None) for e, v in enumerate([1.0, 0.95])] == [False, True]
+    # baseline: wait only restarts when the baseline is beaten too, and the stop test runs on non-improving epochs only
+    cb = EarlyStopping(monitor="loss", patience=2, baseline=0.5)
+    assert [cb.update(e, {"loss": v}, lambda: None) for e, v in enumerate([1.0, 0.9, 0.8, 0.85])] == [False, False, False, True]
+    # a missing metric never stops training; accuracy-like monitors are maximised
+    assert EarlyStopping(monitor="val_loss").update(0, {"loss": 1.0}, lambda: None) is False
+    assert EarlyStopping(monitor="val_accuracy").mode == "max"
+    assert build_callbacks([{"tensorflow.keras.callbacks.TerminateOnNaN": {}}]) == []
+    m = KerasAutoEncoder(kind="feedforward_hourglass", batch_size=128, callbacks=[{"tensorflow.keras.callbacks.EarlyStopping": {"monitor": "val_loss", "patience": 10}}])
+    assert len(m.sk_params["callbacks"]) == 1 and clone(m).get_params() == m.get_params()
+
+
 def test_scaler_multiplier():
     from sklearn.preprocessing import QuantileTransformer, RobustScaler
 
