@@ -488,8 +488,9 @@ class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin, metaclass=abc
         spec = self.model.spec
         fit_args = {**self.extract_supported_fit_args(self.kwargs), **kwargs}
         epochs = int(fit_args.get("epochs", 1))
-        if fit_args.get("callbacks"):
-            logger.warning("callbacks %s are not supported by the B200 fit kernel and are ignored", fit_args["callbacks"])
+        callbacks = build_callbacks(fit_args.get("callbacks"))
+        for cb in callbacks:
+            cb.reset()
         batch_size = int(self.batch_size)
         n_win = len(X) - self.lookback_window + 1 - self.lookahead
         if n_win < 1:
@@ -499,14 +500,34 @@ class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin, metaclass=abc
         xd, yd = engine.to_device_f32(X, dev), engine.to_device_f32(y, dev)
         params = eng.pack_params([self.model.weights])
         jobs = engine.jobs_to_device(engine.make_jobs([0], [n_win], [0]), dev)
-        loss, acc, _ = eng.fit(params, jobs, 1, n_win, xd, yd, epochs=epochs, batch_size=batch_size, lookahead=self.lookahead,
-                               primer=True, adam=getattr(spec, "adam", None))
+        want_acc = "accuracy" in getattr(spec, "metrics", ("accuracy",))
+        history: Dict[str, list] = {"loss": []}
+        if want_acc:
+            history["accuracy"] = []
+        if callbacks:  # one launch sequence per epoch, the callbacks in between (the generator fit has no validation data)
+            state = None
+            for e in range(epochs):
+                loss, acc, state = eng.fit(params, jobs, 1, n_win, xd, yd, epochs=1, batch_size=batch_size, lookahead=self.lookahead,
+                                           primer=(e == 0), adam=getattr(spec, "adam", None), state=state)
+                logs = {"loss": float(loss[0, 0])}
+                if want_acc:
+                    logs["accuracy"] = float(acc[0, 0])
+                for k, v in logs.items():
+                    history[k].append(v)
+                if any([cb.update(e, logs, lambda: params.clone()) for cb in callbacks]):
+                    break
+            for cb in callbacks:
+                if cb.restore_best_weights and cb.best_weights is not None:
+                    params = cb.best_weights
+        else:
+            loss, acc, _ = eng.fit(params, jobs, 1, n_win, xd, yd, epochs=epochs, batch_size=batch_size, lookahead=self.lookahead,
+                                   primer=True, adam=getattr(spec, "adam", None))
+            history["loss"] = [float(v) for v in loss[0].cpu().numpy()]
+            if want_acc:
+                history["accuracy"] = [float(v) for v in acc[0].cpu().numpy()]
         self.model.weights = eng.unpack_params(params)[0]
         self.__dict__["_dev_cache"] = (self.model.weights, params)
-        history: Dict[str, list] = {"loss": [float(v) for v in loss[0].cpu().numpy()]}
-        if "accuracy" in getattr(spec, "metrics", ("accuracy",)):
-            history["accuracy"] = [float(v) for v in acc[0].cpu().numpy()]
-        self._history = History(history, {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n_win / batch_size))}, list(range(epochs)))
+        self._history = History(history, {"verbose": 0, "epochs": epochs, "steps": int(math.ceil(n_win / batch_size))}, list(range(len(history["loss"]))))
         self.model.history = self._history
         return self
 

@@ -517,6 +517,10 @@ def test_lstm_estimator_predict_shapes(engine, torch):
         a.predict(np.random.random((10, 5)))
     a.fit(X, X, epochs=2)
     assert a.get_metadata()["history"]["loss"][1] < a.get_metadata()["history"]["loss"][0]
+    es = KerasLSTMAutoEncoder(kind="lstm_hourglass", lookback_window=10, epochs=50,
+                              callbacks=[{"tensorflow.keras.callbacks.EarlyStopping": {"monitor": "loss", "patience": 1, "min_delta": 10.0}}])
+    es.fit(X, X)  # no epoch can improve by 10: the first non-improving epoch after epoch 0 stops the training
+    assert len(es.get_metadata()["history"]["loss"]) == 2 and es.get_metadata()["history"]["params"]["epochs"] == 50
     assert a.get_metadata()["forecast_steps"] == 0 and len(X) - len(a.predict(X)) == 9
 
 
