@@ -14,6 +14,7 @@ models.py:284,300), sklearn ``MinMaxScaler.fit`` and the pandas arithmetic of
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -388,22 +389,25 @@ class LSTMEngine:
 
 _ff_engines: Dict[tuple, FFEngine] = {}
 _lstm_engines: Dict[tuple, LSTMEngine] = {}
+_engine_lock = threading.Lock()  # gordo.server calls into shared models from several gunicorn threads
 
 
 def ff_engine_for(spec, device=None) -> FFEngine:
     dev = cuda_device(device)
     key = (spec.key(), tuple(spec.l1), dev.index)
-    if key not in _ff_engines:
-        _ff_engines[key] = FFEngine(spec.dims, spec.acts, spec.l1, dev)
-    return _ff_engines[key]
+    with _engine_lock:
+        if key not in _ff_engines:
+            _ff_engines[key] = FFEngine(spec.dims, spec.acts, spec.l1, dev)
+        return _ff_engines[key]
 
 
 def lstm_engine_for(spec, device=None) -> LSTMEngine:
     dev = cuda_device(device)
     key = (spec.key(), dev.index)
-    if key not in _lstm_engines:
-        _lstm_engines[key] = LSTMEngine(spec.n_features, spec.lstm_units, spec.acts, spec.n_features_out, spec.out_func, spec.lookback_window, dev)
-    return _lstm_engines[key]
+    with _engine_lock:
+        if key not in _lstm_engines:
+            _lstm_engines[key] = LSTMEngine(spec.n_features, spec.lstm_units, spec.acts, spec.n_features_out, spec.out_func, spec.lookback_window, dev)
+        return _lstm_engines[key]
 
 
 def to_device_f32(a, device):
