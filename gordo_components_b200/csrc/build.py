@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libgordo_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["gb_api.cu", "ffae_infer_fma.cu", "ffae_infer_tc.cu", "anomaly_reduce.cu", "smooth.cu", "ffae_fit.cu", "lstm_infer.cu", "lstm_infer_tc.cu", "lstm_fit.cu"]
+SOURCES = ["gb_api.cu", "ffae_infer_fma.cu", "ffae_infer_small.cu", "ffae_infer_tc.cu", "anomaly_reduce.cu", "smooth.cu", "ffae_fit.cu", "lstm_infer.cu", "lstm_infer_tc.cu", "lstm_fit.cu"]
 HEADERS = ["gb_common.cuh", os.path.join("..", "..", "include", "gordo_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -84,6 +84,9 @@ size_t gb_ffnet_param_stride(const gb_ffnet* net) { return (gb_ffnet_param_count
 int gb_ffae_infer_score_fma(const gb_ffnet*, const float*, const gb_job*, int32_t, int32_t, const float*, const float*,
                             const float*, const float*, const float*, float*, float*, float*, float*, float*, float*,
                             float*, void*);
+int gb_ffae_small_supported(const gb_ffnet*);
+int gb_ffae_infer_score_small(const gb_ffnet*, const float*, const gb_job*, int32_t, int32_t, const float*, const float*, const float*,
+                              const float*, const float*, float*, float*, float*, float*, float*, float*, float*, void*);
 int gb_ffae_infer_score_tc(const gb_ffnet*, const float*, const gb_job*, int32_t, int32_t, int64_t, int64_t, const float*,
                            const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*,
                            float*, float*, int32_t, void*);
@@ -100,7 +103,7 @@ int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* 
   GB_REQUIRE(n_jobs >= 0 && max_rows >= 0, GB_E_ARG, "negative n_jobs/max_rows");
   const int32_t tc_flags = variant >> 8;
   variant &= 0xff;
-  GB_REQUIRE(variant >= 0 && variant <= 2, GB_E_ARG, "variant=%d unknown", variant);
+  GB_REQUIRE(variant >= 0 && variant <= 3, GB_E_ARG, "variant=%d unknown", variant);
   if (y == nullptr)
     GB_REQUIRE(!out_tag_scaled && !out_tag_unscaled && !out_total_scaled && !out_total_unscaled && !out_conf &&
                    !out_total_conf,
@@ -119,6 +122,11 @@ int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* 
     return gb_ffae_infer_score_tc(net, params, jobs, n_jobs, max_rows, n_x_rows, n_out_rows, x, y, scale, feat_thr, agg_thr,
                                   out_model, out_tag_scaled, out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf,
                                   out_total_conf, tc_flags, stream);
+  const bool small_ok = gb_ffae_small_supported(net) == GB_OK && n_jobs <= 65535;
+  if (variant == 3 && !small_ok) return GB_E_SHAPE;
+  if (variant == 3 || (variant == 0 && small_ok))
+    return gb_ffae_infer_score_small(net, params, jobs, n_jobs, max_rows, x, y, scale, feat_thr, agg_thr, out_model, out_tag_scaled,
+                                     out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf, out_total_conf, stream);
   return gb_ffae_infer_score_fma(net, params, jobs, n_jobs, max_rows, x, y, scale, feat_thr, agg_thr, out_model,
                                  out_tag_scaled, out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf,
                                  out_total_conf, stream);

@@ -97,8 +97,9 @@ size_t gb_ffnet_param_stride(const gb_ffnet* net);
  * params: [n_slots][param_stride]; scale, feat_thr: [n_slots][n_out]; agg_thr: [n_slots].
  * jobs: DEVICE array of n_jobs gb_job; max_rows = max n_rows over jobs (host value, sizes the grid).
  * n_x_rows / n_out_rows: number of rows of the x (and y) array and of the output arrays (TMA tensor extents).
- * variant (low byte): 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 split-precision kernel (GB_E_SHAPE if the
- * architecture is outside gb_ffae_tc_supported); higher bytes are debug knobs of the tcgen05 kernel and must be 0. */
+ * variant (low byte): 0 = auto (tcgen05 kernel for the stacks it covers, the row-per-thread kernel for stacks whose widths are
+ * all <= 16, else the generic one), 1 = generic fp32 CUDA-core kernel, 2 = tcgen05 split-precision kernel, 3 = row-per-thread
+ * fp32 kernel (2 / 3: GB_E_SHAPE if the architecture is outside their range); higher bytes are debug knobs and must be 0. */
 int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* jobs, int32_t n_jobs,
                         int32_t max_rows, int64_t n_x_rows, int64_t n_out_rows, const float* x, const float* y, const float* scale,
                         const float* feat_thr, const float* agg_thr, float* out_model,
