@@ -1,8 +1,8 @@
 // K3, variant 2: LSTM autoencoder prediction on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), machine-batched.
 //
 // Replaces KerasLSTMBaseEstimator.predict (gordo/machine/model/models.py:618-660) for the stacks of
-// factories/lstm_autoencoder.py:72-103 whose layer widths are multiples of 64 (lstm_symmetric's 256/128/64 defaults --
-// BASELINE configs[3]); other stacks take lstm_infer.cu.  Windows are index arithmetic, never materialised (:713-793).
+// factories/lstm_autoencoder.py:72-103 (layer widths are padded to multiples of 64 internally; lstm_symmetric's 256/128/64
+// defaults -- BASELINE configs[3] -- need no padding).  Windows are index arithmetic, never materialised (:713-793).
 //
 // 335 MFLOP per 144 x 128 window is tensor-core work.  One launch advances EVERY window of EVERY job by one (layer,
 // timestep): a CTA owns a tile of 128 windows x 64 units and computes the four gate pre-activations
@@ -329,36 +329,43 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
 
 // ------------------------------------------------------------------------------------------------ preparation kernels (fp32 CUDA cores)
 // reordered gate column n' = ub*256 + g*64 + j  <->  keras column g*u + ub*64 + j
+// Layer widths are padded to multiples of 64 inside this kernel family (zero weights and biases keep the padded units at
+// c = h = 0 for all t), so any stack runs on the tensor cores; u below is the REAL width, -1 marks a padded unit.
 __device__ __forceinline__ int keras_col(int np, int u) {
-  const int ub = np >> 8, g = (np >> 6) & 3, j = np & 63;
-  return g * u + ub * UB + j;
+  const int ub = np >> 8, g = (np >> 6) & 3, j = np & 63, unit = ub * UB + j;
+  return unit < u ? g * u + unit : -1;
 }
 
 // weight images of one layer: rows n' (4u per slot), K contiguous: [below part padded to 64 | own part], FP16 pair
-__global__ void lstm_tc_weights_kernel(const float* __restrict__ params, long pstride, long kofs, int in, int u, int kp_below, int kp, int use_below,
-                                       __half* __restrict__ w_hi, __half* __restrict__ w_lo, float* __restrict__ bias) {
+__global__ void lstm_tc_weights_kernel(const float* __restrict__ params, long pstride, long kofs, int in, int u, int up, int kp_below, int kp,
+                                       int use_below, __half* __restrict__ w_hi, __half* __restrict__ w_lo, float* __restrict__ bias) {
   const int slot = blockIdx.y;
-  const float* P = params + (long)slot * pstride + kofs;  // kernel [in][4u], recurrent [u][4u], bias [4u]
-  const int u4 = 4 * u;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)u4 * kp; i += (long)gridDim.x * blockDim.x) {
+  const float* P = params + (long)slot * pstride + kofs;  // kernel [in][4u], recurrent [u][4u], bias [4u]  (real widths)
+  const int u4 = 4 * u, up4 = 4 * up;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)up4 * kp; i += (long)gridDim.x * blockDim.x) {
     const int np = (int)(i / kp), k = (int)(i - (long)np * kp);
     const int col = keras_col(np, u);
     float v = 0.f;
-    if (k < kp_below) {
-      if (use_below && k < in) v = P[(long)k * u4 + col];
-    } else if (k - kp_below < u) {
-      v = P[(long)(in + k - kp_below) * u4 + col];
+    if (col >= 0) {
+      if (k < kp_below) {
+        if (use_below && k < in) v = P[(long)k * u4 + col];
+      } else if (k - kp_below < u) {
+        v = P[(long)(in + k - kp_below) * u4 + col];
+      }
     }
     const __half h = __float2half_rn(v);
-    w_hi[((long)slot * u4 + np) * kp + k] = h;
-    w_lo[((long)slot * u4 + np) * kp + k] = __float2half_rn(v - __half2float(h));
+    w_hi[((long)slot * up4 + np) * kp + k] = h;
+    w_lo[((long)slot * up4 + np) * kp + k] = __float2half_rn(v - __half2float(h));
   }
   if (blockIdx.x == 0)
-    for (int np = threadIdx.x; np < u4; np += blockDim.x) bias[(long)slot * u4 + np] = P[(long)(in + u) * u4 + keras_col(np, u)];
+    for (int np = threadIdx.x; np < up4; np += blockDim.x) {
+      const int col = keras_col(np, u);
+      bias[(long)slot * up4 + np] = col >= 0 ? P[(long)(in + u) * u4 + col] : 0.f;
+    }
 }
 
 // layer 0 input projection per ROW: xk[row][n'] = x[row] . K0[:, col(n')] + b0[col(n')]; grid (ceil(rows/32), 4u/64, jobs)
-__global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restrict__ jobs, const float* __restrict__ x, int F, int u, int lookback,
+__global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restrict__ jobs, const float* __restrict__ x, int F, int u, int up, int lookback,
                                                          const float* __restrict__ params, long pstride, float* __restrict__ xk) {
   const gb_job job = jobs[blockIdx.z];
   const int n_x = job.n_rows + lookback - 1;  // x rows this job's windows touch
@@ -380,7 +387,8 @@ __global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restric
     }
     for (int i = tid; i < 32 * 64; i += 256) {
       const int kk = i >> 6, c = i & 63, k = k0 + kk;
-      sW[kk][c] = k < F ? __ldg(P + (long)k * u4 + keras_col(c0 + c, u)) : 0.f;
+      const int kcol = keras_col(c0 + c, u);
+      sW[kk][c] = (k < F && kcol >= 0) ? __ldg(P + (long)k * u4 + kcol) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -391,8 +399,8 @@ __global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restric
     }
     __syncthreads();
   }
-  const float b = __ldg(P + (long)(F + u) * u4 + kc);
-  // out: row-blocked [row / 128][4u][128]; staged through shared memory so that lanes run along rows (128-byte segments)
+  const float b = kc >= 0 ? __ldg(P + (long)(F + u) * u4 + kc) : 0.f;
+  // out: row-blocked [row / 128][4 * up][128]; staged through shared memory so that lanes run along rows (128-byte segments)
 #pragma unroll
   for (int i = 0; i < 8; ++i) sW[rg + 4 * i][col] = acc[i] + b;  // sW reused as [32 rows][64 columns]
   __syncthreads();
@@ -400,15 +408,15 @@ __global__ void __launch_bounds__(256) lstm_tc_xk_kernel(const gb_job* __restric
     const int c = i >> 5, rr = i & 31, r = r0 + rr;
     if (r < n_x) {
       const long xr = job.x_row + r;
-      xk[((xr >> 7) * (long)u4 + c0 + c) * TILE + (xr & (TILE - 1))] = sW[rr][c];
+      xk[((xr >> 7) * (long)(4 * up) + c0 + c) * TILE + (xr & (TILE - 1))] = sW[rr][c];
     }
   }
 }
 
 // Dense head on the last layer's final h: out[w][o] = act(sum_k h[w][k] Wd[k][o] + bd[o]); grid (tiles, jobs)
 __global__ void __launch_bounds__(128) lstm_tc_head_kernel(const gb_job* __restrict__ jobs, int tiles_per_job, const __half* __restrict__ h_hi,
-                                                           const __half* __restrict__ h_lo, int u, int n_out, int out_act, const float* __restrict__ params,
-                                                           long pstride, long dofs, float* __restrict__ out) {
+                                                           const __half* __restrict__ h_lo, int u, int up, int n_out, int out_act,
+                                                           const float* __restrict__ params, long pstride, long dofs, float* __restrict__ out) {
   const gb_job job = jobs[blockIdx.y];
   const int w = blockIdx.x * TILE + threadIdx.x;
   if (w >= job.n_rows) return;
@@ -417,7 +425,7 @@ __global__ void __launch_bounds__(128) lstm_tc_head_kernel(const gb_job* __restr
   const float* bd = Wd + (long)u * n_out;
   for (int o = 0; o < n_out; ++o) {
     float acc = __ldg(bd + o);
-    for (int k = 0; k < u; ++k) acc = fmaf(__half2float(h_hi[row * u + k]) + __half2float(h_lo[row * u + k]), __ldg(Wd + (long)k * n_out + o), acc);
+    for (int k = 0; k < u; ++k) acc = fmaf(__half2float(h_hi[row * up + k]) + __half2float(h_lo[row * up + k]), __ldg(Wd + (long)k * n_out + o), acc);
     out[(job.out_row + w) * (long)n_out + o] = gb::apply_act(out_act, acc);
   }
 }
@@ -448,7 +456,7 @@ int make_map_f16(CUtensorMap* map, const void* base, long rows, long cols, int b
 
 struct Plan {
   int nl, F, n_out, L;
-  int u[GB_MAX_LAYERS], in[GB_MAX_LAYERS], kp_below[GB_MAX_LAYERS], kp[GB_MAX_LAYERS];
+  int u[GB_MAX_LAYERS], ur[GB_MAX_LAYERS], in[GB_MAX_LAYERS], kp_below[GB_MAX_LAYERS], kp[GB_MAX_LAYERS];  // u: padded to 64, ur / in: real widths
   long kofs[GB_MAX_LAYERS], dofs;
   // workspace offsets (bytes)
   size_t w_hi[GB_MAX_LAYERS], w_lo[GB_MAX_LAYERS], bias[GB_MAX_LAYERS], h_hi[GB_MAX_LAYERS][2], h_lo[GB_MAX_LAYERS][2], c[GB_MAX_LAYERS], xk, total;
@@ -463,19 +471,19 @@ void make_plan(const gb_lstmnet* net, int n_slots, long rows_pad, long x_rows, P
   int in = net->n_features;
   size_t ofs = 0;
   for (int l = 0; l < p->nl; ++l) {
-    const int u = net->units[l];
-    p->u[l] = u; p->in[l] = in;
+    const int ur = net->units[l], u = gb::round_up(ur, UB);
+    p->u[l] = u; p->ur[l] = ur; p->in[l] = in;
     p->kofs[l] = pofs;
-    pofs += 4L * u * (in + u + 1);
-    p->kp_below[l] = l == 0 ? 0 : gb::round_up(in, KC);
+    pofs += 4L * ur * (in + ur + 1);
+    p->kp_below[l] = l == 0 ? 0 : gb::round_up(in, UB);  // = the padded width of the layer below
     p->kp[l] = p->kp_below[l] + u;
     p->w_hi[l] = ofs; ofs = align256(ofs + (size_t)n_slots * 4 * u * p->kp[l] * sizeof(__half));
     p->w_lo[l] = ofs; ofs = align256(ofs + (size_t)n_slots * 4 * u * p->kp[l] * sizeof(__half));
     p->bias[l] = ofs; ofs = align256(ofs + (size_t)n_slots * 4 * u * sizeof(float));
-    in = u;
+    in = ur;
   }
   p->dofs = pofs;
-  p->xk = ofs; ofs = align256(ofs + (size_t)((x_rows + TILE - 1) / TILE * TILE) * 4 * net->units[0] * sizeof(float));
+  p->xk = ofs; ofs = align256(ofs + (size_t)((x_rows + TILE - 1) / TILE * TILE) * 4 * p->u[0] * sizeof(float));
   p->state_begin = ofs;
   for (int l = 0; l < p->nl; ++l) {
     const size_t hb = (size_t)rows_pad * p->u[l] * sizeof(__half);
@@ -495,8 +503,7 @@ extern "C" int gb_lstm_tc_supported(const gb_lstmnet* net) {
   GB_REQUIRE(net != nullptr, GB_E_ARG, "net is NULL");
   GB_REQUIRE(net->n_layers >= 1 && net->n_layers <= GB_MAX_LAYERS, GB_E_SHAPE, "n_layers=%d outside [1,%d]", net->n_layers, GB_MAX_LAYERS);
   for (int l = 0; l < net->n_layers; ++l)
-    GB_REQUIRE(net->units[l] >= UB && net->units[l] % UB == 0 && net->units[l] <= 512, GB_E_SHAPE,
-               "tcgen05 LSTM variant needs layer widths that are multiples of %d (<= 512), units[%d]=%d", UB, l, net->units[l]);
+    GB_REQUIRE(net->units[l] >= 1 && net->units[l] <= 512, GB_E_SHAPE, "tcgen05 LSTM variant covers layer widths 1..512, units[%d]=%d", l, net->units[l]);
   GB_REQUIRE(net->n_features >= 1 && net->n_features <= 512 && net->n_features_out >= 1 && net->n_features_out <= 512, GB_E_SHAPE, "bad feature counts");
   GB_REQUIRE(net->lookback >= 1, GB_E_ARG, "lookback=%d must be >= 1", net->lookback);
   return GB_OK;
@@ -529,11 +536,11 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
 
   // ---- operands that do not depend on the timestep
   for (int l = 0; l < p.nl; ++l)
-    lstm_tc_weights_kernel<<<dim3(64, n_slots), 256, 0, st>>>(params, pstride, p.kofs[l], p.in[l], p.u[l], p.kp_below[l], p.kp[l], l > 0,
+    lstm_tc_weights_kernel<<<dim3(64, n_slots), 256, 0, st>>>(params, pstride, p.kofs[l], p.in[l], p.ur[l], p.u[l], p.kp_below[l], p.kp[l], l > 0,
                                                                reinterpret_cast<__half*>(ws + p.w_hi[l]), reinterpret_cast<__half*>(ws + p.w_lo[l]),
                                                                reinterpret_cast<float*>(ws + p.bias[l]));
   const int xr_max = max_windows + p.L - 1;
-  lstm_tc_xk_kernel<<<dim3((xr_max + 31) / 32, 4 * p.u[0] / 64, n_jobs), 256, 0, st>>>(jobs, x, p.F, p.u[0], p.L, params, pstride,
+  lstm_tc_xk_kernel<<<dim3((xr_max + 31) / 32, 4 * p.u[0] / 64, n_jobs), 256, 0, st>>>(jobs, x, p.F, p.ur[0], p.u[0], p.L, params, pstride,
                                                                                        reinterpret_cast<float*>(ws + p.xk));
   GB_CUDA_CHECK(cudaMemsetAsync(ws + p.state_begin, 0, p.state_end - p.state_begin, st));
   GB_CUDA_CHECK(cudaGetLastError());
@@ -573,7 +580,7 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
   }
   const int top = p.nl - 1, fin = (p.L - 1) & 1;
   lstm_tc_head_kernel<<<dim3(tiles_per_job, n_jobs), TILE, 0, st>>>(jobs, tiles_per_job, reinterpret_cast<const __half*>(ws + p.h_hi[top][fin]),
-                                                                     reinterpret_cast<const __half*>(ws + p.h_lo[top][fin]), p.u[top], p.n_out, net->out_act,
+                                                                     reinterpret_cast<const __half*>(ws + p.h_lo[top][fin]), p.ur[top], p.u[top], p.n_out, net->out_act,
                                                                      params, pstride, p.dofs, out_model);
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;

@@ -209,7 +209,7 @@ size_t gb_lstm_workspace_bytes(const gb_lstmnet* net, int32_t n_jobs, int32_t ma
 int gb_lstm_infer(const gb_lstmnet* net, const float* params, const gb_job* jobs, int32_t n_jobs,
                   int32_t max_rows, const float* x, float* out_model, void* workspace, void* stream);
 
-/* ---- K3 on tcgen05: stacks whose layer widths are multiples of 64 (lstm_symmetric's 256/128/64).  One launch per
+/* ---- K3 on tcgen05 (layer widths 1..512, padded to multiples of 64 internally).  One launch per
  * (layer, timestep) advances every window of every job: [h_below,t | h_own,t-1] . [K; U]^T on the tensor cores
  * (FP16-pair split operands, fp32 accumulation in TMEM), LSTM cell in the epilogue, recurrent state in `workspace`
  * (gb_lstm_tc_workspace_bytes; x_rows = rows of the x array, n_slots = rows of params). */

@@ -341,7 +341,8 @@ def test_lstm_infer_matches_oracle(engine, torch, F, units, lookback):
 
 
 @pytest.mark.parametrize("F,units,lookback,rows,scale", [(16, [64, 64], 5, [140, 300], 1.0), (128, [256, 128, 64, 64, 128, 256], 20, [57, 190], 1.0),
-                                                          (7, [128], 9, [400], 1000.0)])
+                                                          (7, [128], 9, [400], 1000.0), (5, [7, 9, 3], 4, [50, 133], 1.0),
+                                                          (128, [107, 85, 64, 64, 85, 107], 12, [150], 1.0)])  # widths padded to 64 internally
 def test_lstm_infer_tcgen05_matches_oracle(engine, torch, F, units, lookback, rows, scale):
     """gb_lstm_infer_tc: FP16-pair split operands on the tensor cores, state in HBM, one launch per (layer, timestep).
     Jobs of different lengths (tiles with padding rows), machines sharing the launch, raw inputs of large magnitude (the
@@ -735,16 +736,14 @@ def test_error_paths_raise_like_the_reference(engine, torch):
     from oracle import keras_math as km
 
     dev = engine.cuda_device()
-    # LSTM: widths outside the tcgen05 kernel must be refused when that kernel is demanded, and served by the fp32 kernel otherwise
     spec = km.lstm_model_spec(5, 5, lookback_window=3, encoding_dim=(7,), encoding_func=("tanh",), decoding_dim=(7,), decoding_func=("tanh",))
     eng = engine.LSTMEngine(5, spec.units, spec.acts, 5, "linear", 3)
-    assert not eng.tc_supported
     params = eng.pack_params([km.init_lstm_weights(spec, np.random.default_rng(0))])
     x = torch.rand((20, 5), device=dev)
     jobs = engine.jobs_to_device(engine.make_jobs([0], [18], [0]), dev)
-    with pytest.raises(ValueError):
-        eng.infer(params, jobs, 1, 18, x, 18, variant=2)
     assert eng.infer(params, jobs, 1, 18, x, 18).shape == (18, 5)
+    with pytest.raises(ValueError):  # an unknown kernel variant is an argument error, not a fallback
+        eng.lib.gb_lstm_tc_supported(None) == 0 or _cabi.check(eng.lib.gb_lstm_tc_supported(None))
     with pytest.raises(ValueError):  # batches above 32 windows are not supported by gb_lstm_fit
         eng.fit(params, jobs, 1, 18, x, x, epochs=1, batch_size=64)
     # quantile: more rows than fit in shared memory
