@@ -1,7 +1,7 @@
 // K1+K4, variant 2: fused Dense-stack forward + anomaly score on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
 //
-// Covers 64-tag autoencoders with hidden widths <= 64 (feedforward_hourglass(64) = 64-53-43-32-32-43-53-64 is the
-// BASELINE workload).  The path is HBM-bound (1 548 algorithmic bytes and 30 236 FLOP per window => 128 TFLOP/s at
+// Covers autoencoders of 24..64 tags (multiples of 4; narrower rows ride in zero-padded columns that TMA fills) with hidden
+// widths <= 64 (feedforward_hourglass(64) = 64-53-43-32-32-43-53-64 is the BASELINE workload).  The path is HBM-bound (1 548 algorithmic bytes and 30 236 FLOP per window => 128 TFLOP/s at
 // the measured 6.58 TB/s): fp32 CUDA cores (74 TFLOP/s peak) cannot keep up, the tensor cores can.
 //
 // Numerics: 1e-4 parity with the float32 reference forbids plain TF32/FP16 (2^-11 per operand), so operands are split.
@@ -42,7 +42,7 @@ constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
 constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 rows x 32 fp32
-constexpr int W = 64;                  // feature width this kernel is specialised for
+constexpr int W = 64;                  // widest feature / hidden width; narrower tag counts T (multiples of 4) ride in zero-padded columns
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
 constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, SLOT_COLS = 224, COL_DX = 448, TMEM_COLS = 512;
@@ -52,6 +52,7 @@ constexpr uint32_t COL_A1 = COL_AHI, COL_A2 = COL_AHI + 32;
 // tile while the output warps are still busy with the previous pair (they drain slot 0's accumulator first)
 
 struct TcArgs {
+  int T;                     // tags per row of x / y / every per-tag output (row pitch); <= W, multiple of 4
   int n_layers, last_layer;  // layers actually evaluated: 0..last_layer (debug aid; == n_layers-1 in production)
   int K[MAXL], N[MAXL], Np[MAXL], n8[MAXL], k8[MAXL], k16[MAXL], act[MAXL];  // Np = N rounded up to 16 (MMA N), n8 = to 8 (columns evaluated)
   int whi_ofs[MAXL], wlo_ofs[MAXL], bias_ofs[MAXL];  // byte offsets into dynamic smem
@@ -402,8 +403,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       } else {
         for (int i = tid; i < a.param_bytes / 4; i += NTHREADS) scratch[i] = __ldg(P + i);
       }
-      const float v_scale = (tid < W && a.scale) ? __ldg(a.scale + (long)job.slot * W + tid) : 0.f;
-      const float v_thr = (tid < W && a.feat_thr) ? __ldg(a.feat_thr + (long)job.slot * W + tid) : 1.f;
+      const float v_scale = (tid < a.T && a.scale) ? __ldg(a.scale + (long)job.slot * a.T + tid) : 0.f;
+      const float v_thr = (tid < a.T && a.feat_thr) ? __ldg(a.feat_thr + (long)job.slot * a.T + tid) : 1.f;
       for (int i = tid; i < a.w_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
       __syncthreads();
       if (a.bulk_params) {
@@ -442,7 +443,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       float* vec = reinterpret_cast<float*>(smem + a.vec_ofs);  // [0,64): scale, [64,128): 1/feat_thr
       if (tid < W) {
         vec[tid] = v_scale;
-        vec[W + tid] = a.feat_thr ? 1.0f / v_thr : 0.f;
+        vec[W + tid] = (a.feat_thr && tid < a.T) ? 1.0f / v_thr : 0.f;
       }
       fence_proxy_async();  // generic-proxy writes above are read by the tensor core (async proxy)
     }
@@ -574,7 +575,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
       const float4 rt4 = *reinterpret_cast<const float4*>(vec + W + h * 32 + tc * 4);
       const float4 b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + a.bias_ofs[L - 1]) + h * 32 + tc * 4);
-      const float inv_w = 1.0f / (float)W;
+      const float inv_w = 1.0f / (float)a.T;
+      const bool in_cols = h * 32 + tc * 4 < a.T;  // this lane's four columns exist (T is a multiple of 4)
       const bool totals = has_y && (a.o_tots || a.o_totu || a.o_totconf);
 
       // x -> A operand of layer 0 of tile `tt` (slot tt & 1): these warps have the slack, the layer warps do not
@@ -634,9 +636,11 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
           if (y_smem) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yv.x), "=f"(yv.y), "=f"(yv.z), "=f"(yv.w) : "r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u));
+          if (!in_cols) yv = make_float4(0.f, 0.f, 0.f, 0.f);  // zero-padded columns (T < 64): model output is 0 there too
           yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
-          const bool live = wrow0 + r < nrows && !(a.flags & FLAG_NO_STORES);
-          const long g = (grow0 + wrow0 + r) * (long)W + h * 32 + tc * 4;
+          if (!in_cols) yh = make_float4(0.f, 0.f, 0.f, 0.f);     // columns beyond T: the accumulator holds stale values there
+          const bool live = wrow0 + r < nrows && in_cols && !(a.flags & FLAG_NO_STORES);
+          const long g = (grow0 + wrow0 + r) * (long)a.T + h * 32 + tc * 4;
           if (live) *reinterpret_cast<float4*>(a.o_model + g) = yh;
           ss[i] = 0.f; su[i] = 0.f;
           if (has_y) {
@@ -690,7 +694,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + tr;
-              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)W + h * 32 + tc * 4;
+              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)a.T + (in_cols ? h * 32 + tc * 4 : 0);
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -700,7 +704,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
           for (int i = 0; i < 8; ++i) {  // y rows of the first tile -> registers, requested before its accumulator is ready
             const int r = min(q * 32 + i * 4 + tr, nrows - 1);
-            yt[i] = __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)W + h * 32) + tc);
+            yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)a.T + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed both slots their next tiles
@@ -763,11 +767,11 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // [rows][64] fp32 row-major viewed as a 2-D tensor; box = 32 columns x box_rows rows, SWIZZLE_128B
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int T) {
   EncodeTiledFn fn = get_encode_fn();
   GB_REQUIRE(fn != nullptr, GB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)(rows > 0 ? rows : 1)};
-  cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(float)};
+  cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)(rows > 0 ? rows : 1)};  // columns T..63 of a box are out of bounds: TMA fills zeros
+  cuuint64_t strides[1] = {(cuuint64_t)T * sizeof(float)};
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -791,8 +795,8 @@ extern "C" int gb_debug_set_trace(void* dev_buf, int capacity) {
 extern "C" int gb_ffae_tc_supported(const gb_ffnet* net) {
   if (gb::validate_ffnet(net) != GB_OK) return GB_E_SHAPE;
   const int L = net->n_layers;
-  if (L > MAXL || net->dims[0] != W || net->dims[L] != W) {
-    gb::set_error("tcgen05 variant covers 64-tag autoencoders with at most %d layers", MAXL);
+  if (L > MAXL || net->dims[0] != net->dims[L] || net->dims[0] > W || net->dims[0] < 24 || (net->dims[0] & 3)) {
+    gb::set_error("tcgen05 variant covers autoencoders of 24..%d tags (a multiple of 4) with at most %d layers", W, MAXL);
     return GB_E_SHAPE;
   }
   for (int l = 1; l < L; ++l)
@@ -820,6 +824,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   TcArgs a{};
   const int L = net->n_layers;
   a.n_layers = L;
+  a.T = net->dims[0];
   const int dbg_last = (flags >> 8) & 0xff;
   a.last_layer = (dbg_last > 0 && dbg_last <= L) ? dbg_last - 1 : L - 1;
   a.flags = flags & 0xff;
@@ -872,7 +877,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   if (const char* e = getenv("GB_TC_TRACE_HEAD")) a.trace_head = atoi(e);
 
   CUtensorMap mx;
-  if ((rc = make_map(&mx, x, n_x_rows, TILE)) != GB_OK) return rc;
+  if ((rc = make_map(&mx, x, n_x_rows, TILE, a.T)) != GB_OK) return rc;
 
   const long g_total = (long)n_jobs * tiles_per_job;
   const int grid = (int)(g_total < sms ? g_total : sms);

@@ -66,7 +66,7 @@ def run_infer(engine, torch, spec, weights_per_slot, X, y, jobs_h, scale=None, f
 
 
 # ------------------------------------------------------------------------------------------------ K1 + K4
-@pytest.mark.parametrize("T,variant", [(4, 1), (8, 1), (10, 1), (64, 1), (64, 2), (128, 1), (4, 3), (8, 3), (10, 3), (16, 3), (8, 0)])  # 3: row-per-thread kernel
+@pytest.mark.parametrize("T,variant", [(4, 1), (8, 1), (10, 1), (64, 1), (64, 2), (128, 1), (4, 3), (8, 3), (10, 3), (16, 3), (8, 0), (48, 2), (36, 2), (24, 2), (60, 0)])  # 3: row-per-thread kernel; 2 with T < 64: zero-padded columns
 def test_ffae_infer_score_matches_oracle(engine, torch, T, variant):
     """variant 1 = fp32 CUDA-core kernel (any architecture), variant 2 = tcgen05 split-precision kernel (64-tag nets)."""
     from oracle import anomaly_math as am
