@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgordo_b200.so")
 
 GB_MAX_LAYERS = 16
-GB_MAX_WIDTH = 128
+GB_MAX_WIDTH = 256
 ACT_CODES = {"linear": 0, None: 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 
 EXPORTS = (

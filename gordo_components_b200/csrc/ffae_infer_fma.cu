@@ -16,7 +16,6 @@
 
 namespace {
 
-constexpr int ROWS = 128;
 constexpr int THREADS = 256;
 constexpr int NWARPS = THREADS / 32;
 
@@ -46,7 +45,11 @@ __device__ __forceinline__ void stage_layer(float* dst, const float* P, const Ar
   for (int n = tid; n < Np; n += THREADS) dst[Kp * Np + n] = n < N ? __ldg(bg + n) : 0.f;
 }
 
+// RT row groups of 32 per thread: tiles of 128 rows (RT = 4) for the usual stacks, 64 / 32 rows when wide layers (up to 256: the
+// defaults of feedforward_model / feedforward_symmetric) leave less shared memory for the activation buffers
+template <int RT>
 __global__ void __launch_bounds__(THREADS) ffae_infer_fma_kernel(const Args a) {
+  constexpr int ROWS = 32 * RT;
   extern __shared__ __align__(16) float smem[];
   float* sW = smem;
   float* buf0 = sW + a.wfloats;
@@ -106,21 +109,21 @@ __global__ void __launch_bounds__(THREADS) ffae_infer_fma_kernel(const Args a) {
       for (int task = warp; task < (Np >> 2); task += NWARPS) {
         const int n0 = task << 2;
         const float4 b4 = *reinterpret_cast<const float4*>(bl + n0);
-        float4 acc[4];
+        float4 acc[RT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = b4;
+        for (int i = 0; i < RT; ++i) acc[i] = b4;
         const float* arow = in + lane * pitch;
         const float* wcol = Wl + n0;
         for (int k = 0; k < Kp; k += 4) {
-          float4 av[4];
+          float4 av[RT];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(arow + i * 32 * pitch + k);
+          for (int i = 0; i < RT; ++i) av[i] = *reinterpret_cast<const float4*>(arow + i * 32 * pitch + k);
           const float4 w0 = *reinterpret_cast<const float4*>(wcol + (k + 0) * Np);
           const float4 w1 = *reinterpret_cast<const float4*>(wcol + (k + 1) * Np);
           const float4 w2 = *reinterpret_cast<const float4*>(wcol + (k + 2) * Np);
           const float4 w3 = *reinterpret_cast<const float4*>(wcol + (k + 3) * Np);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < RT; ++i) {
             acc[i].x = fmaf(av[i].x, w0.x, acc[i].x); acc[i].y = fmaf(av[i].x, w0.y, acc[i].y);
             acc[i].z = fmaf(av[i].x, w0.z, acc[i].z); acc[i].w = fmaf(av[i].x, w0.w, acc[i].w);
             acc[i].x = fmaf(av[i].y, w1.x, acc[i].x); acc[i].y = fmaf(av[i].y, w1.y, acc[i].y);
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(THREADS) ffae_infer_fma_kernel(const Args a) {
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RT; ++i) {
           float4 o;
           o.x = gb::apply_act(act, acc[i].x); o.y = gb::apply_act(act, acc[i].y);
           o.z = gb::apply_act(act, acc[i].z); o.w = gb::apply_act(act, acc[i].w);
@@ -249,12 +252,19 @@ extern "C" int gb_ffae_infer_score_fma(const gb_ffnet* net, const float* params,
   a.n_out = net->dims[net->n_layers];
   int max_layer = 0;
   for (int l = 0; l < net->n_layers; ++l) max_layer = max(max_layer, a.im.kp[l] * a.im.np[l] + a.im.np[l]);
-  const size_t act_bytes = (size_t)(2 * ROWS * a.pitch + 2 * ROWS) * sizeof(float);
   const size_t budget = 220 * 1024;
-  a.resident = ((size_t)a.im.total * sizeof(float) + act_bytes) <= budget;
-  a.wfloats = gb::round_up(a.resident ? a.im.total : max_layer, 4);
-  const size_t smem = (size_t)a.wfloats * sizeof(float) + act_bytes;
+  int rt = 4;
+  size_t smem = 0;
+  for (;; rt >>= 1) {  // the largest row tile whose activation buffers fit next to the (resident or per-layer staged) weights
+    const int rows = 32 * rt;
+    const size_t act_bytes = (size_t)(2 * rows * a.pitch + 2 * rows) * sizeof(float);
+    a.resident = ((size_t)a.im.total * sizeof(float) + act_bytes) <= budget;
+    a.wfloats = gb::round_up(a.resident ? a.im.total : max_layer, 4);
+    smem = (size_t)a.wfloats * sizeof(float) + act_bytes;
+    if (smem <= 227 * 1024 || rt == 1) break;
+  }
   GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory", smem);
+  const int ROWS = 32 * rt;
   a.pstride = (long)gb_ffnet_param_stride(net);
   a.params = params; a.jobs = jobs; a.x = x; a.y = y; a.scale = scale; a.feat_thr = feat_thr; a.agg_thr = agg_thr;
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_tots = out_total_scaled;
@@ -270,8 +280,13 @@ extern "C" int gb_ffae_infer_score_fma(const gb_ffnet* net, const float* params,
   a.rows_per_chunk = tiles_per_chunk * ROWS;
   const int chunks = (tiles_per_job + tiles_per_chunk - 1) / tiles_per_chunk;
   GB_REQUIRE(n_jobs <= 65535, GB_E_ARG, "n_jobs=%d exceeds 65535 per launch", n_jobs);
-  GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_infer_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ffae_infer_fma_kernel<<<dim3(chunks, n_jobs), THREADS, smem, (cudaStream_t)stream>>>(a);
+  auto launch = [&](auto kern) -> int {
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(chunks, n_jobs), THREADS, smem, (cudaStream_t)stream>>>(a);
+    return GB_OK;
+  };
+  int rc = rt == 4 ? launch(ffae_infer_fma_kernel<4>) : rt == 2 ? launch(ffae_infer_fma_kernel<2>) : launch(ffae_infer_fma_kernel<1>);
+  if (rc != GB_OK) return rc;
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }

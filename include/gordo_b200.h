@@ -34,7 +34,7 @@ extern "C" {
 
 #define GB_ABI_VERSION 1
 #define GB_MAX_LAYERS 16
-#define GB_MAX_WIDTH 128 /* widest layer / feature count the resident-weight kernels accept */
+#define GB_MAX_WIDTH 256 /* widest layer / feature count (the feedforward_model / feedforward_symmetric defaults are 256-128-64) */
 
 typedef enum gb_status {
   GB_OK = 0,

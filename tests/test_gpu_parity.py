@@ -97,6 +97,39 @@ def test_ffae_infer_score_matches_oracle(engine, torch, T, variant):
         close(got["total-anomaly-confidence"][sl], want["total-anomaly-confidence"], float(scales[m].max()) * np.sqrt(want["total-anomaly-scaled"].max()) / float(agg[m]), name="total-confidence")
 
 
+@pytest.mark.parametrize("T", [10, 64])
+def test_wide_symmetric_stack_defaults(engine, torch, T):
+    """feedforward_symmetric / feedforward_model default to 256-128-64 encoders (feedforward_autoencoder.py:19,111): wider than the
+    resident-weight budget, so inference stages layer by layer with a smaller row tile and fit keeps the weight image in L2."""
+    from gordo_components_b200.machine.model.models import KerasAutoEncoder
+    from oracle import keras_math as km
+
+    spec = km.ff_symmetric_spec(T)
+    assert max(spec.dims) == 256
+    rng = np.random.default_rng(T)
+    w = km.init_ff_weights(spec, rng)
+    w = [(W, rng.uniform(-0.1, 0.1, b.shape).astype(np.float32)) for W, b in w]
+    R = 300
+    X = rng.random((R, T)).astype(np.float32)
+    got = run_infer(engine, torch, spec, [w], X, X, engine.uniform_jobs(1, R), np.ones((1, T), np.float32), np.ones((1, T), np.float32), np.ones(1, np.float32))
+    close(got["model-output"], km.ff_forward(spec, w, X, np.float64), 1.0, name="256-wide model output")
+    # fit: same weights + visiting order => same trained weights as the oracle
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    perm = np.stack([[np.random.default_rng(e).permutation(R) for e in range(2)]]).astype(np.int32)
+    params = eng.pack_params([w])
+    xd = torch.from_numpy(X).to(dev)
+    loss, acc, _ = eng.fit(params, engine.jobs_to_device(engine.uniform_jobs(1, R), dev), 1, R, xd, xd.clone(), epochs=2, batch_size=32, perm=torch.from_numpy(perm).to(dev))
+    w_ref, hist, _ = km.ff_fit(spec, w, X, X, epochs=2, batch_size=32, perms=list(perm[0]))
+    for (Wg, bg), (Wr, br) in zip(eng.unpack_params(params)[0], w_ref):
+        close(Wg, Wr, mag=float(np.abs(Wr).max()), name="256-wide trained weights")
+    close(loss[0].cpu().numpy(), np.array(hist["loss"]), mag=0.0, rtol=5e-4, name="loss history")
+    # and through the estimator with the factory's defaults
+    np.random.seed(0)
+    m = KerasAutoEncoder(kind="feedforward_symmetric", epochs=2).fit(X, X)
+    assert m.predict(X).shape == (R, T) and m.get_metadata()["history"]["loss"][1] < m.get_metadata()["history"]["loss"][0]
+
+
 def test_ffae_jobs_slots_and_row_offsets(engine, torch):
     """Jobs may share a slot, read any row range and write anywhere; empty jobs are no-ops; predict-only mode."""
     from oracle import keras_math as km
