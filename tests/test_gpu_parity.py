@@ -130,6 +130,32 @@ def test_wide_symmetric_stack_defaults(engine, torch, T):
     assert m.predict(X).shape == (R, T) and m.get_metadata()["history"]["loss"][1] < m.get_metadata()["history"]["loss"][0]
 
 
+@pytest.mark.parametrize("cls_name,kind,kw", [
+    ("KerasAutoEncoder", "feedforward_model", {}), ("KerasAutoEncoder", "feedforward_symmetric", {}), ("KerasAutoEncoder", "feedforward_hourglass", {}),
+    ("KerasLSTMAutoEncoder", "lstm_model", {"lookback_window": 3}), ("KerasLSTMAutoEncoder", "lstm_symmetric", {"lookback_window": 3}),
+    ("KerasLSTMForecast", "lstm_hourglass", {"lookback_window": 3}), ("KerasLSTMAutoEncoder", "lstm_symmetric", {})])
+def test_every_registered_factory_with_its_defaults(engine, torch, cls_name, kind, kw):
+    """Every `kind` the reference registers (register.py:10-75; factories' default dims are 256-128-64) builds, trains and
+    predicts with its default arguments; the trained weights reproduce the prediction in the oracle."""
+    from gordo_components_b200.machine.model import models
+    from oracle import keras_math as km
+
+    np.random.seed(2)
+    X = np.random.random((60, 5)).astype(np.float32)
+    m = getattr(models, cls_name)(kind=kind, epochs=1, **kw).fit(X, X)
+    out = m.predict(X)
+    L = kw.get("lookback_window", 1)
+    assert out.shape == (60 - (L - 1 + m.lookahead if cls_name != "KerasAutoEncoder" else 0), 5) and np.isfinite(out).all()
+    spec = m.model.spec
+    if cls_name == "KerasAutoEncoder":
+        want = km.ff_forward(km.FFSpec(list(spec.dims), list(spec.acts), list(spec.l1)), m.model.weights, X, np.float64)
+    else:
+        ospec = km.LSTMSpec(spec.n_features, list(spec.lstm_units), list(spec.acts), spec.n_features_out, spec.out_func, spec.lookback_window)
+        want = km.lstm_predict(ospec, m.model.weights, X, lookahead=m.lookahead, dtype=np.float64)
+    close(out, want, 1.0, rtol=2e-4, name=f"{kind} defaults")
+    assert "loss" in m.get_metadata()["history"]
+
+
 def test_ffae_jobs_slots_and_row_offsets(engine, torch):
     """Jobs may share a slot, read any row range and write anywhere; empty jobs are no-ops; predict-only mode."""
     from oracle import keras_math as km
