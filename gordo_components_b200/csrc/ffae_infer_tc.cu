@@ -302,7 +302,8 @@ __device__ __forceinline__ void hidden_epilogue_pair(uint32_t slot_lane, int c0,
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int NE>
+// FULL: 64 tags (the row pitch and every column guard fold to constants -- the BASELINE workload); otherwise T < 64 rides in padded columns
+template <int NE, bool FULL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap map_x) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -327,6 +328,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t bars = sbase + a.bar_ofs;
   const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64, BW = 80;  // BW: bulk copy of a slot's parameter vector
   const bool has_y = a.y != nullptr;
+  const int TP = FULL ? W : a.T;  // tags per row = row pitch of x / y / per-tag outputs
   const int L = a.last_layer + 1;
 
   if (tid == 0) {
@@ -403,8 +405,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       } else {
         for (int i = tid; i < a.param_bytes / 4; i += NTHREADS) scratch[i] = __ldg(P + i);
       }
-      const float v_scale = (tid < a.T && a.scale) ? __ldg(a.scale + (long)job.slot * a.T + tid) : 0.f;
-      const float v_thr = (tid < a.T && a.feat_thr) ? __ldg(a.feat_thr + (long)job.slot * a.T + tid) : 1.f;
+      const float v_scale = (tid < TP && a.scale) ? __ldg(a.scale + (long)job.slot * TP + tid) : 0.f;
+      const float v_thr = (tid < TP && a.feat_thr) ? __ldg(a.feat_thr + (long)job.slot * TP + tid) : 1.f;
       for (int i = tid; i < a.w_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
       __syncthreads();
       if (a.bulk_params) {
@@ -443,7 +445,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       float* vec = reinterpret_cast<float*>(smem + a.vec_ofs);  // [0,64): scale, [64,128): 1/feat_thr
       if (tid < W) {
         vec[tid] = v_scale;
-        vec[W + tid] = (a.feat_thr && tid < a.T) ? 1.0f / v_thr : 0.f;
+        vec[W + tid] = (a.feat_thr && tid < TP) ? 1.0f / v_thr : 0.f;
       }
       fence_proxy_async();  // generic-proxy writes above are read by the tensor core (async proxy)
     }
@@ -575,8 +577,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
       const float4 rt4 = *reinterpret_cast<const float4*>(vec + W + h * 32 + tc * 4);
       const float4 b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + a.bias_ofs[L - 1]) + h * 32 + tc * 4);
-      const float inv_w = 1.0f / (float)a.T;
-      const bool in_cols = h * 32 + tc * 4 < a.T;  // this lane's four columns exist (T is a multiple of 4)
+      const float inv_w = 1.0f / (float)TP;
+      const bool in_cols = FULL || h * 32 + tc * 4 < TP;  // this lane's four columns exist (T is a multiple of 4)
       const bool totals = has_y && (a.o_tots || a.o_totu || a.o_totconf);
 
       // x -> A operand of layer 0 of tile `tt` (slot tt & 1): these warps have the slack, the layer warps do not
@@ -640,7 +642,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
           if (!in_cols) yh = make_float4(0.f, 0.f, 0.f, 0.f);     // columns beyond T: the accumulator holds stale values there
           const bool live = wrow0 + r < nrows && in_cols && !(a.flags & FLAG_NO_STORES);
-          const long g = (grow0 + wrow0 + r) * (long)a.T + h * 32 + tc * 4;
+          const long g = (grow0 + wrow0 + r) * (long)TP + h * 32 + tc * 4;
           if (live) *reinterpret_cast<float4*>(a.o_model + g) = yh;
           ss[i] = 0.f; su[i] = 0.f;
           if (has_y) {
@@ -694,7 +696,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + tr;
-              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)a.T + (in_cols ? h * 32 + tc * 4 : 0);
+              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)TP + (in_cols ? h * 32 + tc * 4 : 0);
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -704,7 +706,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
           for (int i = 0; i < 8; ++i) {  // y rows of the first tile -> registers, requested before its accumulator is ready
             const int r = min(q * 32 + i * 4 + tr, nrows - 1);
-            yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)a.T + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed both slots their next tiles
@@ -886,7 +888,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
     kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx);
     return GB_OK;
   };
-  rc = launch(ffae_tc_kernel<DEFAULT_NE>);  // NE = 2..4 (part of the tanh evaluations on the FMA pipe) measured 1-5 % slower
+  rc = a.T == W ? launch(ffae_tc_kernel<DEFAULT_NE, true>) : launch(ffae_tc_kernel<DEFAULT_NE, false>);  // NE = 2..4 (part of the tanh evaluations on the FMA pipe) measured 1-5 % slower
   if (rc != GB_OK) return rc;
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
