@@ -207,6 +207,38 @@ class FleetBuild:
         return det
 
 
+def dump_fleet(fb: "FleetBuild", root: str, names: Sequence[str], tags: Optional[Sequence[Sequence[str]]] = None,
+               metadata: Optional[Dict[str, dict]] = None, info: Optional[dict] = None) -> List[str]:
+    """
+    Writes every machine of a ``FleetBuild`` in the layout ``gordo.serializer.dump`` produces and ``gordo.serializer.load`` /
+    ``load_metadata`` / gordo.server read (gordo/serializer/serializer.py:149-196): ``<root>/<name>/model.pkl`` (the pickled
+    detector), ``metadata.json`` (user metadata + the model's own ``get_metadata()`` under ``metadata.build_metadata.model.
+    model_meta`` -- where ModelBuilder puts it, gordo/builder/build_model.py:291-321) and, when given, ``info.json``.
+    Returns the directories written.
+    """
+    import json
+    import os
+    import pickle
+
+    out = []
+    for m, name in enumerate(names):
+        det = fb.detector(m, tags=None if tags is None else tags[m])
+        dest = os.path.join(root, name)
+        os.makedirs(dest, exist_ok=True)
+        with open(os.path.join(dest, "model.pkl"), "wb") as f:
+            pickle.dump(det, f)
+        meta = dict((metadata or {}).get(name, {}))
+        meta.setdefault("name", name)
+        meta.setdefault("metadata", {}).setdefault("build_metadata", {}).setdefault("model", {})["model_meta"] = det.get_metadata()
+        with open(os.path.join(dest, "metadata.json"), "w") as f:
+            json.dump(meta, f, default=str)
+        if info is not None:
+            with open(os.path.join(dest, "info.json"), "w") as f:
+                json.dump(info, f, default=str)
+        out.append(dest)
+    return out
+
+
 def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_size: int = 32, n_splits: int = 3, seed: int = 0,
                 adam: Optional[Dict[str, float]] = None, shuffle: bool = True, generator=None) -> FleetBuild:
     """

@@ -900,9 +900,22 @@ def test_fleet_build_matches_per_machine_oracle(engine, torch):
     sc, mn = am.minmax_fit(Xs[2])
     want = am.anomaly_arrays(pred, Xs[2], sc, mn, det.feature_thresholds_.values, det.aggregate_threshold_)
     close(frame["total-anomaly-confidence"].values.ravel(), want["total-anomaly-confidence"], float(sc.max()) * np.sqrt(want["total-anomaly-scaled"].max()) / det.aggregate_threshold_, name="confidence")
+    import json
     import pickle
+    import tempfile
 
     pickle.loads(pickle.dumps(det)).anomaly(frame_x, frame_x)
+    # gordo.serializer layout: <root>/<machine>/model.pkl + metadata.json (+ info.json), loadable with plain pickle
+    with tempfile.TemporaryDirectory() as root:
+        names = [f"machine-{m}" for m in range(M)]
+        dirs = fleet.dump_fleet(fb, root, names, tags=[[f"tag-{i}" for i in range(T)]] * M, info={"checksum": "abc"})
+        assert [os.path.basename(d) for d in dirs] == names
+        with open(os.path.join(dirs[2], "model.pkl"), "rb") as f:
+            loaded = pickle.load(f)
+        np.testing.assert_array_equal(loaded.anomaly(frame_x, frame_x)["model-output"].values, frame["model-output"].values)
+        meta = json.load(open(os.path.join(dirs[2], "metadata.json")))
+        assert meta["name"] == "machine-2" and "feature-thresholds" in meta["metadata"]["build_metadata"]["model"]["model_meta"]
+        assert json.load(open(os.path.join(dirs[2], "info.json"))) == {"checksum": "abc"}
 
 
 # ------------------------------------------------------------------------------------------------ BASELINE-size properties
