@@ -156,6 +156,36 @@ def test_every_registered_factory_with_its_defaults(engine, torch, cls_name, kin
     assert "loss" in m.get_metadata()["history"]
 
 
+def test_tc_work_split_many_ragged_jobs(engine, torch):
+    """More jobs than SMs with ragged lengths (whole-job waves + a split tail, empty tiles, jobs shorter than a tile): the tcgen05
+    kernel against the generic fp32 kernel (itself checked against the oracle above) on every output."""
+    from gordo_components_b200 import fleet
+    from oracle import keras_math as km
+
+    spec = km.ff_hourglass_spec(64)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    rng = np.random.default_rng(11)
+    M = 333
+    n_rows = rng.integers(1, 700, size=M)
+    n_rows[[5, 77, 200]] = [1, 128, 129]
+    x_rows = np.concatenate([[0], np.cumsum(n_rows)[:-1]])
+    slots = rng.permutation(M)
+    jobs = engine.jobs_to_device(engine.make_jobs(slots, n_rows, x_rows), dev)
+    g = torch.Generator(device=dev).manual_seed(4)
+    total = int(n_rows.sum())
+    x = torch.rand((total, 64), generator=g, device=dev)
+    y = x + 0.05 * torch.randn((total, 64), generator=g, device=dev)
+    params = fleet.random_glorot_params(eng, M, g)
+    scale = torch.rand((M, 64), generator=g, device=dev) + 0.5
+    feat = torch.rand((M, 64), generator=g, device=dev) + 0.5
+    agg = torch.rand((M,), generator=g, device=dev) + 0.5
+    a = eng.infer_score(params, jobs, M, int(n_rows.max()), x, y, scale, feat, agg, variant=2)
+    b = eng.infer_score(params, jobs, M, int(n_rows.max()), x, y, scale, feat, agg, variant=1)
+    for k in b:
+        close(a[k].cpu().numpy(), b[k].cpu().numpy(), mag=float(b[k].abs().max()), name=f"tcgen05 vs fp32: {k}")
+
+
 def test_ffae_jobs_slots_and_row_offsets(engine, torch):
     """Jobs may share a slot, read any row range and write anywhere; empty jobs are no-ops; predict-only mode."""
     from oracle import keras_math as km
