@@ -643,17 +643,17 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           if (!in_cols) yh = make_float4(0.f, 0.f, 0.f, 0.f);     // columns beyond T: the accumulator holds stale values there
           const bool live = wrow0 + r < nrows && in_cols && !(a.flags & FLAG_NO_STORES);
           const long g = (grow0 + wrow0 + r) * (long)TP + h * 32 + tc * 4;
-          if (live) *reinterpret_cast<float4*>(a.o_model + g) = yh;
+          if (live) __stcs(reinterpret_cast<float4*>(a.o_model + g), yh);  // written once, never re-read by this kernel: streaming stores
           ss[i] = 0.f; su[i] = 0.f;
           if (has_y) {
             float4 d, e;
             d.x = fabsf(yh.x - yv.x); d.y = fabsf(yh.y - yv.y); d.z = fabsf(yh.z - yv.z); d.w = fabsf(yh.w - yv.w);
             su[i] = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-            if (live && a.o_tu) *reinterpret_cast<float4*>(a.o_tu + g) = d;
+            if (live && a.o_tu) __stcs(reinterpret_cast<float4*>(a.o_tu + g), d);
             e.x = d.x * sc4.x; e.y = d.y * sc4.y; e.z = d.z * sc4.z; e.w = d.w * sc4.w;
             ss[i] = e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
-            if (live && a.o_ts) *reinterpret_cast<float4*>(a.o_ts + g) = e;
-            if (live && a.o_conf) *reinterpret_cast<float4*>(a.o_conf + g) = make_float4(d.x * rt4.x, d.y * rt4.y, d.z * rt4.z, d.w * rt4.w);
+            if (live && a.o_ts) __stcs(reinterpret_cast<float4*>(a.o_ts + g), e);
+            if (live && a.o_conf) __stcs(reinterpret_cast<float4*>(a.o_conf + g), make_float4(d.x * rt4.x, d.y * rt4.y, d.z * rt4.z, d.w * rt4.w));
           }
         }
         __syncwarp();  // staging box reusable
