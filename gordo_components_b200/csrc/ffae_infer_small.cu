@@ -56,7 +56,7 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int T, const fl
   if ((T & 3) == 0) {
 #pragma unroll
     for (int c = 0; c < W / 4; ++c)
-      if (4 * c < T) reinterpret_cast<float4*>(p)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      if (4 * c < T) __stcs(reinterpret_cast<float4*>(p) + c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));  // streaming: written once
   } else {
 #pragma unroll
     for (int c = 0; c < W; ++c)
