@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 
 T = 64
 BYTES_PER_WINDOW = 4 * T + 4 * T + 4 * 4 * T + 12  # read x, y; write model-output, 2 tag-anomaly blocks, confidence; 3 row scalars
-NCU_DRAM_BYTES_PER_WINDOW = {"tcgen05": (1.563999e9 + 3.071377e9) / 3.0e6, "fma": (1.037003e9 + 2.019607e9) / 2.0e6}
+NCU_DRAM_BYTES_PER_WINDOW = {"tcgen05": (1.564020e9 + 3.051605e9) / 3.0e6, "fma": (1.037003e9 + 2.019607e9) / 2.0e6}
 METRIC = "anomaly windows/sec (64-tag feedforward_hourglass AE, 1k machines x 10k rows per GPU, fused predict+score)"
 
 
