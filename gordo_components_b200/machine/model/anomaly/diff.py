@@ -26,6 +26,7 @@ from sklearn.model_selection import cross_validate as sk_cross_validate
 from sklearn.pipeline import Pipeline
 from sklearn.preprocessing import MinMaxScaler
 from sklearn.utils import shuffle as sk_shuffle
+from sklearn.utils.validation import check_is_fitted
 
 from .. import utils as model_utils
 from ..base import GordoBase
@@ -275,8 +276,8 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             X_test = X.iloc[test_idxs] if isinstance(X, pd.DataFrame) else X[test_idxs]
             y_test = y.iloc[test_idxs] if isinstance(y, pd.DataFrame) else y[test_idxs]
             try:
-                fold.scaler.transform(_values(y_test)[:1])
-            except (NotFittedError, ValueError):
+                check_is_fitted(fold.scaler)
+            except NotFittedError:
                 fold.scaler.fit(y_test)
             res = self._score(fold, X_test, y_test, fold.scaler, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
             n = len(res["model-output"])
