@@ -170,6 +170,46 @@ __global__ void __launch_bounds__(THREADS) anomaly_score_kernel(const gb_job* jo
   }
 }
 
+// ---------------------------------------------------------------- column moments of one CV fold (build_model.py:378-446)
+// The builder's cross-validation metrics (explained variance, r2, MSE, MAE: per tag and averaged) are all functions of five
+// per-column sums over the fold's test rows.  out[job][q][j] (double), with e = yhat - y and y0 = the job's first target row
+// (a shift that keeps the second moment of y well conditioned):  q=0 sum e, 1 sum e^2, 2 sum |e|, 3 sum (y-y0), 4 sum (y-y0)^2.
+// One CTA per job and a fixed summation order: the result does not depend on the launch.
+__global__ void __launch_bounds__(THREADS) cv_moments_kernel(const gb_job* jobs, const float* yhat, const float* y, int n_out,
+                                                              double* out) {
+  __shared__ double s_acc[NWARPS][5][32];
+  const gb_job job = jobs[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* yb = y + job.x_row * (long)n_out;
+  const float* pb = yhat + job.out_row * (long)n_out;
+  double* o = out + (long)blockIdx.x * 5 * n_out;
+  for (int j0 = 0; j0 < n_out; j0 += 32) {
+    const int j = j0 + lane;
+    double a0 = 0., a1 = 0., a2 = 0., a3 = 0., a4 = 0.;
+    if (j < n_out && job.n_rows > 0) {
+      const double y0 = (double)__ldg(yb + j);
+      for (int r = warp; r < job.n_rows; r += NWARPS) {
+        const double yv = (double)__ldg(yb + (long)r * n_out + j);
+        const double e = (double)__ldg(pb + (long)r * n_out + j) - yv;
+        const double c = yv - y0;
+        a0 += e; a1 += e * e; a2 += fabs(e); a3 += c; a4 += c * c;
+      }
+    }
+    s_acc[warp][0][lane] = a0; s_acc[warp][1][lane] = a1; s_acc[warp][2][lane] = a2; s_acc[warp][3][lane] = a3; s_acc[warp][4][lane] = a4;
+    __syncthreads();
+    if (threadIdx.x < 5 * 32) {
+      const int q = threadIdx.x >> 5;
+      if (j < n_out) {
+        double t = s_acc[0][q][lane];
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) t += s_acc[w][q][lane];
+        o[q * n_out + j] = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -231,6 +271,17 @@ int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const fl
     if (chunks) rollmin_max_kernel<<<dim3(chunks, n_jobs), THREADS, 0, st>>>(jobs, total_scaled, 1, window, agg_thr);
     rollmax_finalize_kernel<<<n_jobs, 32, 0, st>>>(jobs, 1, agg_thr);
   }
+  GB_CUDA_CHECK(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_cv_moments(const gb_job* jobs, int32_t n_jobs, const float* yhat, const float* y, int32_t n_out, double* out,
+                  void* stream) {
+  GB_REQUIRE(jobs && yhat && y && out, GB_E_ARG, "jobs/yhat/y/out must be non-NULL");
+  GB_REQUIRE(n_out >= 1, GB_E_SHAPE, "n_out=%d must be >= 1", n_out);
+  GB_REQUIRE(n_jobs >= 0, GB_E_ARG, "bad n_jobs");
+  if (n_jobs == 0) return GB_OK;
+  cv_moments_kernel<<<n_jobs, THREADS, 0, (cudaStream_t)stream>>>(jobs, yhat, y, n_out, out);
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }

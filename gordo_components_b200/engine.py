@@ -219,6 +219,16 @@ def thresholds(jobs_dev, n_jobs, max_rows, tag_unscaled, total_scaled, n_out, n_
     return feat, agg
 
 
+def cv_moments(jobs_dev, n_jobs, yhat, y, n_out):
+    """Per job and column: sums of e, e^2, |e|, (y-y0), (y-y0)^2 over the job's rows (e = yhat - y): [n_jobs, 5, n_out] float64."""
+    torch = _torch()
+    lib = _cabi.load_library()
+    out = torch.zeros((int(n_jobs), 5, int(n_out)), dtype=torch.float64, device=yhat.device)
+    p = _cabi.ptr
+    _cabi.check(lib.gb_cv_moments(p(jobs_dev), int(n_jobs), p(yhat), p(y), int(n_out), p(out), _stream_ptr()))
+    return out
+
+
 def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_thr=None, agg_thr=None, want=SCORE_KEYS, device=None):
     """Anomaly columns for predictions that already exist (base estimators that are not ours, LSTM outputs)."""
     torch = _torch()

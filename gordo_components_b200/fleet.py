@@ -162,15 +162,22 @@ class FleetBuild:
     machine -- final weights, target scaler, CV thresholds (per fold and final), loss histories -- for all machines at once.
     """
 
-    def __init__(self, eng, n_machines, n_splits, params, scale, offset, feat_thr, agg_thr, loss, acc, fold_loss, fold_feat_thr, fold_agg_thr):
+    def __init__(self, eng, n_machines, n_splits, params, scale, offset, feat_thr, agg_thr, loss, acc, fold_loss, fold_feat_thr, fold_agg_thr,
+                 fold_params=None, cv_moments=None):
         self.eng, self.n_machines, self.n_splits = eng, n_machines, n_splits
+        self.fold_params = fold_params                                         # [M, K, stride]: the CV models (cv["estimator"] of the reference)
+        self.cv_moments = cv_moments                                           # [M, K, 5, T] float64: gb_cv_moments of every fold's test block
         self.params, self.scale, self.offset = params, scale, offset          # [M, stride], [M, T], [M, T]
         self.feat_thr, self.agg_thr = feat_thr, agg_thr                        # [M, T], [M]  (last fold, diff.py:257-264)
         self.loss, self.acc = loss, acc                                        # [M, epochs]
         self.fold_loss, self.fold_feat_thr, self.fold_agg_thr = fold_loss, fold_feat_thr, fold_agg_thr  # [M, K, ...]
 
-    def detector(self, m: int, tags=None):
-        """Materialise machine ``m`` as a ``DiffBasedAnomalyDetector`` (picklable, servable by gordo.server)."""
+    def detector(self, m: int, tags=None, template=None):
+        """
+        Materialise machine ``m`` as a ``DiffBasedAnomalyDetector`` (picklable, servable by gordo.server).  ``template``: an
+        unfitted detector built from the machine's own definition (same architecture) to fill in, so that ``kind`` and the
+        other constructor arguments survive into ``get_params`` / ``into_definition``.
+        """
         import pandas as pd
         from sklearn.preprocessing import MinMaxScaler
 
@@ -181,9 +188,17 @@ class FleetBuild:
         eng = self.eng
         T = eng.n_out
         tags = list(tags) if tags is not None else list(range(T))
-        ae = KerasAutoEncoder(kind="feedforward_model", n_features=eng.n_in, n_features_out=T)
-        spec = FFNetSpec(list(eng.dims), list(eng.acts), list(eng.l1))
-        ae.model = FittedNet(spec, eng.unpack_params(self.params[m : m + 1])[0])
+        if template is not None:
+            ae = template.base_estimator
+            ae.kwargs.update({"n_features": eng.n_in, "n_features_out": T})
+            ae._prepare_model()
+            if list(ae.model.spec.dims) != list(eng.dims) or list(ae.model.spec.acts) != list(eng.acts):
+                raise ValueError("template architecture differs from the fleet's")
+            ae.model.weights = eng.unpack_params(self.params[m : m + 1])[0]
+        else:
+            ae = KerasAutoEncoder(kind="feedforward_model", n_features=eng.n_in, n_features_out=T)
+            spec = FFNetSpec(list(eng.dims), list(eng.acts), list(eng.l1))
+            ae.model = FittedNet(spec, eng.unpack_params(self.params[m : m + 1])[0])
         hist = {"loss": [float(v) for v in self.loss[m].cpu().numpy()], "accuracy": [float(v) for v in self.acc[m].cpu().numpy()]}
         ae._history = History(hist, {"verbose": 0, "epochs": len(hist["loss"]), "steps": None}, list(range(len(hist["loss"]))))
         sc = MinMaxScaler()
@@ -194,7 +209,11 @@ class FleetBuild:
         sc.data_range_ = 1.0 / scale
         sc.data_max_ = sc.data_min_ + sc.data_range_
         sc.n_features_in_, sc.n_samples_seen_ = T, 0
-        det = DiffBasedAnomalyDetector(base_estimator=ae, scaler=sc)
+        if template is not None:
+            det = template
+            det.scaler = sc
+        else:
+            det = DiffBasedAnomalyDetector(base_estimator=ae, scaler=sc)
         det.feature_thresholds_ = pd.Series(self.feat_thr[m].cpu().numpy().astype(np.float64), index=tags, name=f"fold-{self.n_splits - 1}")
         det.aggregate_threshold_ = float(self.agg_thr[m])
         ff = self.fold_feat_thr[m].cpu().numpy().astype(np.float64)
@@ -281,8 +300,12 @@ def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_
     res = eng.infer_score(params, sc_jobs, K * M, test, x, y, scale, out_rows=K * M * test, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
     feat, agg = eng.thresholds(sc_jobs, K * M, test, res["tag-anomaly-unscaled"], res["total-anomaly-scaled"], M * (K + 1), window=6)
     T = eng.n_out
+    # the evaluation metrics of ModelBuilder's cross validation (build_model.py:250-289) reduce to five sums per (fold, tag)
+    moments = engine.cv_moments(sc_jobs, K * M, res["model-output"], y, T).view(K, M, 5, T).permute(1, 0, 2, 3).contiguous()
+    fold_params = params[M:].view(K, M, -1).permute(1, 0, 2).contiguous()
     fold_feat = feat[M:].view(K, M, T).permute(1, 0, 2).contiguous()
     fold_agg = agg[M:].view(K, M).t().contiguous()
     E = loss.shape[1]
     return FleetBuild(eng, M, K, params[:M].contiguous(), scale[:M].contiguous(), offset[:M].contiguous(), fold_feat[:, K - 1].contiguous(),
-                      fold_agg[:, K - 1].contiguous(), loss[:M], acc[:M], loss[M:].view(K, M, E).permute(1, 0, 2), fold_feat, fold_agg)
+                      fold_agg[:, K - 1].contiguous(), loss[:M], acc[:M], loss[M:].view(K, M, E).permute(1, 0, 2), fold_feat, fold_agg,
+                      fold_params=fold_params, cv_moments=moments)

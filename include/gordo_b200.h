@@ -134,6 +134,14 @@ int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const fl
                   const float* total_scaled, int32_t n_out, int32_t window, float* feat_thr,
                   float* agg_thr, int32_t n_slots, void* stream);
 
+/* ---- K8: column moments behind the builder's cross-validation metrics (build_model.py:250-289, 378-446) ----
+ * For job i, over rows yhat[out_row .. out_row+n_rows) and y[x_row .. x_row+n_rows), with e = yhat - y and
+ * y0 = the job's first target row:  out[i][q][j] (double) = q0: sum e, q1: sum e^2, q2: sum |e|,
+ * q3: sum (y - y0), q4: sum (y - y0)^2.  explained_variance / r2 / mean_squared_error / mean_absolute_error
+ * (per tag and uniform-averaged, under any per-tag affine scoring scaler) follow from these on the host. */
+int gb_cv_moments(const gb_job* jobs, int32_t n_jobs, const float* yhat, const float* y, int32_t n_out,
+                  double* out, void* stream);
+
 /* ---- K6: optional smoothing of anomaly columns (diff.py:302-308, 387-415) ------------------
  * method 0 = smm rolling(window).median(), 1 = sma rolling(window).mean() (first window-1 rows NaN),
  * 2 = ewma ewm(span=window).mean() (adjust=True).  arr / out: [rows][n_cols], rows taken at [out_row, out_row+n_rows). */
