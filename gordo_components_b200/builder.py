@@ -5,11 +5,11 @@ definition -> cross validation with the evaluation metrics -> final fit -> offse
 (``FleetModelBuilder``).
 
 ``FleetModelBuilder`` is where the batched kernels pay off: machines whose definition is the canonical
-``DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(<feed-forward kind>), scaler=MinMaxScaler())`` are bucketed by
-architecture and training length, and every bucket is built by ``fleet.build_fleet`` -- all final fits and all CV folds
+``DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(<feed-forward kind>), scaler=MinMaxScaler())`` -- the network bare or
+behind one ``MinMaxScaler`` in a Pipeline, as in gordo's example configs -- are bucketed by architecture and training length, and every bucket is built by ``fleet.build_fleet`` -- all final fits and all CV folds
 in one ``gb_ffae_fit`` launch, fold scoring / thresholds / scaler statistics / metric moments one launch each.  The
 cross-validation ``scores`` block of the metadata is then assembled on the host from ``gb_cv_moments``' five sums per
-(fold, tag).  Any other definition (input scalers in a Pipeline, LSTM models, K-fold detectors, custom metrics ...) goes
+(fold, tag).  Any other definition (other transformers in a Pipeline, LSTM models, K-fold detectors, custom metrics ...) goes
 through ``ModelBuilder``: one machine at a time, still on the GPU through the estimators' own fit / predict.
 
 Machines are plain dicts in the layout of ``Machine.to_dict()`` (gordo/machine/machine.py:226-246): ``name``, ``model`` (a
@@ -310,15 +310,16 @@ class ModelBuilder:
 class _Canonical:
     """What ``FleetModelBuilder`` needs to know about a machine that can take the batched path."""
 
-    def __init__(self, index, machine, model, spec, X, y, dataset_meta, query_sec, fit, n_splits, evaluation):
-        self.index, self.machine, self.model, self.spec = index, machine, model, spec
+    def __init__(self, index, machine, model, spec, X, y, dataset_meta, query_sec, fit, n_splits, evaluation, input_scaler):
+        self.index, self.machine, self.model, self.spec, self.input_scaler = index, machine, model, spec, input_scaler
         self.X, self.y, self.dataset_meta, self.query_sec = X, y, dataset_meta, query_sec
         self.fit, self.n_splits, self.evaluation = fit, n_splits, evaluation
 
     def bucket(self):
         s = self.spec
         return (tuple(s.dims), tuple(s.acts), tuple(float(v) for v in s.l1), tuple(sorted(s.adam.items())), tuple(s.metrics),
-                len(self.X), self.fit["epochs"], self.fit["batch_size"], self.fit["shuffle"], self.n_splits, int(self.evaluation.get("seed", 0)))
+                len(self.X), self.fit["epochs"], self.fit["batch_size"], self.fit["shuffle"], self.n_splits, int(self.evaluation.get("seed", 0)),
+                self.input_scaler)
 
 
 def _default_minmax(scaler) -> bool:
@@ -354,9 +355,11 @@ def _canonical(index, machine) -> Optional[_Canonical]:
         return no("model is not a plain DiffBasedAnomalyDetector")
     if not _default_minmax(model.scaler):
         return no("detector scaler is not a default MinMaxScaler")
-    ae = model.base_estimator
+    ae, input_scaler = model.base_estimator, False
+    if type(ae) is Pipeline and len(ae.steps) == 2 and _default_minmax(ae.steps[0][1]):
+        ae, input_scaler = ae.steps[1][1], True  # Pipeline([MinMaxScaler(), KerasAutoEncoder]): gordo's example config
     if type(ae) is not KerasAutoEncoder:
-        return no("base_estimator is not a bare KerasAutoEncoder")
+        return no("base_estimator is not a KerasAutoEncoder, bare or behind one default MinMaxScaler")
     fit_args = ae.extract_supported_fit_args(ae.kwargs)
     if fit_args.get("validation_split") or fit_args.get("callbacks"):
         return no("validation_split / callbacks need the per-epoch loop")
@@ -371,7 +374,7 @@ def _canonical(index, machine) -> Optional[_Canonical]:
     if len(X) != len(y) or len(X) // (split_obj.n_splits + 1) == 0:
         return no("too few rows for the CV folds")
     fit = {"epochs": int(fit_args.get("epochs", 1)), "batch_size": int(fit_args.get("batch_size") or 32), "shuffle": bool(fit_args.get("shuffle", True))}
-    return _Canonical(index, machine, model, spec, X, y, dataset_meta, query_sec, fit, split_obj.n_splits, evaluation)
+    return _Canonical(index, machine, model, spec, X, y, dataset_meta, query_sec, fit, split_obj.n_splits, evaluation, input_scaler)
 
 
 class FleetModelBuilder:
@@ -417,7 +420,8 @@ class FleetModelBuilder:
         xd = engine.to_device_f32(x_host, eng.device)
         yd = xd if same_y else engine.to_device_f32(np.concatenate([np.ascontiguousarray(c.y.values, dtype=np.float32) for c in members]), eng.device)
         fb = fleet.build_fleet(eng, xd, yd, rows, epochs=first.fit["epochs"], batch_size=first.fit["batch_size"], n_splits=K,
-                               seed=int(first.evaluation.get("seed", 0)), adam=first.spec.adam, shuffle=first.fit["shuffle"])
+                               seed=int(first.evaluation.get("seed", 0)), adam=first.spec.adam, shuffle=first.fit["shuffle"],
+                               input_scaler=first.input_scaler)
         moments = fb.cv_moments.cpu().numpy()
         scale = fb.scale.cpu().numpy().astype(np.float64)
         engine._torch().cuda.synchronize()
@@ -427,7 +431,7 @@ class FleetModelBuilder:
         out = []
         for m, c in enumerate(members):
             tags = list(c.y.columns)
-            model = fb.detector(m, tags=tags, template=c.model)
+            model = fb.detector(m, tags=tags, template=c.model, input_tags=list(c.X.columns))
             names = [s.rpartition(".")[2] for s in c.evaluation["metrics"]]
             scoring_scale = scale[m] if c.evaluation.get("scoring_scaler") else None
             scores = scores_block(scores_from_moments(moments[m], test, scoring_scale, names), tags)

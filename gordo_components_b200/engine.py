@@ -195,8 +195,12 @@ class FFEngine:
         return thresholds(jobs_dev, n_jobs, max_rows, tag_unscaled, total_scaled, self.n_out, n_slots, window, self.device)
 
 
-def minmax_fit(jobs_dev, n_jobs, max_rows, y, n_out, n_slots, device):
-    """MinMaxScaler.fit per job on device: returns (scale_ [n_slots, n_out], min_ [n_slots, n_out])."""
+def minmax_fit(jobs_dev, n_jobs, max_rows, y, n_out, n_slots, device, return_minmax=False):
+    """
+    MinMaxScaler.fit per job on device: returns (scale_ [n_slots, n_out], min_ [n_slots, n_out]); with ``return_minmax`` also
+    the raw (data_min_, data_max_) the kernel found -- exact float32 values, for callers that need sklearn's float64 arithmetic
+    on them (a scaler in front of the network, where ``x * scale_ + min_`` cancels for offset-dominated tags).
+    """
     torch = _torch()
     lib = _cabi.load_library()
     scale = torch.ones((n_slots, n_out), dtype=torch.float32, device=device)
@@ -204,6 +208,8 @@ def minmax_fit(jobs_dev, n_jobs, max_rows, y, n_out, n_slots, device):
     ws = torch.empty((n_slots, 2, n_out), dtype=torch.float32, device=device)
     p = _cabi.ptr
     _cabi.check(lib.gb_minmax_fit(p(jobs_dev), int(n_jobs), int(max_rows), p(y), int(n_out), p(scale), p(offset), p(ws), int(n_slots), _stream_ptr()))
+    if return_minmax:
+        return scale, offset, ws[:, 0], ws[:, 1]
     return scale, offset
 
 

@@ -163,7 +163,9 @@ class FleetBuild:
     """
 
     def __init__(self, eng, n_machines, n_splits, params, scale, offset, feat_thr, agg_thr, loss, acc, fold_loss, fold_feat_thr, fold_agg_thr,
-                 fold_params=None, cv_moments=None):
+                 fold_params=None, cv_moments=None, in_scale=None, in_offset=None, fold_in_scale=None, fold_in_offset=None):
+        # float64 scale_ / min_ of the MinMaxScaler in front of the network ([M, T]; per CV fold [M, K, T]); None without one
+        self.in_scale, self.in_offset, self.fold_in_scale, self.fold_in_offset = in_scale, in_offset, fold_in_scale, fold_in_offset
         self.eng, self.n_machines, self.n_splits = eng, n_machines, n_splits
         self.fold_params = fold_params                                         # [M, K, stride]: the CV models (cv["estimator"] of the reference)
         self.cv_moments = cv_moments                                           # [M, K, 5, T] float64: gb_cv_moments of every fold's test block
@@ -172,7 +174,19 @@ class FleetBuild:
         self.loss, self.acc = loss, acc                                        # [M, epochs]
         self.fold_loss, self.fold_feat_thr, self.fold_agg_thr = fold_loss, fold_feat_thr, fold_agg_thr  # [M, K, ...]
 
-    def detector(self, m: int, tags=None, template=None):
+    @staticmethod
+    def _fill_minmax(sc, scale, offset, names):
+        """Give a MinMaxScaler the fitted attributes sklearn's ``fit`` would have left (feature_range (0, 1))."""
+        sc.scale_, sc.min_ = scale, offset
+        sc.data_min_ = -offset / scale
+        sc.data_range_ = 1.0 / scale
+        sc.data_max_ = sc.data_min_ + sc.data_range_
+        sc.n_features_in_, sc.n_samples_seen_ = len(scale), 0
+        if names is not None and all(isinstance(n, str) for n in names):
+            sc.feature_names_in_ = np.asarray(names, dtype=object)
+        return sc
+
+    def detector(self, m: int, tags=None, template=None, input_tags=None):
         """
         Materialise machine ``m`` as a ``DiffBasedAnomalyDetector`` (picklable, servable by gordo.server).  ``template``: an
         unfitted detector built from the machine's own definition (same architecture) to fill in, so that ``kind`` and the
@@ -188,8 +202,15 @@ class FleetBuild:
         eng = self.eng
         T = eng.n_out
         tags = list(tags) if tags is not None else list(range(T))
+        from sklearn.pipeline import Pipeline
+
         if template is not None:
-            ae = template.base_estimator
+            est = template.base_estimator
+            ae = est.steps[-1][1] if isinstance(est, Pipeline) else est
+            if isinstance(est, Pipeline) != (self.in_scale is not None):
+                raise ValueError("the template's input scaler and the fleet's do not match")
+            if isinstance(est, Pipeline):
+                self._fill_minmax(est.steps[0][1], self.in_scale[m].cpu().numpy(), self.in_offset[m].cpu().numpy(), input_tags)
             ae.kwargs.update({"n_features": eng.n_in, "n_features_out": T})
             ae._prepare_model()
             if list(ae.model.spec.dims) != list(eng.dims) or list(ae.model.spec.acts) != list(eng.acts):
@@ -201,14 +222,7 @@ class FleetBuild:
             ae.model = FittedNet(spec, eng.unpack_params(self.params[m : m + 1])[0])
         hist = {"loss": [float(v) for v in self.loss[m].cpu().numpy()], "accuracy": [float(v) for v in self.acc[m].cpu().numpy()]}
         ae._history = History(hist, {"verbose": 0, "epochs": len(hist["loss"]), "steps": None}, list(range(len(hist["loss"]))))
-        sc = MinMaxScaler()
-        scale = self.scale[m].cpu().numpy().astype(np.float64)
-        offset = self.offset[m].cpu().numpy().astype(np.float64)
-        sc.scale_, sc.min_ = scale, offset
-        sc.data_min_ = -offset / scale
-        sc.data_range_ = 1.0 / scale
-        sc.data_max_ = sc.data_min_ + sc.data_range_
-        sc.n_features_in_, sc.n_samples_seen_ = T, 0
+        sc = self._fill_minmax(MinMaxScaler(), self.scale[m].cpu().numpy().astype(np.float64), self.offset[m].cpu().numpy().astype(np.float64), None)
         if template is not None:
             det = template
             det.scaler = sc
@@ -259,7 +273,7 @@ def dump_fleet(fb: "FleetBuild", root: str, names: Sequence[str], tags: Optional
 
 
 def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_size: int = 32, n_splits: int = 3, seed: int = 0,
-                adam: Optional[Dict[str, float]] = None, shuffle: bool = True, generator=None) -> FleetBuild:
+                adam: Optional[Dict[str, float]] = None, shuffle: bool = True, generator=None, input_scaler: bool = False) -> FleetBuild:
     """
     The batched form of ``gordo build`` for one architecture bucket: for every machine the 3-fold TimeSeriesSplit
     cross-validation (fit on each prefix, thresholds from the following test block: diff.py:176-266) and the final fit on
@@ -267,6 +281,11 @@ def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_
     then fold scoring, threshold reduction and scaler statistics, each a single launch.
 
     x, y: device tensors [n_machines * rows, T]; machine m owns rows [m*rows, (m+1)*rows).
+
+    ``input_scaler``: the network sits behind a MinMaxScaler (``Pipeline([MinMaxScaler(), KerasAutoEncoder])``, the shape of
+    gordo's example configs, examples/config.yaml:74-81).  Inside cross validation every fold clone fits that scaler on its
+    own training prefix, so every fit slot gets its own scaled copy of its machine's rows -- sklearn's float64 arithmetic on
+    the exact column extrema (``gb_minmax_fit`` finds them, ``gb_affine_f64`` applies them), rounded to float32 once.
     """
     torch = engine._torch()
     dev = eng.device
@@ -288,13 +307,30 @@ def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_
     fit_slots = np.concatenate([np.arange(M)] + [M + k * M + np.arange(M) for k in range(K)])
     fit_rows = np.concatenate([np.full(M, N)] + [np.full(M, starts[k]) for k in range(K)])
     fit_x = np.concatenate([base] * (K + 1))
+    in_scale = in_offset = None
+    if input_scaler:
+        S = M * (K + 1)
+        prefix_jobs = engine.jobs_to_device(engine.make_jobs(fit_slots, fit_rows, fit_x), dev)
+        _, _, lo, hi = engine.minmax_fit(prefix_jobs, S, N, x, eng.n_in, S, dev, return_minmax=True)
+        lo, span = lo.double(), hi.double() - lo.double()
+        span[~(span >= 10 * np.finfo(np.float64).eps)] = 1.0  # sklearn _handle_zeros_in_scale (also catches all-NaN columns)
+        in_scale = 1.0 / span
+        in_offset = -lo * in_scale
+        # slot s works on its own copy of machine (s mod M)'s rows, at rows [s*N, (s+1)*N) of the replicated arrays
+        copy_jobs = engine.jobs_to_device(engine.make_jobs(np.arange(S), N, fit_x, np.arange(S, dtype=np.int64) * N), dev)
+        x = engine.affine_f64(copy_jobs, S, N, x.double(), in_scale.contiguous(), in_offset.contiguous(), out_rows=S * N)
+        y = y.view(M, N, -1).repeat(K + 1, 1, 1).view(S * N, -1)
+        base_of = lambda k: (M + k * M + np.arange(M, dtype=np.int64)) * N  # noqa: E731
+        fit_x = np.arange(S, dtype=np.int64) * N
+    else:
+        base_of = lambda k: base  # noqa: E731
     fit_jobs = engine.jobs_to_device(engine.make_jobs(fit_slots, fit_rows, fit_x), dev)
     loss, acc, _ = eng.fit(params, fit_jobs, len(fit_slots), N, x, y, epochs=epochs, batch_size=batch_size, shuffle=shuffle, adam=adam, seed=seed)
     # scalers: final on all rows, fold k on its training prefix (diff.py:173 inside each CV clone)
     scale, offset = eng.minmax_fit(fit_jobs, len(fit_slots), N, y, M * (K + 1))
     # fold scoring on the test blocks: compact output rows [(k*M + m)*test, ...)
     sc_slots = np.concatenate([M + k * M + np.arange(M) for k in range(K)])
-    sc_x = np.concatenate([base + starts[k] for k in range(K)])
+    sc_x = np.concatenate([base_of(k) + starts[k] for k in range(K)])
     sc_out = np.arange(K * M, dtype=np.int64) * test
     sc_jobs = engine.jobs_to_device(engine.make_jobs(sc_slots, test, sc_x, sc_out), dev)
     res = eng.infer_score(params, sc_jobs, K * M, test, x, y, scale, out_rows=K * M * test, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
@@ -308,4 +344,7 @@ def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_
     E = loss.shape[1]
     return FleetBuild(eng, M, K, params[:M].contiguous(), scale[:M].contiguous(), offset[:M].contiguous(), fold_feat[:, K - 1].contiguous(),
                       fold_agg[:, K - 1].contiguous(), loss[:M], acc[:M], loss[M:].view(K, M, E).permute(1, 0, 2), fold_feat, fold_agg,
-                      fold_params=fold_params, cv_moments=moments)
+                      fold_params=fold_params, cv_moments=moments,
+                      in_scale=None if in_scale is None else in_scale[:M].contiguous(), in_offset=None if in_offset is None else in_offset[:M].contiguous(),
+                      fold_in_scale=None if in_scale is None else in_scale[M:].view(K, M, -1).permute(1, 0, 2).contiguous(),
+                      fold_in_offset=None if in_offset is None else in_offset[M:].view(K, M, -1).permute(1, 0, 2).contiguous())

@@ -122,14 +122,22 @@ def test_which_machines_take_the_batched_path():
     five = builder._canonical(0, _machine(evaluation={"cv": {"sklearn.model_selection.TimeSeriesSplit": {"n_splits": 5}}, "metrics": ["r2_score"], "scoring_scaler": None}))
     assert five is not None and five.n_splits == 5
 
-    pipeline = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler", AE]}}}}
+    # gordo's example config: the network behind one MinMaxScaler -- batched too, in its own bucket
+    scaled = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler", AE]}}}}
+    sc = builder._canonical(0, _machine(model=scaled))
+    assert sc is not None and sc.input_scaler and not c.input_scaler and sc.bucket() != c.bucket() and sc.bucket()[:-1] == c.bucket()[:-1]
+    pipeline = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.StandardScaler", AE]}}}}
+    ranged = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": [
+        {"sklearn.preprocessing.MinMaxScaler": {"feature_range": [-1, 1]}}, AE]}}}}
+    three = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": [
+        "gordo.machine.model.transformers.imputer.InfImputer", "sklearn.preprocessing.MinMaxScaler", AE]}}}}
     lstm = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"gordo.machine.model.models.KerasLSTMAutoEncoder": {"kind": "lstm_hourglass", "lookback_window": 3}}}}
     smooth = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": AE, "window": 12}}
     robust = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": AE, "scaler": "sklearn.preprocessing.RobustScaler"}}
     kfcv = {"gordo.machine.model.anomaly.diff.DiffBasedKFCVAnomalyDetector": {"base_estimator": AE}}
     stopping = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"gordo.machine.model.models.KerasAutoEncoder": {
         "kind": "feedforward_hourglass", "validation_split": 0.1, "callbacks": [{"tensorflow.keras.callbacks.EarlyStopping": {"patience": 1}}]}}}}
-    for model in (pipeline, lstm, smooth, robust, kfcv, stopping, AE):
+    for model in (pipeline, ranged, three, lstm, smooth, robust, kfcv, stopping, AE):
         assert builder._canonical(0, _machine(model=model)) is None
     for evaluation in ({"cv_mode": "cross_val_only"}, {"metrics": ["max_error"]}, {"scoring_scaler": "sklearn.preprocessing.StandardScaler"},
                        {"cv": {"sklearn.model_selection.KFold": {"n_splits": 3}}}, {"cv": {"sklearn.model_selection.TimeSeriesSplit": {"n_splits": 3, "gap": 2}}}):

@@ -98,7 +98,8 @@ def test_fleet_cv_scores_match_sklearn_on_the_fold_models(engine, torch):
 
 AE = {"gordo.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "epochs": 3, "compression_factor": 0.5, "encoding_layers": 2}}
 DETECTOR = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": AE}}
-PIPELINE = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler", AE]}}}}
+SCALED = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler", AE]}}}}
+PIPELINE = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.StandardScaler", AE]}}}}
 LSTM = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"gordo.machine.model.models.KerasLSTMAutoEncoder": {
     "kind": "lstm_hourglass", "lookback_window": 4, "epochs": 1, "encoding_layers": 1}}}}
 
@@ -108,12 +109,13 @@ def test_fleet_model_builder_end_to_end(engine, torch, tmp_path):
     from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
 
     N, T = 320, 5
-    frames = {name: _series(N, T, seed) for seed, name in enumerate(["a-1", "a-2", "a-3", "pipe", "lstm"])}
+    frames = {name: _series(N, T, seed) for seed, name in enumerate(["a-1", "a-2", "a-3", "pipe", "lstm", "s-1", "s-2"])}
     machines = [{"name": n, "model": DETECTOR, "dataset": {"X": frames[n], "y": frames[n]}, "metadata": {"user_defined": {"plant": "X"}}} for n in ("a-1", "a-2", "a-3")]
     machines.insert(1, {"name": "pipe", "model": PIPELINE, "dataset": (frames["pipe"], frames["pipe"])})
     machines.append({"name": "lstm", "model": LSTM, "dataset": {"X": frames["lstm"]}, "evaluation": {"metrics": ["r2_score"], "scoring_scaler": None}})
+    machines += [{"name": n, "model": SCALED, "dataset": {"X": frames[n]}} for n in ("s-1", "s-2")]
     results = builder.FleetModelBuilder(machines).build(str(tmp_path))
-    assert [m["name"] for _, m in results] == ["a-1", "pipe", "a-2", "a-3", "lstm"]
+    assert [m["name"] for _, m in results] == ["a-1", "pipe", "a-2", "a-3", "lstm", "s-1", "s-2"]
 
     by_name = {m["name"]: (model, m) for model, m in results}
     fleet_scores = by_name["a-2"][1]["metadata"]["build_metadata"]["model"]["cross_validation"]["scores"]
@@ -148,6 +150,21 @@ def test_fleet_model_builder_end_to_end(engine, torch, tmp_path):
         frame = loaded.anomaly(frames[name], frames[name], frequency=pd.Timedelta("10min"))
         np.testing.assert_array_equal(frame["model-output"].values, model.anomaly(frames[name], frames[name], frequency=pd.Timedelta("10min"))["model-output"].values)
         assert len(frame) == N - block["model"]["model_offset"] and "total-anomaly-confidence" in frame
+
+    # a batched machine behind an input scaler: the Pipeline's MinMaxScaler carries sklearn's own statistics of the training
+    # data, and the detector answers exactly like the Pipeline run step by step on the host in float64
+    model, _ = by_name["s-2"]
+    pipe = model.base_estimator
+    want = MinMaxScaler().fit(frames["s-2"].values.astype(np.float64))
+    np.testing.assert_allclose(pipe.steps[0][1].scale_, want.scale_, rtol=1e-14)
+    np.testing.assert_allclose(pipe.steps[0][1].min_, want.min_, rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(pipe.steps[0][1].data_max_, want.data_max_, rtol=1e-12)
+    scaled_x = want.transform(frames["s-2"].values.astype(np.float64)).astype(np.float32)
+    direct = pipe.steps[1][1].predict(scaled_x)
+    np.testing.assert_allclose(model.predict(frames["s-2"]), direct, rtol=1e-5, atol=1e-5)
+    s_loss = by_name["s-1"][1]["metadata"]["build_metadata"]["model"]["model_meta"]["history"]["loss"]
+    assert s_loss[-1] < s_loss[0]
+    assert set(by_name["s-1"][1]["metadata"]["build_metadata"]["model"]["cross_validation"]["scores"]) == set(fleet_scores)
 
     # the batched machines keep their own definition and user metadata, and trained (loss falls)
     model, machine = by_name["a-3"]
