@@ -187,5 +187,10 @@ def make_lstmnet(n_features, units, acts, n_features_out, out_act, lookback) -> 
 
 
 def ptr(t):
-    """Raw device address of a torch tensor (None -> NULL)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Raw device address of a torch tensor (None -> NULL).  The kernels index dense row-major memory: anything else is refused."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError(f"tensor of shape {tuple(t.shape)} with strides {tuple(t.stride())} is not C-contiguous; the gordo_b200 "
+                         "kernels take dense row-major arrays (call .contiguous() / np.ascontiguousarray first)")
+    return C.c_void_p(t.data_ptr())

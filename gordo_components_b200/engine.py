@@ -230,6 +230,8 @@ def cv_moments(jobs_dev, n_jobs, yhat, y, n_out):
     torch = _torch()
     lib = _cabi.load_library()
     out = torch.zeros((int(n_jobs), 5, int(n_out)), dtype=torch.float64, device=yhat.device)
+    if int(n_jobs) == 0:
+        return out
     p = _cabi.ptr
     _cabi.check(lib.gb_cv_moments(p(jobs_dev), int(n_jobs), p(yhat), p(y), int(n_out), p(out), _stream_ptr()))
     return out

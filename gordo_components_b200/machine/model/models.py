@@ -226,6 +226,10 @@ class KerasBaseEstimator(BaseEstimator, GordoBase):
     def __sklearn_clone__(self):
         return self.__class__(self.kind, **deepcopy(self.kwargs))
 
+    def __sklearn_is_fitted__(self) -> bool:
+        # no trailing-underscore attributes here: tell sklearn (Pipeline.predict checks its last step) what "fitted" means
+        return self.model is not None
+
     # ------------------------------------------------------------------ pickling: plain numpy state, no device handles
     def __getstate__(self):
         state = self.__dict__.copy()

@@ -159,8 +159,13 @@ def load_params_from_definition(definition: dict) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------- object -> definition
+def _has_hook(obj, name) -> bool:
+    # looked up on the class: the detectors forward unknown attributes to their base estimator, whose hook is not theirs
+    return hasattr(type(obj), name)
+
+
 def _value_definition(value, tuples_to_list):
-    if hasattr(value, "get_params") or hasattr(value, "into_definition"):
+    if _has_hook(value, "get_params") or _has_hook(value, "into_definition"):
         return _node_definition(value, False, tuples_to_list)
     if isinstance(value, list):
         return [_node_definition(v[1], False, tuples_to_list) if isinstance(v, tuple) else v for v in value]
@@ -173,7 +178,7 @@ def _value_definition(value, tuples_to_list):
 
 def _node_definition(obj, prune_default_params, tuples_to_list):
     path = f"{type(obj).__module__}.{type(obj).__name__}"
-    if hasattr(obj, "into_definition"):
+    if _has_hook(obj, "into_definition"):
         return {path: obj.into_definition()}
     params = obj.get_params(deep=False)
     if prune_default_params:

@@ -222,6 +222,11 @@ def test_detector_definitions():
     kf = serializer.from_definition({"gordo.machine.model.anomaly.diff.DiffBasedKFCVAnomalyDetector": {
         "threshold_percentile": 0.9, "base_estimator": {"gordo.machine.model.models.KerasLSTMAutoEncoder": {"kind": "lstm_hourglass", "lookback_window": 4}}}})
     assert type(kf) is DiffBasedKFCVAnomalyDetector and kf.threshold_percentile == 0.9 and type(kf.base_estimator) is KerasLSTMAutoEncoder
+    # a detector directly around a model with hooks: the detector forwards unknown attributes to it, yet its definition is its own
+    plain = serializer.from_definition({"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {"gordo.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "epochs": 3}}}})
+    d = serializer.into_definition(plain)["gordo_components_b200.machine.model.anomaly.diff.DiffBasedAnomalyDetector"]
+    assert d["base_estimator"] == {"gordo_components_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "epochs": 3}} and d["shuffle"] is False
+    assert serializer.into_definition(serializer.from_definition(serializer.into_definition(plain))) == serializer.into_definition(plain)
     # the pre-1.0 package layout still names the same classes
     old = serializer.from_definition({"gordo_components.model.models.KerasAutoEncoder": {"kind": "feedforward_symmetric"}})
     assert type(old) is KerasAutoEncoder
