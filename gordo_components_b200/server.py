@@ -1,0 +1,250 @@
+"""
+The serving side of the hot path without the web framework: what ``POST /gordo/v0/<project>/<name>/anomaly/prediction``
+and ``.../prediction`` do between the HTTP layer and ``model.anomaly`` (gordo/server/blueprints/anomaly.py:28-122,
+base.py:30-120, utils.py:47-330), as plain functions a Flask / ASGI view can call:
+
+* the wire formats: frames as nested JSON dicts or parquet bytes (``dataframe_to_dict`` / ``dataframe_from_dict`` /
+  ``dataframe_into_parquet_bytes`` / ``dataframe_from_parquet_bytes``), and the check of request frames against the model's
+  tag list (``verify_dataframe``);
+* ``ModelStore``: the models of a project directory kept loaded -- the reference unpickles through ``lru_cache(2)``
+  (utils.py:334-353) because a TensorFlow model per machine is heavy; here a model is a few hundred KB of numpy weights whose
+  device copy is cached on the estimator, so a whole project stays resident (``max_models`` bounds it if needed);
+* ``anomaly_prediction`` / ``prediction``: request payload in, ``Reply(status, body)`` out, with the reference's status
+  codes and messages (400 without ``X`` / ``y`` or on unexpected features, 422 when the model is not an anomaly detector).
+
+Many small concurrent requests are better served through ``serving.AnomalyCoalescer`` (one launch for everything that is
+waiting); this module is the per-request path and the data formats either way.
+"""
+import io
+import os
+import threading
+import timeit
+from collections import OrderedDict
+from typing import Any, Dict, List, Optional, Union
+
+import dateutil.parser
+import pandas as pd
+
+from . import serializer
+from .machine.model import utils as model_utils
+
+DELETED_FROM_RESPONSE_COLUMNS = (
+    "smooth-tag-anomaly-scaled",
+    "smooth-total-anomaly-scaled",
+    "smooth-tag-anomaly-unscaled",
+    "smooth-total-anomaly-unscaled",
+)
+
+
+# ------------------------------------------------------------------------------------------------ wire formats
+def dataframe_into_parquet_bytes(df: pd.DataFrame, compression: str = "snappy") -> bytes:
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    sink = pa.BufferOutputStream()
+    pq.write_table(pa.Table.from_pandas(df), sink, compression=compression)
+    return sink.getvalue().to_pybytes()
+
+
+def dataframe_from_parquet_bytes(buf: bytes) -> pd.DataFrame:
+    import pyarrow.parquet as pq
+
+    return pq.read_table(io.BytesIO(buf)).to_pandas()
+
+
+def dataframe_to_dict(df: pd.DataFrame) -> dict:
+    """
+    JSON-able form of a frame: ``{column: {index: value}}``, and for two-level columns (the anomaly frame)
+    ``{top: {sub: {index: value}}}``; a DatetimeIndex is written as strings (utils.py:86-143).
+    """
+    data = df.copy(deep=False)
+    if isinstance(data.index, pd.DatetimeIndex):
+        data.index = data.index.astype(str)
+    if not isinstance(df.columns, pd.MultiIndex):
+        return data.to_dict()
+    out = {}
+    for top in data.columns.get_level_values(0).unique():
+        block = data[top]
+        out[top] = (block if isinstance(block, pd.DataFrame) else pd.DataFrame(block)).to_dict()
+    return out
+
+
+def dataframe_from_dict(data: dict) -> pd.DataFrame:
+    """Inverse of ``dataframe_to_dict``; the index is parsed as ISO timestamps, else as integers, and sorted (utils.py:146-191)."""
+    if isinstance(data, dict) and any(isinstance(v, dict) for v in data.values()):
+        try:
+            keys = list(data.keys())
+            df = pd.concat((pd.DataFrame.from_dict(data[k]) for k in keys), axis=1, keys=keys)
+        except (ValueError, AttributeError):
+            df = pd.DataFrame.from_dict(data)
+    else:
+        df = pd.DataFrame.from_dict(data)
+    try:
+        df.index = df.index.map(dateutil.parser.isoparse)
+    except (TypeError, ValueError):
+        df.index = df.index.map(int)
+    return df.sort_index()
+
+
+class Reply:
+    """What a view returns: an HTTP status and a JSON-able dict or raw (parquet) bytes."""
+
+    def __init__(self, status: int, body: Union[dict, bytes]):
+        self.status, self.body = status, body
+
+    @property
+    def content_type(self) -> str:
+        return "application/octet-stream" if isinstance(self.body, (bytes, bytearray)) else "application/json"
+
+    def __repr__(self):
+        return f"Reply({self.status}, {self.content_type})"
+
+
+def verify_dataframe(df: pd.DataFrame, expected_columns: List[str]) -> Union[pd.DataFrame, Reply]:
+    """
+    The request frame reduced / relabelled to the model's tags, or a 400 ``Reply`` (utils.py:206-247): unlabelled frames of
+    the right width get the expected names, frames that carry all expected names are reordered, anything else is refused.
+    """
+    if isinstance(df.columns, pd.MultiIndex):
+        return Reply(400, {"message": f"Server does not support multi-level dataframes at this time: {df.columns.tolist()}"})
+    if all(col in df.columns for col in expected_columns):
+        return df[expected_columns]
+    if len(df.columns) != len(expected_columns):
+        return Reply(400, {"message": f"Unexpected features: was expecting {expected_columns} length of {len(expected_columns)}, "
+                                      f"but got {df.columns} length of {len(df.columns)}"})
+    df = df.copy(deep=False)
+    df.columns = expected_columns
+    return df
+
+
+# ------------------------------------------------------------------------------------------------ resident models
+def _tag_names(tags) -> List[str]:
+    return [t["name"] if isinstance(t, dict) else str(getattr(t, "name", t)) for t in tags or []]
+
+
+class ModelStore:
+    """
+    ``<directory>/<name>/{model.pkl, metadata.json}`` (what ``serializer.dump`` and the builders write) kept loaded.
+    Thread safe; ``max_models=None`` keeps everything, otherwise least-recently-used models are dropped.
+    """
+
+    def __init__(self, directory: str, max_models: Optional[int] = None):
+        self.directory, self.max_models = directory, max_models
+        self._models: "OrderedDict[str, Any]" = OrderedDict()
+        self._metadata: Dict[str, dict] = {}
+        self._lock = threading.Lock()
+
+    def names(self) -> List[str]:
+        return sorted(d for d in os.listdir(self.directory) if os.path.isfile(os.path.join(self.directory, d, "model.pkl")))
+
+    def model(self, name: str):
+        with self._lock:
+            if name in self._models:
+                self._models.move_to_end(name)
+                return self._models[name]
+        path = os.path.join(self.directory, name)
+        if not os.path.isfile(os.path.join(path, "model.pkl")):
+            raise FileNotFoundError(f"No such model found: '{name}'")
+        model = serializer.load(path)
+        with self._lock:
+            self._models[name] = model
+            while self.max_models is not None and len(self._models) > self.max_models:
+                self._models.popitem(last=False)
+        return model
+
+    def metadata(self, name: str) -> dict:
+        with self._lock:
+            if name in self._metadata:
+                return self._metadata[name]
+        meta = serializer.load_metadata(os.path.join(self.directory, name))
+        with self._lock:
+            self._metadata[name] = meta
+        return meta
+
+    def tags(self, name: str) -> List[str]:
+        return _tag_names(self.metadata(name).get("dataset", {}).get("tag_list"))
+
+    def target_tags(self, name: str) -> List[str]:
+        dataset = self.metadata(name).get("dataset", {})
+        return _tag_names(dataset.get("target_tag_list")) or self.tags(name)
+
+    def frequency(self, name: str):
+        resolution = self.metadata(name).get("dataset", {}).get("resolution")
+        return None if resolution is None else pd.tseries.frequencies.to_offset(resolution)
+
+
+# ------------------------------------------------------------------------------------------------ the two POST views
+def _extract_X_y(store: ModelStore, name: str, json: Optional[dict], files: Optional[Dict[str, bytes]]):
+    """(X, y) frames of a request -- JSON ``{"X": ..., "y": ...}`` or parquet parts -- or a 400 ``Reply`` (utils.py:250-330)."""
+    payload = json if json is not None else (files or {})
+    if "X" not in payload:
+        return Reply(400, {"message": 'Cannot predict without "X"'})
+    load = dataframe_from_dict if json is not None else dataframe_from_parquet_bytes
+    X = load(payload["X"])
+    y = payload.get("y")
+    if y is not None:
+        y = load(y)
+    tags, targets = store.tags(name), store.target_tags(name)
+    X = verify_dataframe(X, tags) if tags else X
+    if isinstance(X, Reply):
+        return X
+    if y is not None and targets:
+        y = verify_dataframe(y, targets)
+        if isinstance(y, Reply):
+            return y
+    return X, y
+
+
+def _respond(frame: pd.DataFrame, fmt: Optional[str], start: float) -> Reply:
+    if fmt == "parquet":
+        return Reply(200, dataframe_into_parquet_bytes(frame))
+    return Reply(200, {"data": dataframe_to_dict(frame), "time-seconds": f"{timeit.default_timer() - start:.4f}"})
+
+
+def anomaly_prediction(store: ModelStore, name: str, json: Optional[dict] = None, files: Optional[Dict[str, bytes]] = None,
+                       all_columns: bool = False, fmt: Optional[str] = None) -> Reply:
+    """``POST .../<name>/anomaly/prediction`` (anomaly.py:28-122): the anomaly frame of the request's X against its y."""
+    start = timeit.default_timer()
+    try:
+        model = store.model(name)
+    except FileNotFoundError as e:
+        return Reply(404, {"message": str(e)})
+    xy = _extract_X_y(store, name, json, files)
+    if isinstance(xy, Reply):
+        return xy
+    X, y = xy
+    if y is None:
+        return Reply(400, {"message": "Cannot perform anomaly without 'y' to compare against."})
+    not_a_detector = Reply(422, {"message": f"Model is not an AnomalyDetector, it is of type: {type(model)}"})
+    if not hasattr(type(model), "anomaly"):
+        return not_a_detector
+    try:
+        frame = model.anomaly(X, y, frequency=store.frequency(name))
+    except AttributeError:  # as the reference: also what a detector without its required thresholds answers (anomaly.py:46-52)
+        return not_a_detector
+    if not all_columns:
+        frame = frame.drop(columns=[c for c in frame.columns if c[0] in DELETED_FROM_RESPONSE_COLUMNS])
+    return _respond(frame, fmt, start)
+
+
+def prediction(store: ModelStore, name: str, json: Optional[dict] = None, files: Optional[Dict[str, bytes]] = None,
+               fmt: Optional[str] = None) -> Reply:
+    """``POST .../<name>/prediction`` (base.py:30-120): model input and output side by side, no scoring."""
+    start = timeit.default_timer()
+    try:
+        model = store.model(name)
+    except FileNotFoundError as e:
+        return Reply(404, {"message": str(e)})
+    xy = _extract_X_y(store, name, json, files)
+    if isinstance(xy, Reply):
+        return xy
+    X, _ = xy
+    try:
+        output = model.predict(X) if hasattr(type(model), "predict") or hasattr(model, "predict") else model.transform(X)
+    except ValueError as err:
+        return Reply(400, {"error": f"ValueError: {err}"})
+    except Exception:  # the reference answers every other failure of the model the same way (base.py:83-91)
+        return Reply(400, {"error": "Something unexpected happened; check your input data"})
+    frame = model_utils.make_base_dataframe(tags=store.tags(name) or list(X.columns), model_input=X.values, model_output=output,
+                                            target_tag_list=store.target_tags(name) or None, index=X.index)
+    return _respond(frame, fmt, start)

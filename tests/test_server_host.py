@@ -1,0 +1,122 @@
+"""
+Wire formats, the resident model store and the request checks of the serving path (no GPU needed).  Modelled on
+tests/gordo/server/test_utils.py (frame <-> dict / parquet round trips, _verify_dataframe) and
+tests/gordo/server/test_gordo_server.py / test_anomaly_view.py (status codes of malformed requests).
+"""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from sklearn.preprocessing import MinMaxScaler
+
+from gordo_components_b200 import serializer, server
+from gordo_components_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+from gordo_components_b200.machine.model.models import KerasAutoEncoder
+
+TAGS = ["tag-0", "tag-1", "tag-2"]
+
+
+def _frame(rows=6, cols=TAGS, seed=0):
+    idx = pd.date_range("2016-01-01", periods=rows, freq="10min", tz="UTC")
+    return pd.DataFrame(np.random.default_rng(seed).random((rows, len(cols))), columns=cols, index=idx)
+
+
+def _anomaly_like_frame():
+    X = _frame()
+    columns = pd.MultiIndex.from_tuples([("start", ""), ("model-output", "tag-0"), ("model-output", "tag-1"), ("total-anomaly-scaled", "")])
+    data = pd.DataFrame(np.arange(24.0).reshape(6, 4), columns=columns, index=X.index)
+    data[("start", "")] = [t.isoformat() for t in X.index]
+    return data
+
+
+def test_dict_round_trips():
+    """test_utils.py: multi-level frames, plain frames, integer indexes."""
+    df = _anomaly_like_frame()
+    as_dict = server.dataframe_to_dict(df)
+    json.dumps(as_dict)  # string keys only
+    assert set(as_dict) == {"start", "model-output", "total-anomaly-scaled"} and set(as_dict["model-output"]) == {"tag-0", "tag-1"}
+    back = server.dataframe_from_dict(as_dict)
+    assert back.index.equals(df.index)
+    np.testing.assert_array_equal(back["model-output"].values, df["model-output"].values)
+    np.testing.assert_array_equal(back["total-anomaly-scaled"].values.ravel(), df["total-anomaly-scaled"].values.ravel())
+    assert df.index.dtype != object  # the input frame's index is left alone
+
+    plain = _frame()
+    again = server.dataframe_from_dict(json.loads(json.dumps(server.dataframe_to_dict(plain))))
+    pd.testing.assert_frame_equal(again, plain, check_freq=False)
+    numbered = pd.DataFrame({"a": [1.0, 2.0, 3.0]}, index=[2, 0, 1])
+    back = server.dataframe_from_dict(json.loads(json.dumps(server.dataframe_to_dict(numbered))))
+    assert list(back.index) == [0, 1, 2] and list(back["a"]) == [2.0, 3.0, 1.0]  # integer index restored and sorted
+
+
+def test_parquet_round_trips():
+    for df in (_frame(), _anomaly_like_frame()):
+        buf = server.dataframe_into_parquet_bytes(df)
+        assert isinstance(buf, bytes) and buf[:4] == b"PAR1"
+        pd.testing.assert_frame_equal(server.dataframe_from_parquet_bytes(buf), df, check_freq=False)
+
+
+def test_verify_dataframe():
+    """test_utils.py::test_verify_dataframe: relabel, reorder / select, refuse."""
+    unlabeled = pd.DataFrame(np.zeros((2, 3)))
+    assert list(server.verify_dataframe(unlabeled, TAGS).columns) == TAGS and list(unlabeled.columns) == [0, 1, 2]
+    shuffled = _frame(cols=["tag-2", "extra", "tag-0", "tag-1"])
+    assert list(server.verify_dataframe(shuffled, TAGS).columns) == TAGS
+    wrong = server.verify_dataframe(pd.DataFrame(np.zeros((2, 4))), TAGS)
+    assert isinstance(wrong, server.Reply) and wrong.status == 400 and "Unexpected features" in wrong.body["message"]
+    multi = server.verify_dataframe(_anomaly_like_frame(), TAGS)
+    assert isinstance(multi, server.Reply) and multi.status == 400 and "multi-level" in multi.body["message"]
+
+
+@pytest.fixture
+def project(tmp_path):
+    meta = {"name": "machine-1", "dataset": {"tag_list": [{"name": t, "asset": None} for t in TAGS], "resolution": "10min"}}
+    serializer.dump(DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass")), str(tmp_path / "machine-1"), metadata=meta)
+    serializer.dump(MinMaxScaler().fit(np.random.random((5, 3))), str(tmp_path / "scaler-only"), metadata={"name": "scaler-only", "dataset": {"tag_list": TAGS, "target_tag_list": TAGS[:2]}})
+    os.makedirs(tmp_path / "not-a-model")
+    return str(tmp_path)
+
+
+def test_model_store(project):
+    store = server.ModelStore(project)
+    assert store.names() == ["machine-1", "scaler-only"]
+    assert store.model("machine-1") is store.model("machine-1")  # stays loaded
+    assert store.tags("machine-1") == TAGS and store.target_tags("machine-1") == TAGS
+    assert store.target_tags("scaler-only") == TAGS[:2] and store.frequency("scaler-only") is None
+    assert store.frequency("machine-1") == pd.tseries.frequencies.to_offset("10min")
+    with pytest.raises(FileNotFoundError):
+        store.model("not-a-model")
+    small = server.ModelStore(project, max_models=1)
+    first = small.model("machine-1")
+    small.model("scaler-only")
+    assert small.model("machine-1") is not first  # evicted and loaded again
+
+
+def test_request_checks_answer_like_the_reference(project):
+    """Status codes and messages of utils.extract_X_y / anomaly._create_anomaly_response, before any model arithmetic."""
+    store = server.ModelStore(project)
+    X = server.dataframe_to_dict(_frame())
+    missing = server.anomaly_prediction(store, "machine-1", json={"y": X})
+    assert missing.status == 400 and missing.body == {"message": 'Cannot predict without "X"'} and missing.content_type == "application/json"
+    assert server.anomaly_prediction(store, "machine-1", files={}).status == 400
+    no_y = server.anomaly_prediction(store, "machine-1", json={"X": X})
+    assert no_y.status == 400 and no_y.body == {"message": "Cannot perform anomaly without 'y' to compare against."}
+    wide = server.anomaly_prediction(store, "machine-1", json={"X": server.dataframe_to_dict(_frame(cols=TAGS + ["more"])), "y": X})
+    # a frame carrying all expected tags is reduced to them and reaches the model -- which has no thresholds yet: the detector's
+    # AttributeError is answered like the reference does (anomaly.py:46-52)
+    assert wide.status == 422
+    bad = server.anomaly_prediction(store, "machine-1", json={"X": server.dataframe_to_dict(_frame(cols=["a", "b"])), "y": X})
+    assert bad.status == 400 and "Unexpected features" in bad.body["message"]
+    bad_y = server.anomaly_prediction(store, "machine-1", files={"X": server.dataframe_into_parquet_bytes(_frame()),
+                                                                     "y": server.dataframe_into_parquet_bytes(_frame(cols=["a", "b"]))})
+    assert bad_y.status == 400 and "Unexpected features" in bad_y.body["message"]
+    not_detector = server.anomaly_prediction(store, "scaler-only", json={"X": X, "y": server.dataframe_to_dict(_frame(cols=TAGS[:2]))})
+    assert not_detector.status == 422 and "Model is not an AnomalyDetector" in not_detector.body["message"]
+    assert server.anomaly_prediction(store, "nope", json={"X": X, "y": X}).status == 404
+    assert server.prediction(store, "nope", json={"X": X}).status == 404
+    # a transformer-only model is served through transform (base.py / model_io.get_model_output)
+    ok = server.prediction(store, "scaler-only", json={"X": X})
+    assert ok.status == 200 and set(ok.body["data"]) == {"start", "end", "model-input", "model-output"} and float(ok.body["time-seconds"]) >= 0
+    assert set(ok.body["data"]["model-input"]) == set(TAGS) and set(ok.body["data"]["model-output"]) == {"0", "1", "2"}  # 3 outputs, 2 target names: positions
