@@ -1,0 +1,87 @@
+"""
+Build -> model directory -> ModelStore -> the two POST views, JSON and parquet, on the GPU
+(tests/gordo/server/test_anomaly_view.py:14-120, test_gordo_server.py).  Kept in a file of its own that sorts after the
+kernel parity tests.
+"""
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from test_gpu_builder import DETECTOR, _series
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    if not t.cuda.is_available():
+        pytest.skip("needs a B200")
+    import __graft_entry__ as ge
+
+    ge.build()
+    return t
+
+
+@pytest.fixture(scope="module")
+def engine(torch):
+    from gordo_components_b200 import engine as e
+
+    return e
+
+
+def test_built_models_answer_requests(engine, torch, tmp_path):
+    """Build -> directory -> ModelStore -> the two POST views, JSON and parquet (tests/gordo/server/test_anomaly_view.py:14-120)."""
+    from gordo_components_b200 import builder, server
+
+    N, T = 240, 4
+
+    class Dataset:
+        def __init__(self, frame):
+            self.frame = frame
+
+        def get_data(self):
+            return self.frame, self.frame
+
+        def get_metadata(self):
+            return {"rows": len(self.frame)}
+
+        def to_dict(self):
+            return {"type": "TimeSeriesDataset", "tag_list": [{"name": c, "asset": None} for c in self.frame.columns], "resolution": "10min"}
+
+    frames = {n: _series(N, T, seed) for seed, n in enumerate(["m-1", "m-2"])}
+    builder.FleetModelBuilder([{"name": n, "model": DETECTOR, "dataset": Dataset(f)} for n, f in frames.items()]).build(str(tmp_path))
+    store = server.ModelStore(str(tmp_path))
+    assert store.names() == ["m-1", "m-2"] and store.tags("m-2") == list(frames["m-2"].columns)
+    assert store.metadata("m-1")["metadata"]["build_metadata"]["dataset"]["dataset_meta"] == {"rows": N}
+
+    X = frames["m-2"].iloc[100:140].astype(np.float64)
+    want = store.model("m-2").anomaly(X, X, frequency=store.frequency("m-2"))
+    reply = server.anomaly_prediction(store, "m-2", json={"X": server.dataframe_to_dict(X), "y": server.dataframe_to_dict(X)})
+    assert reply.status == 200 and reply.content_type == "application/json" and float(reply.body["time-seconds"]) > 0
+    json.dumps(reply.body)
+    got = server.dataframe_from_dict(reply.body["data"])
+    assert set(got.columns.get_level_values(0)) == set(want.columns.get_level_values(0))
+    for block in ("model-output", "tag-anomaly-scaled", "total-anomaly-confidence", "anomaly-confidence"):
+        np.testing.assert_array_equal(got[block].values.ravel(), want[block].values.ravel())
+    assert list(got["start"].values.ravel()) == list(want["start"].values.ravel())
+
+    # parquet in, parquet out; unlabelled columns are accepted when the width fits (utils.py:206-247)
+    unlabelled = X.copy()
+    unlabelled.columns = [str(i) for i in range(T)]
+    files = {"X": server.dataframe_into_parquet_bytes(unlabelled), "y": server.dataframe_into_parquet_bytes(X)}
+    reply = server.anomaly_prediction(store, "m-2", files=files, fmt="parquet")
+    assert reply.status == 200 and reply.content_type == "application/octet-stream"
+    frame = server.dataframe_from_parquet_bytes(reply.body)
+    np.testing.assert_array_equal(frame["total-anomaly-scaled"].values.ravel(), want["total-anomaly-scaled"].values.ravel())
+    assert not any(c[0].startswith("smooth-") for c in frame.columns)
+
+    # the plain prediction view
+    reply = server.prediction(store, "m-1", json={"X": server.dataframe_to_dict(frames["m-1"].iloc[:10].astype(np.float64))})
+    assert reply.status == 200 and set(reply.body["data"]) == {"start", "end", "model-input", "model-output"}
+    out = server.dataframe_from_dict(reply.body["data"])
+    np.testing.assert_array_equal(out["model-output"].values.ravel(), store.model("m-1").predict(frames["m-1"].iloc[:10]).astype(np.float64).ravel())
+    assert server.anomaly_prediction(store, "m-1", json={"X": server.dataframe_to_dict(X[list(X.columns[:2])]), "y": server.dataframe_to_dict(X)}).status == 400
