@@ -39,42 +39,24 @@ class DefinitionTestModel:
 
 
 # ---------------------------------------------------------------- from_definition (test_serializer_from_definition.py:27-82)
-@pytest.mark.parametrize(
-    "definition",
-    [
-        """
-    sklearn.multioutput.MultiOutputRegressor:
-      estimator: sklearn.ensemble.RandomForestRegressor
-    """,
-        """
-    sklearn.multioutput.MultiOutputRegressor:
-      estimator:
-        sklearn.ensemble.RandomForestRegressor:
-          n_estimators: 20
-    """,
-        """
-    sklearn.multioutput.MultiOutputRegressor:
-      estimator:
-        sklearn.pipeline.Pipeline:
-            steps:
-                - sklearn.ensemble.RandomForestRegressor:
-                    n_estimators: 20
-    """,
-        """
-    sklearn.multioutput.MultiOutputRegressor:
-        estimator:
-            sklearn.pipeline.Pipeline:
-                steps:
-                    - sklearn.cluster.FeatureAgglomeration:
-                        n_clusters: 2
-                        pooling_func: numpy.mean
-                    - sklearn.linear_model.LinearRegression
-    """,
-    ],
-)
+MODELS_IN_PARAMS = [
+    # a class path as a parameter value -> default instance
+    {"sklearn.multioutput.MultiOutputRegressor": {"estimator": "sklearn.tree.DecisionTreeRegressor"}},
+    # a one-key mapping as a parameter value -> instance with kwargs
+    {"sklearn.multioutput.MultiOutputRegressor": {"estimator": {"sklearn.tree.DecisionTreeRegressor": {"max_depth": 3}}}},
+    # a Pipeline as a parameter value, itself holding definitions
+    {"sklearn.multioutput.MultiOutputRegressor": {"estimator": {"sklearn.pipeline.Pipeline": {"steps": [
+        "sklearn.preprocessing.StandardScaler", {"sklearn.linear_model.Ridge": {"alpha": 0.5}}]}}}},
+    # ... and a function path inside that Pipeline becomes the function
+    {"sklearn.multioutput.MultiOutputRegressor": {"estimator": {"sklearn.pipeline.Pipeline": {"steps": [
+        {"sklearn.cluster.FeatureAgglomeration": {"n_clusters": 3, "pooling_func": "numpy.median"}}, "sklearn.linear_model.LinearRegression"]}}}},
+]
+
+
+@pytest.mark.parametrize("definition", MODELS_IN_PARAMS)
 def test_models_taking_models_as_parameters(definition):
     X, y = np.random.random((10, 10)), np.random.random((10, 2))
-    model = serializer.from_definition(yaml.safe_load(definition))
+    model = serializer.from_definition(definition)
     assert isinstance(model, MultiOutputRegressor)
     model.fit(X, y)
     assert model.predict(X).shape == (10, 2)
@@ -108,55 +90,52 @@ def _all_kinds():
             yield cls_name, kind
 
 
+# the same estimator graph twice: every keyword spelled out (as into_definition writes it), and the short list forms
 FULL = """
 sklearn.pipeline.Pipeline:
+    memory:
+    verbose: false
     steps:
-        - sklearn.decomposition.PCA:
-            n_components: 2
-            copy: true
-            whiten: false
-            svd_solver:  auto
-            tol: 0.0
-            iterated_power: auto
-            random_state:
         - sklearn.preprocessing._function_transformer.FunctionTransformer:
             func: gordo.machine.model.transformer_funcs.general.multiply_by
             kw_args:
-                factor: 1
+                factor: 2
         - sklearn.pipeline.FeatureUnion:
+            n_jobs: 1
+            transformer_weights:
             transformer_list:
-            - sklearn.decomposition.PCA:
-                n_components: 3
             - sklearn.pipeline.Pipeline:
+                memory:
                 steps:
                 - sklearn.preprocessing.MinMaxScaler:
-                    feature_range:
-                    - 0
-                    - 1
+                    feature_range: [-1, 1]
                     copy: true
                 - sklearn.decomposition.TruncatedSVD:
                     n_components: 2
-                memory:
-            n_jobs: 1
-            transformer_weights:
+            - sklearn.decomposition.PCA:
+                n_components: 3
+                whiten: false
+                random_state:
+        - sklearn.decomposition.PCA:
+            n_components: 4
         - gordo.machine.model.models.{cls}:
             kind: {kind}
 """
 SHORT = """
 sklearn.pipeline.Pipeline:
-    - sklearn.decomposition.PCA:
-        n_components: 2
-    - sklearn.preprocessing._function_transformer.FunctionTransformer:
+    - sklearn.preprocessing.FunctionTransformer:
         func: gordo.machine.model.transformer_funcs.general.multiply_by
-        kw_args:
-            factor: 1
+        kw_args: {{factor: 2}}
     - sklearn.pipeline.FeatureUnion:
-        - sklearn.decomposition.PCA:
-            n_components: 3
         - sklearn.pipeline.Pipeline:
-            - sklearn.preprocessing.MinMaxScaler
+            - sklearn.preprocessing.MinMaxScaler:
+                feature_range: [-1, 1]
             - sklearn.decomposition.TruncatedSVD:
                 n_components: 2
+        - sklearn.decomposition.PCA:
+            n_components: 3
+    - sklearn.decomposition.PCA:
+        n_components: 4
     - gordo.machine.model.models.{cls}:
         kind: {kind}
 """
@@ -168,14 +147,13 @@ def test_pipeline_definitions_for_every_registered_kind(template, cls_name, kind
     """test_serializer_from_definition.py:84-272: reference class paths resolve to this package's estimators."""
     pipe = serializer.from_definition(yaml.safe_load(template.format(cls=cls_name, kind=kind)))
     assert isinstance(pipe, Pipeline) and [name for name, _ in pipe.steps] == ["step_0", "step_1", "step_2", "step_3"]
-    pca, func, union, model = (s for _, s in pipe.steps)
-    assert isinstance(pca, PCA) and pca.n_components == 2
-    assert isinstance(func, FunctionTransformer) and func.func is multiply_by and func.kw_args == {"factor": 1}
-    assert isinstance(union, FeatureUnion) and len(union.transformer_list) == 2
-    assert isinstance(union.transformer_list[0][1], PCA) and union.transformer_list[0][1].n_components == 3
-    inner = union.transformer_list[1][1]
+    func, union, pca, model = (s for _, s in pipe.steps)
+    assert isinstance(func, FunctionTransformer) and func.func is multiply_by and func.kw_args == {"factor": 2}
+    assert isinstance(union, FeatureUnion) and [n for n, _ in union.transformer_list] == ["step_0", "step_1"]
+    inner, inner_pca = (t for _, t in union.transformer_list)
     assert isinstance(inner, Pipeline) and isinstance(inner.steps[0][1], MinMaxScaler) and isinstance(inner.steps[1][1], TruncatedSVD)
-    assert inner.steps[0][1].feature_range == (0, 1)  # a YAML list became the tuple sklearn expects
+    assert inner.steps[0][1].feature_range == (-1, 1)  # a YAML list became the tuple sklearn expects
+    assert isinstance(inner_pca, PCA) and inner_pca.n_components == 3 and isinstance(pca, PCA) and pca.n_components == 4
     assert type(model).__name__ == cls_name and type(model).__module__ == "gordo_components_b200.machine.model.models"
     assert model.kind == kind
     # and back (test_serializer_into_definition.py:191-298)
