@@ -390,6 +390,15 @@ class FleetModelBuilder:
         if len(set(names)) != len(names):
             raise ValueError("machine names must be unique")
 
+    def shard(self, rank: int, world: int) -> "FleetModelBuilder":
+        """
+        This rank's contiguous block of the project (``fleet.partition``): machines are independent, so a multi-GPU build is
+        ``FleetModelBuilder(machines).shard(rank, world).build(output_dir)`` in every process, with no collective at all.
+        """
+        from . import fleet
+
+        return FleetModelBuilder([self.machines[i] for i in fleet.partition(len(self.machines), world)[rank]])
+
     def build(self, output_dir: Optional[str] = None) -> List[Tuple[Any, dict]]:
         results: List[Optional[Tuple[Any, dict]]] = [None] * len(self.machines)
         buckets: Dict[tuple, List[_Canonical]] = {}

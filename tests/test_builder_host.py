@@ -171,3 +171,13 @@ def test_machine_validation_and_datasets():
     out = builder._machine_out({"name": "n", "model": AE, "dataset": DS(), "metadata": {"user_defined": {"k": 1}}}, {"model": {}, "dataset": {}})
     assert out["dataset"] == {"type": "DS"} and out["metadata"]["user_defined"] == {"k": 1} and out["metadata"]["build_metadata"] == {"model": {}, "dataset": {}}
     assert out["evaluation"]["cv_mode"] == "full_build"
+
+
+def test_shards_cover_the_project_once():
+    machines = [_machine(f"m-{i}", rows=40) for i in range(11)]
+    full = builder.FleetModelBuilder(machines)
+    for world in (1, 2, 4, 8, 16):
+        names = [m["name"] for r in range(world) for m in full.shard(r, world).machines]
+        assert names == [m["name"] for m in machines]  # contiguous blocks, in order, nothing twice
+        sizes = [len(full.shard(r, world).machines) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
