@@ -154,6 +154,140 @@ def kfcv_fixture(name, n_rows, n_tags, window, method, q, seed):
     print(name, "ok", frame.shape)
 
 
+# ------------------------------------------------------------------------------------------------ the path's callers
+# definitions whose class paths exist here (sklearn / numpy only): the reference expands them with its own serializer
+CALLER_DEFINITIONS = [
+    "sklearn.preprocessing.MinMaxScaler",
+    {"sklearn.preprocessing.MinMaxScaler": {"feature_range": [-1, 1]}},
+    {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler", {"sklearn.decomposition.PCA": {"n_components": 2}}]}},
+    {"sklearn.pipeline.Pipeline": ["sklearn.preprocessing.StandardScaler", {"sklearn.linear_model.Ridge": {"alpha": 0.5}}]},
+    {"sklearn.pipeline.Pipeline": {"steps": [
+        {"sklearn.preprocessing.FunctionTransformer": {"func": "numpy.log1p", "inverse_func": "numpy.expm1"}},
+        {"sklearn.pipeline.FeatureUnion": {"transformer_list": [
+            {"sklearn.decomposition.PCA": {"n_components": 3}},
+            {"sklearn.pipeline.Pipeline": ["sklearn.preprocessing.MinMaxScaler", {"sklearn.decomposition.TruncatedSVD": {"n_components": 2}}]}]}},
+        "sklearn.linear_model.LinearRegression"]}},
+    {"sklearn.multioutput.MultiOutputRegressor": {"estimator": "sklearn.tree.DecisionTreeRegressor"}},
+    {"sklearn.multioutput.MultiOutputRegressor": {"estimator": {"sklearn.tree.DecisionTreeRegressor": {"max_depth": 3}}}},
+    {"sklearn.compose.TransformedTargetRegressor": {"transformer": "sklearn.preprocessing.MinMaxScaler", "regressor": {
+        "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.RobustScaler", {"sklearn.linear_model.Ridge": {"alpha": 2.0}}]}}}},
+    {"sklearn.pipeline.Pipeline": {"steps": [{"sklearn.cluster.FeatureAgglomeration": {"n_clusters": 2, "pooling_func": "numpy.median"}},
+                                             "sklearn.linear_model.LinearRegression"], "memory": None, "verbose": True}},
+]
+
+BUILD_MODEL = {"sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler", {"sklearn.linear_model.Ridge": {"alpha": 0.1}}]}}
+BUILD_EVALUATIONS = {
+    "default": {"cv_mode": "full_build", "scoring_scaler": "sklearn.preprocessing.MinMaxScaler",
+                "metrics": ["explained_variance_score", "r2_score", "mean_squared_error", "mean_absolute_error"]},
+    "five_folds_unscaled": {"cv_mode": "full_build", "scoring_scaler": None, "metrics": ["sklearn.metrics.r2_score", "max_error" if False else "mean_absolute_error"],
+                            "cv": {"sklearn.model_selection.TimeSeriesSplit": {"n_splits": 5}}, "seed": 3},
+    "cv_only": {"cv_mode": "cross_val_only", "scoring_scaler": "sklearn.preprocessing.RobustScaler", "metrics": ["mean_squared_error"]},
+}
+
+
+def _jsonable(obj):
+    if isinstance(obj, dict):
+        return {str(k): _jsonable(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_jsonable(v) for v in obj]
+    if isinstance(obj, (np.floating, np.integer)):
+        return obj.item()
+    if isinstance(obj, (pd.Timestamp,)):
+        return str(obj)
+    if hasattr(obj, "to_dict") and not isinstance(obj, (pd.DataFrame, pd.Series)):
+        return _jsonable(obj.to_dict())
+    return obj
+
+
+def build_frame(rows=240, tags=4, seed=11):
+    rng = np.random.default_rng(seed)
+    t = np.linspace(0, 20, rows)[:, None]
+    values = (0.5 + 0.4 * np.sin(t * rng.uniform(0.5, 2, tags) + rng.uniform(0, 3, tags)) + rng.normal(0, 0.05, (rows, tags))) * rng.uniform(1, 40, tags) + rng.uniform(-5, 100, tags)
+    values[:, -1] = 3.25  # a constant tag: the zero-variance conventions of the ratio metrics
+    idx = pd.date_range("2020-03-01", periods=rows, freq="10min", tz="UTC")
+    return pd.DataFrame(values, index=idx, columns=[f"TAG {i}" for i in range(tags)])
+
+
+def callers_fixture():
+    """Golden outputs of the reference's serializer, builder, server wire formats and InfImputer (tests/golden/callers.json + callers.npz)."""
+    from oracle.reference_loader import load_reference_callers
+
+    rc = load_reference_callers()
+    out, arrays = {}, {}
+
+    # ---- serializer: into_definition(from_definition(d)), the expansion `gordo build` applies before hashing (cli.py:142-144)
+    out["expansions"] = [{"definition": d, "expanded": _jsonable(rc.into_definition(rc.from_definition(d)))} for d in CALLER_DEFINITIONS]
+
+    # ---- builder: ModelBuilder._build (build_model.py:192-339) on stand-in Machine objects
+    frame = build_frame()
+    out["build"] = {}
+    for name, evaluation in BUILD_EVALUATIONS.items():
+        class Dataset:
+            def get_data(self):
+                return frame, frame
+
+            def get_metadata(self):
+                return {"rows": len(frame)}
+
+        rc.GordoBaseDataset.registry["fixture"] = Dataset()
+        machine = rc.Record(name="fixture-machine", project_name="p", model=BUILD_MODEL, evaluation=dict(evaluation), runtime={},
+                            dataset=rc.Record(key="fixture"), metadata=rc.Record(user_defined={"k": 1}))
+        builder = rc.ModelBuilder.__new__(rc.ModelBuilder)
+        builder.machine, builder.back_compatibles, builder.default_data_provider = machine, None, None
+        model, built = builder._build()
+        block = _jsonable(built.metadata.build_metadata)
+        for k in ("model_creation_date", "model_training_duration_sec"):
+            block["model"].pop(k, None)
+        block["model"]["cross_validation"].pop("cv_duration_sec", None)
+        block["dataset"].pop("query_duration_sec", None)
+        out["build"][name] = {"evaluation": evaluation, "build_metadata": block}
+        if evaluation["cv_mode"] == "full_build":
+            arrays[f"build_{name}_prediction"] = np.asarray(model.predict(frame), dtype=np.float64)
+    arrays["build_frame"] = frame.values
+    out["build_model"] = BUILD_MODEL
+    out["default_evaluation"] = rc.default_evaluation
+    out["build_frame"] = {"rows": len(frame), "columns": list(frame.columns), "start": str(frame.index[0]), "freq": "10min", "seed": 11}
+
+    # ---- server wire formats (gordo/server/utils.py:47-247)
+    idx = pd.date_range("2016-01-01", periods=4, freq="10min", tz="UTC")
+    cols = pd.MultiIndex.from_tuples([("start", ""), ("model-output", "tag 0"), ("model-output", "tag 1"), ("total-anomaly-scaled", "")])
+    multi = pd.DataFrame(np.arange(16.0).reshape(4, 4) / 7.0, columns=cols, index=idx)
+    multi[("start", "")] = [t.isoformat() for t in idx]
+    plain = pd.DataFrame(np.arange(8.0).reshape(4, 2) / 3.0, columns=["a", "b"], index=idx)
+    numbered = pd.DataFrame({"a": [1.5, 2.5, 3.5]}, index=[2, 0, 1])
+    out["wire"] = {"multi": rc.dataframe_to_dict(multi), "plain": rc.dataframe_to_dict(plain), "numbered": _jsonable(rc.dataframe_to_dict(numbered))}
+    back = rc.dataframe_from_dict(json.loads(json.dumps(out["wire"]["multi"])))
+    out["wire"]["multi_back"] = {"columns": [list(c) for c in back.columns], "index": [str(t) for t in back.index],
+                                 "model_output": back["model-output"].values.tolist()}
+    nb = rc.dataframe_from_dict(json.loads(json.dumps(out["wire"]["numbered"])))
+    out["wire"]["numbered_back"] = {"index": [int(i) for i in nb.index], "a": nb["a"].tolist()}
+    expected = ["tag-0", "tag-1", "tag-2"]
+    verify = {}
+    for case, df in (("unlabelled", pd.DataFrame(np.zeros((2, 3)))), ("shuffled_superset", pd.DataFrame(np.zeros((2, 4)), columns=["tag-2", "x", "tag-0", "tag-1"])),
+                     ("too_wide", pd.DataFrame(np.zeros((2, 4)))), ("multi_level", multi)):
+        res = rc.verify_dataframe(df, expected)
+        verify[case] = {"columns": [str(c) for c in res.columns]} if isinstance(res, pd.DataFrame) else {"status": res[-1], "message": res[0]["message"]}
+    out["wire"]["verify"] = verify
+
+    # ---- InfImputer (gordo/machine/model/transformers/imputer.py:12-127)
+    rng = np.random.default_rng(5)
+    for dtype in ("float32", "float64"):
+        base = rng.random((50, 6)).astype(dtype) * 10 - 3
+        flat = base.ravel()
+        flat[rng.integers(0, flat.size, 30)] = np.inf
+        flat[rng.integers(0, flat.size, 30)] = -np.inf
+        arrays[f"imputer_{dtype}_input"] = base.copy()
+        arrays[f"imputer_{dtype}_minmax"] = rc.InfImputer(strategy="minmax", delta=2.0).fit_transform(base.copy())
+        arrays[f"imputer_{dtype}_extremes"] = rc.InfImputer(strategy="extremes").fit_transform(base.copy())
+        arrays[f"imputer_{dtype}_filled"] = rc.InfImputer(inf_fill_value=99.0, neg_inf_fill_value=-99.0, strategy=None).fit_transform(base.copy())
+        arrays[f"imputer_{dtype}_half"] = rc.InfImputer(inf_fill_value=99.0, delta=0.5).fit_transform(base.copy())
+
+    with open(os.path.join(HERE, "callers.json"), "w") as f:
+        json.dump(out, f, indent=1, default=str)
+    np.savez_compressed(os.path.join(HERE, "callers.npz"), **arrays)
+    print("callers ok:", len(out["expansions"]), "expansions;", {k: len(v["build_metadata"]["model"]["cross_validation"]["scores"]) for k, v in out["build"].items()})
+
+
 if __name__ == "__main__":
     dims_fixture()
     kfcv_fixture("kfcv_smm", 300, 3, 12, "smm", 0.99, seed=6)
@@ -164,3 +298,4 @@ if __name__ == "__main__":
     anomaly_fixture("anomaly_ewma", 200, 4, 12, "ewma", False, seed=3)
     anomaly_fixture("ffnet_anomaly", 400, 8, None, None, True, base="net", seed=4)
     anomaly_fixture("ffnet_anomaly_t64", 200, 64, None, None, True, base="net", seed=5)
+    callers_fixture()
