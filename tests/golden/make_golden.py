@@ -243,6 +243,19 @@ def callers_fixture():
         out["build"][name] = {"evaluation": evaluation, "build_metadata": block}
         if evaluation["cv_mode"] == "full_build":
             arrays[f"build_{name}_prediction"] = np.asarray(model.predict(frame), dtype=np.float64)
+    # the same build with the model wrapped in the reference's DiffBasedAnomalyDetector: thresholds land in model_meta
+    detector_model = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": BUILD_MODEL}}
+    machine = rc.Record(name="fixture-detector", project_name="p", model=detector_model, evaluation=dict(BUILD_EVALUATIONS["default"]), runtime={},
+                        dataset=rc.Record(key="fixture"), metadata=rc.Record(user_defined={}))
+    builder = rc.ModelBuilder.__new__(rc.ModelBuilder)
+    builder.machine, builder.back_compatibles, builder.default_data_provider = machine, None, None
+    model, built = builder._build()
+    block = _jsonable(built.metadata.build_metadata)
+    out["build_detector"] = {"model": detector_model, "scores": block["model"]["cross_validation"]["scores"], "model_offset": block["model"]["model_offset"],
+                             "model_meta": _jsonable(block["model"]["model_meta"])}
+    anomaly = model.anomaly(frame.iloc[-50:], frame.iloc[-50:], frequency=pd.Timedelta("10min"))
+    arrays["build_detector_total_confidence"] = np.asarray(anomaly["total-anomaly-confidence"], dtype=np.float64).ravel()
+    arrays["build_detector_tag_scaled"] = np.asarray(anomaly["tag-anomaly-scaled"], dtype=np.float64)
     arrays["build_frame"] = frame.values
     out["build_model"] = BUILD_MODEL
     out["default_evaluation"] = rc.default_evaluation

@@ -85,3 +85,46 @@ def test_built_models_answer_requests(engine, torch, tmp_path):
     out = server.dataframe_from_dict(reply.body["data"])
     np.testing.assert_array_equal(out["model-output"].values.ravel(), store.model("m-1").predict(frames["m-1"].iloc[:10]).astype(np.float64).ravel())
     assert server.anomaly_prediction(store, "m-1", json={"X": server.dataframe_to_dict(X[list(X.columns[:2])]), "y": server.dataframe_to_dict(X)}).status == 400
+
+
+def test_detector_build_equals_the_reference_build(engine, torch):
+    """
+    ModelBuilder on a DiffBasedAnomalyDetector around a scikit-learn model, against the reference's ModelBuilder._build with the
+    reference's own detector (tests/golden/callers.json "build_detector", produced by tests/golden/make_golden.py): the scores come
+    from the same CPU predictions (1e-9); thresholds and anomaly columns pass through this package's float32 kernels (1e-4).
+    """
+    import os
+
+    from gordo_components_b200 import builder
+
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    with open(os.path.join(golden, "callers.json")) as f:
+        meta = json.load(f)
+    arrays = np.load(os.path.join(golden, "callers.npz"))
+    info, want = meta["build_frame"], meta["build_detector"]
+    frame = pd.DataFrame(arrays["build_frame"], index=pd.date_range(info["start"], periods=info["rows"], freq=info["freq"]), columns=info["columns"])
+    model, built = builder.ModelBuilder({"name": "fixture-detector", "model": want["model"], "dataset": (frame, frame),
+                                         "evaluation": meta["build"]["default"]["evaluation"]}).build()
+    got = built["metadata"]["build_metadata"]["model"]
+    assert got["model_offset"] == want["model_offset"] == 0
+    assert list(got["cross_validation"]["scores"]) == list(want["scores"])
+    for key, stats in want["scores"].items():
+        for stat, value in stats.items():
+            np.testing.assert_allclose(got["cross_validation"]["scores"][key][stat], value, rtol=1e-9, atol=1e-12, err_msg=f"{key} {stat}")
+    mm, ref = got["model_meta"], want["model_meta"]
+    assert set(mm) == set(ref)
+    # the targets sit at magnitude ~100: one float32 ulp there is 7.6e-6, which is the absolute uncertainty of every |prediction - target|
+    # the thresholds are taken from (measured on this fixture in numpy float32: <= 5e-6 absolute, up to 8e-4 relative on the small ones)
+    ULP = 2e-5
+    np.testing.assert_allclose(mm["feature-thresholds"], ref["feature-thresholds"], rtol=1e-4, atol=ULP)
+    np.testing.assert_allclose(mm["aggregate-threshold"], ref["aggregate-threshold"], rtol=2e-3)
+    for fold, value in ref["aggregate-thresholds-per-fold"].items():
+        np.testing.assert_allclose(mm["aggregate-thresholds-per-fold"][fold], value, rtol=2e-3)
+    for tag, folds in ref["feature-thresholds-per-fold"].items():
+        for fold, value in folds.items():
+            np.testing.assert_allclose(mm["feature-thresholds-per-fold"][tag][fold], value, rtol=1e-4, atol=ULP)
+    anomaly = model.anomaly(frame.iloc[-50:], frame.iloc[-50:], frequency=pd.Timedelta("10min"))
+    scale = float(np.abs(arrays["build_detector_tag_scaled"]).max())
+    np.testing.assert_allclose(np.asarray(anomaly["tag-anomaly-scaled"], dtype=np.float64), arrays["build_detector_tag_scaled"], rtol=1e-4, atol=1e-4 * scale)
+    np.testing.assert_allclose(np.asarray(anomaly["total-anomaly-confidence"], dtype=np.float64).ravel(), arrays["build_detector_total_confidence"],
+                               rtol=5e-3, atol=1e-4 * float(arrays["build_detector_total_confidence"].max()))
