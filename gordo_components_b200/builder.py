@@ -409,7 +409,12 @@ class FleetModelBuilder:
             else:
                 buckets.setdefault(c.bucket(), []).append(c)
         for members in buckets.values():
-            for c, built in zip(members, self._build_bucket(members)):
+            try:
+                built_bucket = self._build_bucket(members)
+            except Exception as exc:  # e.g. an architecture the batched fit kernel cannot hold: the machines still get built, one by one
+                logger.warning("batched build of %d machines failed (%s: %s); building them one at a time", len(members), type(exc).__name__, exc)
+                built_bucket = [ModelBuilder(c.machine).build() for c in members]
+            for c, built in zip(members, built_bucket):
                 results[c.index] = built
         if output_dir is not None:
             for model, machine in results:

@@ -181,3 +181,32 @@ def test_shards_cover_the_project_once():
         assert names == [m["name"] for m in machines]  # contiguous blocks, in order, nothing twice
         sizes = [len(full.shard(r, world).machines) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_fleet_builder_control_flow(monkeypatch, tmp_path):
+    """Bucketing, result order, per-machine fallback and the directory layout, with the two GPU entry points replaced."""
+    calls = []
+
+    def fake_bucket(members):
+        calls.append([c.machine["name"] for c in members])
+        if len(members[0].X) == 300:
+            raise RuntimeError("does not fit")
+        return [(f"batched:{c.machine['name']}", builder._machine_out(c.machine, {"model": {}, "dataset": {}})) for c in members]
+
+    def fake_single(self, output_dir=None):
+        calls.append(("single", self.machine["name"]))
+        return f"single:{self.machine['name']}", builder._machine_out(self.machine, {"model": {}, "dataset": {}})
+
+    monkeypatch.setattr(builder.FleetModelBuilder, "_build_bucket", staticmethod(fake_bucket))
+    monkeypatch.setattr(builder.ModelBuilder, "build", fake_single)
+    kfcv = {"gordo.machine.model.anomaly.diff.DiffBasedKFCVAnomalyDetector": {"base_estimator": AE}}
+    machines = [_machine("a"), _machine("k", model=kfcv), _machine("big-1", rows=300), _machine("b"), _machine("big-2", rows=300)]
+    results = builder.FleetModelBuilder(machines).build(str(tmp_path))
+    assert [m for m, _ in results] == ["batched:a", "single:k", "single:big-1", "batched:b", "single:big-2"]
+    assert calls == [("single", "k"), ["a", "b"], ["big-1", "big-2"], ("single", "big-1"), ("single", "big-2")]
+    import os
+
+    from gordo_components_b200 import serializer
+
+    assert sorted(os.listdir(tmp_path)) == ["a", "b", "big-1", "big-2", "k"]
+    assert serializer.load(str(tmp_path / "big-2")) == "single:big-2" and serializer.load_metadata(str(tmp_path / "a"))["name"] == "a"
