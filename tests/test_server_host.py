@@ -120,3 +120,61 @@ def test_request_checks_answer_like_the_reference(project):
     ok = server.prediction(store, "scaler-only", json={"X": X})
     assert ok.status == 200 and set(ok.body["data"]) == {"start", "end", "model-input", "model-output"} and float(ok.body["time-seconds"]) >= 0
     assert set(ok.body["data"]["model-input"]) == set(TAGS) and set(ok.body["data"]["model-output"]) == {"0", "1", "2"}  # 3 outputs, 2 target names: positions
+
+
+class EchoDetector:
+    """A stand-in with the detector's serving surface (picklable, no GPU): output = 2 * input, one smoothed block."""
+
+    def predict(self, X):
+        return np.asarray(getattr(X, "values", X), dtype=np.float32) * 2
+
+    def anomaly(self, X, y, frequency=None):
+        from gordo_components_b200.machine.model import utils as model_utils
+
+        out = self.predict(X)
+        frame = model_utils.make_base_dataframe(tags=list(X.columns), model_input=X.values, model_output=out, target_tag_list=list(y.columns),
+                                                index=X.index, frequency=frequency)
+        diff = np.abs(out - y.values).astype(np.float32)
+        for j, tag in enumerate(y.columns):
+            frame[("tag-anomaly-scaled", tag)] = diff[:, j]
+            frame[("smooth-tag-anomaly-scaled", tag)] = diff[:, j] * 0.5
+        frame[("total-anomaly-scaled", "")] = (diff ** 2).mean(axis=1)
+        frame[("smooth-total-anomaly-scaled", "")] = frame[("total-anomaly-scaled", "")] * 0.5
+        return frame
+
+
+def test_views_json_and_parquet_with_a_stand_in_model(tmp_path):
+    """The whole request path around the model: JSON and parquet in and out, dropped smooth columns, the plain prediction view."""
+    meta = {"name": "echo", "dataset": {"tag_list": TAGS, "resolution": "10min"}}
+    serializer.dump(EchoDetector(), str(tmp_path / "echo"), metadata=meta)
+    store = server.ModelStore(str(tmp_path))
+    X = _frame(rows=8)
+    want = store.model("echo").anomaly(X, X, frequency=store.frequency("echo"))
+
+    reply = server.anomaly_prediction(store, "echo", json={"X": server.dataframe_to_dict(X), "y": server.dataframe_to_dict(X)})
+    assert reply.status == 200 and reply.content_type == "application/json"
+    body = json.loads(json.dumps(reply.body))  # what actually travels
+    assert float(body["time-seconds"]) >= 0 and not any(k.startswith("smooth-") for k in body["data"])
+    got = server.dataframe_from_dict(body["data"])
+    np.testing.assert_array_equal(got["model-output"].values, want["model-output"].values)
+    np.testing.assert_array_equal(got["total-anomaly-scaled"].values.ravel(), want["total-anomaly-scaled"].values.ravel())
+    assert list(got["end"].values.ravel()) == list(want["end"].values.ravel()) and got.index.equals(want.index)
+    everything = server.anomaly_prediction(store, "echo", json={"X": server.dataframe_to_dict(X), "y": server.dataframe_to_dict(X)}, all_columns=True)
+    assert {"smooth-tag-anomaly-scaled", "smooth-total-anomaly-scaled"} <= set(everything.body["data"])
+
+    unlabelled = X.copy()
+    unlabelled.columns = [str(i) for i in range(len(TAGS))]
+    files = {"X": server.dataframe_into_parquet_bytes(unlabelled), "y": server.dataframe_into_parquet_bytes(X)}
+    reply = server.anomaly_prediction(store, "echo", files=files, fmt="parquet")
+    assert reply.status == 200 and reply.content_type == "application/octet-stream"
+    frame = server.dataframe_from_parquet_bytes(reply.body)
+    assert not any(c[0].startswith("smooth-") for c in frame.columns)
+    pd.testing.assert_frame_equal(frame, want.drop(columns=[c for c in want.columns if c[0].startswith("smooth-")]), check_freq=False)
+
+    reply = server.prediction(store, "echo", json={"X": server.dataframe_to_dict(X)})
+    assert reply.status == 200 and set(reply.body["data"]) == {"start", "end", "model-input", "model-output"}
+    out = server.dataframe_from_dict(json.loads(json.dumps(reply.body))["data"])
+    np.testing.assert_array_equal(out["model-output"].values, X.values.astype(np.float32) * 2)
+    np.testing.assert_array_equal(out["model-input"].values, X.values)
+    as_parquet = server.prediction(store, "echo", files={"X": server.dataframe_into_parquet_bytes(X)}, fmt="parquet")
+    assert server.dataframe_from_parquet_bytes(as_parquet.body)["model-output"].shape == (8, 3)
