@@ -460,3 +460,130 @@ class FleetModelBuilder:
             dataset_block = {"query_duration_sec": c.query_sec, "dataset_meta": c.dataset_meta}
             out.append((model, _machine_out(c.machine, {"model": model_block, "dataset": dataset_block})))
         return out
+
+
+# ------------------------------------------------------------------------------------------------ from a project config
+MACHINE_YAML_FIELDS = ("model", "dataset", "evaluation", "metadata", "runtime")  # may arrive as YAML text blocks (machine/constants.py)
+
+
+def patch_dict(original: dict, patch: dict) -> dict:
+    """``original`` with every path of ``patch`` added or replaced, nothing removed (workflow_generator/helpers.py:16-45)."""
+    out = copy.deepcopy(original)
+    for key, value in (patch or {}).items():
+        if isinstance(value, dict) and isinstance(out.get(key), dict):
+            out[key] = patch_dict(out[key], value)
+        else:
+            out[key] = copy.deepcopy(value)
+    return out
+
+
+class RandomDataset:
+    """
+    Stand-in for gordo-core's ``RandomDataProvider`` datasets [3P, not installed]: seeded uniform noise for the configured tags on
+    the regular ``resolution`` grid between ``train_start_date`` and ``train_end_date``.  It exists so that project configs written
+    for the reference's tests and docs (``data_provider: {type: RandomDataProvider}``) build here; real data comes from any object
+    with ``get_data()`` passed through ``datasets=``.
+    """
+
+    def __init__(self, **config):
+        self.config = config
+        tags = config.get("tag_list") or config.get("tags")
+        if not tags:
+            raise ValueError("dataset needs 'tag_list' (or 'tags')")
+        self.tag_list = [t["name"] if isinstance(t, dict) else str(t) for t in tags]
+        targets = config.get("target_tag_list") or tags
+        self.target_tag_list = [t["name"] if isinstance(t, dict) else str(t) for t in targets]
+        self.resolution = config.get("resolution", "10min")
+        self.start, self.end = pd.Timestamp(config["train_start_date"]), pd.Timestamp(config["train_end_date"])
+        if self.start.tzinfo is None or self.end.tzinfo is None:
+            raise ValueError("train_start_date / train_end_date need a timezone")
+        if self.start >= self.end:
+            raise ValueError(f"train_end_date ({self.end}) must be after train_start_date ({self.start})")
+
+    def get_data(self):
+        import zlib
+
+        index = pd.date_range(self.start, self.end, freq=pd.tseries.frequencies.to_offset(self.resolution), inclusive="left")
+        names = list(dict.fromkeys(self.tag_list + self.target_tag_list))
+        rng = np.random.default_rng(zlib.crc32("|".join(names).encode()))
+        data = pd.DataFrame(rng.random((len(index), len(names))), index=index, columns=names)
+        return data[self.tag_list], data[self.target_tag_list]
+
+    def get_metadata(self):
+        return {"tag_list": self.tag_list, "target_tag_list": self.target_tag_list, "resolution": self.resolution,
+                "train_start_date": str(self.start), "train_end_date": str(self.end)}
+
+    def to_dict(self):
+        out = {k: v for k, v in self.config.items() if k != "tags"}
+        out.update({"type": "RandomDataset", "tag_list": self.tag_list, "target_tag_list": self.target_tag_list, "resolution": self.resolution})
+        return out
+
+
+def _dataset_from_config(config: dict):
+    provider = (config.get("data_provider") or {}).get("type", "") if isinstance(config.get("data_provider"), dict) else ""
+    if str(config.get("type", "")).endswith("RandomDataset") or str(provider).endswith("RandomDataProvider"):
+        return RandomDataset(**config)
+    raise TypeError("only RandomDataset / RandomDataProvider dataset configs can be instantiated here; pass datasets= (name or machine -> an "
+                    "object with get_data()) for real data")
+
+
+def machines_from_config(config, project_name: str = "local-build", datasets=None) -> List[dict]:
+    """
+    The machines of a project config -- ``{"machines": [...], "globals": {...}}`` as a dict or YAML text -- in the dict form the
+    builders take, with the globals folded in the way ``Machine.from_config`` does (gordo/machine/machine.py:78-149: the machine's
+    model wins, runtime and evaluation are globals patched by the machine, dataset is the machine patched by the globals) over
+    the default evaluation of ``NormalizedConfig``.  ``datasets``: mapping name -> dataset object, or a callable taking the machine.
+    """
+    import yaml
+
+    if isinstance(config, str):
+        config = yaml.safe_load(config)
+    if not isinstance(config, dict) or not config.get("machines"):
+        raise ValueError("config needs a non-empty 'machines' list")
+
+    def parsed(block: dict) -> dict:
+        out = dict(block or {})
+        for field in MACHINE_YAML_FIELDS:
+            if isinstance(out.get(field), str):
+                out[field] = yaml.safe_load(out[field])
+        return out
+
+    config_globals = patch_dict({"evaluation": DEFAULT_EVALUATION}, parsed(config.get("globals")))
+    machines = []
+    for conf in config["machines"]:
+        conf = parsed(conf)
+        if "name" not in conf:
+            raise ValueError("every machine needs a name")
+        model = conf.get("model") or config_globals.get("model")
+        if model is None:
+            raise ValueError("model is empty")
+        machine = {
+            "name": conf["name"],
+            "project_name": conf.get("project_name") or project_name,
+            "model": model,
+            "runtime": patch_dict(config_globals.get("runtime") or {}, conf.get("runtime") or {}),
+            "evaluation": patch_dict(config_globals.get("evaluation") or {}, conf.get("evaluation") or {"cv_mode": "full_build"}),
+            "metadata": {"user_defined": {"global-metadata": config_globals.get("metadata") or {}, "machine-metadata": conf.get("metadata") or {}}},
+        }
+        dataset_config = patch_dict(conf.get("dataset") or {}, config_globals.get("dataset") or {})
+        if callable(datasets):
+            machine["dataset"] = datasets({**machine, "dataset": dataset_config})
+        elif datasets is not None and conf["name"] in datasets:
+            machine["dataset"] = datasets[conf["name"]]
+        else:
+            machine["dataset"] = _dataset_from_config(dataset_config)
+        machines.append(machine)
+    return machines
+
+
+def local_build(config_str, datasets=None, batched: bool = True):
+    """
+    Build the model(s) of a bare gordo config locally and yield ``(model, machine)`` per machine, in config order
+    (gordo/builder/local_build.py:15-80).  ``batched=False`` builds one machine at a time like the reference does.
+    """
+    machines = machines_from_config(config_str, datasets=datasets)
+    if batched:
+        yield from FleetModelBuilder(machines).build()
+    else:
+        for machine in machines:
+            yield ModelBuilder(machine).build()

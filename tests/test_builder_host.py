@@ -210,3 +210,88 @@ def test_fleet_builder_control_flow(monkeypatch, tmp_path):
 
     assert sorted(os.listdir(tmp_path)) == ["a", "b", "big-1", "big-2", "k"]
     assert serializer.load(str(tmp_path / "big-2")) == "single:big-2" and serializer.load_metadata(str(tmp_path / "a"))["name"] == "a"
+
+
+PROJECT = """
+machines:
+  - name: pipe-1
+    dataset: |
+      tags: [TAG 1, TAG 2, TAG 3]
+      target_tag_list: [TAG 3, TAG 4]
+      train_start_date: '2019-01-01T00:00:00+00:00'
+      train_end_date: '2019-01-03T00:00:00+00:00'
+      data_provider:
+        type: RandomDataProvider
+    metadata: |
+      information: first machine
+    model: |
+      sklearn.pipeline.Pipeline:
+        steps:
+          - sklearn.preprocessing.MinMaxScaler
+          - sklearn.multioutput.MultiOutputRegressor:
+              estimator: sklearn.linear_model.LinearRegression
+  - name: pipe-2
+    dataset:
+      tag_list: [A, B]
+      train_start_date: '2019-01-01T00:00:00+00:00'
+      train_end_date: '2019-01-02T00:00:00+00:00'
+      type: RandomDataset
+    evaluation:
+      cv_mode: cross_val_only
+      metrics: [r2_score]
+    runtime:
+      builder: {resources: {limits: {memory: 1}}}
+globals:
+  model:
+    sklearn.linear_model.Ridge:
+      alpha: 0.5
+  dataset:
+    resolution: 30min
+  evaluation:
+    scoring_scaler: null
+  metadata:
+    owner: someone
+  runtime:
+    builder: {resources: {limits: {memory: 9, cpu: 2}}}
+"""
+
+
+def test_machines_from_config_and_local_build():
+    """gordo/builder/local_build.py + Machine.from_config (machine.py:78-149): text blocks, globals, build of scikit-learn models."""
+    machines = builder.machines_from_config(PROJECT, project_name="proj")
+    one, two = machines
+    assert [m["name"] for m in machines] == ["pipe-1", "pipe-2"] and one["project_name"] == "proj"
+    assert "sklearn.pipeline.Pipeline" in one["model"] and two["model"] == {"sklearn.linear_model.Ridge": {"alpha": 0.5}}  # machine model wins, else globals
+    assert one["evaluation"] == {**builder.DEFAULT_EVALUATION, "scoring_scaler": None}
+    assert two["evaluation"]["cv_mode"] == "cross_val_only" and two["evaluation"]["metrics"] == ["r2_score"] and two["evaluation"]["scoring_scaler"] is None
+    assert one["metadata"]["user_defined"] == {"global-metadata": {"owner": "someone"}, "machine-metadata": {"information": "first machine"}}
+    assert two["runtime"] == {"builder": {"resources": {"limits": {"memory": 1, "cpu": 2}}}}  # globals patched by the machine
+    X, y = one["dataset"].get_data()
+    assert list(X.columns) == ["TAG 1", "TAG 2", "TAG 3"] and list(y.columns) == ["TAG 3", "TAG 4"]
+    assert len(X) == 96 and X.index[0] == pd.Timestamp("2019-01-01T00:00:00+00:00") and (X.index[1] - X.index[0]) == pd.Timedelta("30min")  # resolution from globals
+    np.testing.assert_array_equal(X["TAG 3"].values, y["TAG 3"].values)
+    pd.testing.assert_frame_equal(one["dataset"].get_data()[0], X)  # seeded by the tag names
+    assert one["dataset"].to_dict()["tag_list"] == ["TAG 1", "TAG 2", "TAG 3"] and one["dataset"].to_dict()["resolution"] == "30min"
+
+    built = list(builder.local_build(PROJECT))
+    assert [m["name"] for _, m in built] == ["pipe-1", "pipe-2"]
+    (model1, m1), (model2, m2) = built
+    scores = m1["metadata"]["build_metadata"]["model"]["cross_validation"]["scores"]
+    assert "r2-score-TAG-4" in scores and "mean-absolute-error" in scores and len(scores) == 4 * 3
+    assert m1["metadata"]["build_metadata"]["model"]["model_offset"] == 0 and model1.predict(X).shape == (96, 2)
+    assert m1["dataset"]["tag_list"] == ["TAG 1", "TAG 2", "TAG 3"] and m1["metadata"]["build_metadata"]["dataset"]["dataset_meta"]["resolution"] == "30min"
+    assert set(m2["metadata"]["build_metadata"]["model"]) == {"cross_validation"} and set(m2["metadata"]["build_metadata"]["model"]["cross_validation"]["scores"]) == {"r2-score-A", "r2-score-B", "r2-score"}
+    assert [m["name"] for _, m in builder.local_build(PROJECT, batched=False)] == ["pipe-1", "pipe-2"]
+
+    # real data comes in through datasets=; configs without a random provider say so
+    frame = _frame(60, 2)
+    custom = builder.machines_from_config({"machines": [{"name": "x", "model": AE, "dataset": {"tag_list": ["a"]}}]}, datasets={"x": (frame, frame)})
+    assert custom[0]["dataset"][0] is frame
+    called = builder.machines_from_config({"machines": [{"name": "x", "model": AE}]}, datasets=lambda m: ("made for", m["name"]))
+    assert called[0]["dataset"] == ("made for", "x")
+    with pytest.raises(TypeError):
+        builder.machines_from_config({"machines": [{"name": "x", "model": AE, "dataset": {"tag_list": ["a"], "type": "TimeSeriesDataset"}}]})
+    for bad in ({"machines": []}, {"machines": [{"model": AE}]}, {"machines": [{"name": "x"}]}):
+        with pytest.raises(ValueError):
+            builder.machines_from_config(bad)
+    assert builder.patch_dict({"a": {"b": 1, "c": 2}}, {"a": {"b": 10}, "d": 4}) == {"a": {"b": 10, "c": 2}, "d": 4}
