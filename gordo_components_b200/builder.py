@@ -467,7 +467,10 @@ MACHINE_YAML_FIELDS = ("model", "dataset", "evaluation", "metadata", "runtime") 
 
 
 def patch_dict(original: dict, patch: dict) -> dict:
-    """``original`` with every path of ``patch`` added or replaced, nothing removed (workflow_generator/helpers.py:16-45)."""
+    """
+    ``original`` with every path of ``patch`` added or replaced, nothing removed (workflow_generator/helpers.py:16-45).  Lists are
+    replaced as a whole; the reference patches through dictdiffer [3P, not installed here], which walks lists element by element.
+    """
     out = copy.deepcopy(original)
     for key, value in (patch or {}).items():
         if isinstance(value, dict) and isinstance(out.get(key), dict):
