@@ -37,7 +37,8 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NTHREADS = 576;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17: control of slot 0 / 1
+constexpr int NSLOT = 3;       // tiles in flight
+constexpr int NTHREADS = 608;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17,18: control of slot 0 / 1 / 2
 constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;  // in both groups: warp%4 = TMEM lane quadrant, (warp/4)%2 = column half
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
@@ -45,7 +46,7 @@ constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 row
 constexpr int W = 64;                  // widest feature / hidden width; narrower tag counts T (multiples of 4) ride in zero-padded columns
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
-constexpr uint32_t COL_D = 0, COL_ALB = 64, COL_ABF = 96, SLOT_COLS = 128, COL_DX = 256, TMEM_COLS = 512;  // 256 columns still free: two more slots
+constexpr uint32_t COL_D = 0, COL_ALB = 64, COL_ABF = 96, SLOT_COLS = 128, COL_DX = 384, TMEM_COLS = 512;  // 3 slots + 2 spare accumulators (COL_DX, COL_DX + 64)
 // layers >= 1 keep their two packed-FP16 operand images (32 columns each) where layer 0's TF32-hi image was
 constexpr uint32_t COL_A1 = COL_ALB, COL_A2 = COL_ABF;
 // COL_DX: spare accumulator (absolute column) that receives the OUTPUT layer of slot-1 tiles, so slot 1 can start its next
@@ -76,7 +77,7 @@ constexpr int DEFAULT_NE = 0;
 
 // debug timeline (gb_debug_set_trace): three recorder threads of CTA 0 (epilogue tid 0, the two control leaders) stamp
 // events into shared memory (one clock read + one store each) and flush them to global memory when the kernel ends
-constexpr int TRACE_SLOTS = 320;
+constexpr int TRACE_SLOTS = 64;  // (scratch/dbg_trace.py must be told: the buffer layout depends on it)
 __device__ __forceinline__ void trace_ev(const TcArgs& a, unsigned long long* ring, int& cnt, int code, int tile, int layer, int slot) {
   if (a.trace == nullptr || blockIdx.x != 0 || cnt >= TRACE_SLOTS || (tile < a.trace_from && tile >= a.trace_head)) return;
   ring[cnt++] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(tile & 0xfff) << 12) | ((layer & 0xf) << 8) | ((slot & 0xf) << 4) | (code & 0xf);  // code < 16
@@ -343,13 +344,13 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t sbase = smem_u32(smem);
   // mbarriers, two of each (tile slot 0/1): x_full, a_ready, d_ready (hidden-layer MMAs), f_ready (output-layer MMAs), d_free
   const uint32_t bars = sbase + a.bar_ofs;
-  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64, BW = 80;  // BW: bulk copy of a slot's parameter vector
+  const uint32_t BX = 0, BA = 24, BD = 48, BF = 72, BE = 96, BW = 120;  // 8 bytes per tile slot each; BW: bulk copy of a slot's parameter vector
   const bool has_y = a.y != nullptr;
   const int TP = FULL ? W : a.T;  // tags per row = row pitch of x / y / per-tag outputs
   const int L = a.last_layer + 1;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bars + BX + 8 * s, 1);
       mbar_init(bars + BA + 8 * s, MAIN_WARPS);
       mbar_init(bars + BD + 8 * s, 1);
@@ -370,7 +371,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
   // phase parities (each role uses the subset it waits on)
-  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0, ph_w = 0;
+  uint32_t ph_x = 0, ph_d = 0, ph_f = 0;  // one parity bit per tile slot
+  uint32_t ph_a = 0, ph_e = 0, ph_w = 0;
   int cur_slot = -1;
   // Work split.  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so work items are as long as
   // possible: whole jobs, dealt round-robin in waves of gridDim.x (neighbouring CTAs stream neighbouring jobs: cutting the whole
@@ -486,7 +488,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)s * TILE), bar_x);
         tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)s * TILE), bar_x);
       }
-      for (int t = s; t < n_tiles; t += 2) {
+      for (int t = s; t < n_tiles; t += NSLOT) {
         for (int l = 0; l < L; ++l) {
           const int Np = a.Np[l], k8 = a.k8[l], k16 = a.k16[l];
           const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(l == 0 ? 1 : 0, Np);  // kind::f16 inputs: BF16 (layer 0) / FP16
@@ -497,18 +499,18 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           ph_a ^= 1;
           // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
           // layer (wait before layer 0); slot 1 sends only its output layer to the spare accumulator (wait before that layer)
-          if (t >= 2 && l == (s == 0 ? 0 : L - 1)) {
+          if (t >= NSLOT && l == (s == 0 ? 0 : L - 1)) {
             mbar_wait(bar_e, ph_e);
             ph_e ^= 1;
           }
-          const uint32_t dcol = (s == 1 && l == L - 1) ? tmem + COL_DX : tb + COL_D;
+          const uint32_t dcol = (s >= 1 && l == L - 1) ? tmem + COL_DX + (uint32_t)(s - 1) * 64u : tb + COL_D;
           tc_fence_after();
           if (leader && s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
           if (leader) {
-            if (l == 1 && t + 2 < n_tiles) {  // layer 0's MMAs (which read the x boxes) are complete => the boxes are free
+            if (l == 1 && t + NSLOT < n_tiles) {  // layer 0's MMAs (which read the x boxes) are complete => the boxes are free
               mbar_expect_tx(bar_x, 2 * BOX_BYTES);
-              tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
-              tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
+              tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)(t + NSLOT) * TILE), bar_x);
+              tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + NSLOT) * TILE), bar_x);
             }
             // straight-line issue (K <= 64 => at most 8 / 8 / 4 steps): measured 49 cycles per MMA against 73 for a rolled loop
             if (l == 0) {
@@ -545,17 +547,17 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
       // =========================================== layer-epilogue warps (SFU-bound): hidden layers only
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
+      for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
         // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
         for (int l = 0; l + 1 < L; ++l) {
           const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
           const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < NSLOT; ++s) {
             if (t0 + s >= n_tiles) continue;
             if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, s ? ph_d1 : ph_d0);
-            if (s) ph_d1 ^= 1; else ph_d0 ^= 1;
+            mbar_wait(bars + BD + 8 * s, (ph_d >> s) & 1u);
+            ph_d ^= 1u << s;
             tc_fence_after();
             if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
             const uint32_t sl = lane_base + s * SLOT_COLS;
@@ -589,8 +591,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // Only the accumulator has to change layout (TMEM gives one thread = one row): it goes once through this warp's swizzled
       // staging box; y is loaded straight into the transposed layout and every output column is formed and stored there.
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * 2 * OBOX_BYTES;  // transpose staging of the accumulator
-      const uint32_t ybox = stage + OBOX_BYTES;                                           // y rows of the second tile of a pair
+      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * OBOX_BYTES;  // transpose staging of the accumulator
       float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2 halves][2][TILE] row sums
       const int tr = lane >> 3, tc = lane & 7;
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
@@ -602,10 +603,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 
       // x -> A operand of layer 0 of tile `tt` (slot tt & 1): these warps have the slack, the layer warps do not
       auto split_x = [&](int tt) {
-        const int s = tt & 1;
+        const int s = tt % NSLOT;
         const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-        mbar_wait(bars + BX + 8 * s, s ? ph_x1 : ph_x0);
-        if (s) ph_x1 ^= 1; else ph_x0 ^= 1;
+        mbar_wait(bars + BX + 8 * s, (ph_x >> s) & 1u);
+        ph_x ^= 1u << s;
 #pragma unroll
         for (int piece = 0; piece < 4; ++piece) {  // 8 columns at a time keeps the register footprint small (y rows are live)
           float v[8];
@@ -625,7 +626,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // accumulator of the output layer -> this warp's staging box ("one thread = one row" -> row-major lines), accumulator freed
       auto park = [&](int s, int t) {
         float acc[32];
-        const uint32_t sl = lane_base + (s == 1 ? COL_DX : COL_D) + h * 32;
+        const uint32_t sl = lane_base + (s >= 1 ? COL_DX + (uint32_t)(s - 1) * 64u : COL_D) + h * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
 #pragma unroll
@@ -644,7 +645,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       float4 yt[8];
       // every output column of tile t from the staged accumulator; y comes from registers (first tile of a pair) or from the
       // warp's y box in shared memory (second tile, fetched with cp.async while the first was being written)
-      auto emit = [&](int t, bool y_smem) {
+      auto emit = [&](int t) {
         const int trow = row_begin + t * TILE;
         const int nrows = min(TILE, row_end - trow);
         const long grow0 = job.out_row + trow;
@@ -656,7 +657,6 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           float4 yh, yv = yt[i];
           const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
-          if (y_smem) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yv.x), "=f"(yv.y), "=f"(yv.z), "=f"(yv.w) : "r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u));
           if (!in_cols) yv = make_float4(0.f, 0.f, 0.f, 0.f);  // zero-padded columns (T < 64): model output is 0 there too
           yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
           if (!in_cols) yh = make_float4(0.f, 0.f, 0.f, 0.f);     // columns beyond T: the accumulator holds stale values there
@@ -676,7 +676,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
         __syncwarp();  // staging box reusable
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t & 1);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t % NSLOT);
         if (totals) {
           // row sums: 8 lanes (tc) hold the 32 columns of this half; halves meet in shared memory
 #pragma unroll
@@ -700,55 +700,57 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
           named_bar_sync(1 + q, 64);
         }
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t & 1);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t % NSLOT);
+      };
+
+      // y rows of tile t -> registers (transposed layout), requested as early as the registers are free
+      auto load_y = [&](int t) {
+        const int trow = row_begin + t * TILE;
+        const int nrows = min(TILE, row_end - trow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = min(q * 32 + i * 4 + tr, nrows - 1);
+          yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto wait_f = [&](int s, int t) {
+        mbar_wait(bars + BF + 8 * s, (ph_f >> s) & 1u);
+        ph_f ^= 1u << s;
+        tc_fence_after();
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
       };
 
       split_x(0);
       if (n_tiles > 1) split_x(1);
+      if (n_tiles > 2) split_x(2);
 
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-        const bool two = t0 + 1 < n_tiles;
-        if (has_y) {
-          if (two) {  // y rows of the pair's second tile -> y box (asynchronously; needed only after the first tile is written)
-            const int trow = row_begin + (t0 + 1) * TILE;
-            const int nrows = min(TILE, row_end - trow);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + tr;
-              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)TP + (in_cols ? h * 32 + tc * 4 : 0);
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-          }
-          const int trow = row_begin + t0 * TILE;
-          const int nrows = min(TILE, row_end - trow);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {  // y rows of the first tile -> registers, requested before its accumulator is ready
-            const int r = min(q * 32 + i * 4 + tr, nrows - 1);
-            yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed both slots their next tiles
+      for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
+        const int n_in = min(NSLOT, n_tiles - t0);
+        if (has_y) load_y(t0);  // requested before the tile's accumulator is ready
+        // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed every slot its next tile
         if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t0, L - 1, 0);
-        mbar_wait(bars + BF, ph_f0);
-        ph_f0 ^= 1;
-        tc_fence_after();
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0, L - 1, 0);
+        wait_f(0, t0);
         park(0, t0);
-        if (t0 + 2 < n_tiles) split_x(t0 + 2);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
-        if (two) {
-          mbar_wait(bars + BF + 8, ph_f1);
-          ph_f1 ^= 1;
-          tc_fence_after();
-          if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0 + 1, L - 1, 1);
-          if (t0 + 3 < n_tiles) split_x(t0 + 3);  // slot 1's output sits in the spare accumulator until the stores below are done
+        if (t0 + NSLOT < n_tiles) split_x(t0 + NSLOT);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
+        if (n_in > 1) {
+          wait_f(1, t0 + 1);
+          if (t0 + NSLOT + 1 < n_tiles) split_x(t0 + NSLOT + 1);  // slots 1 and 2 keep their output in a spare accumulator until parked below
+        }
+        if (n_in > 2) {
+          wait_f(2, t0 + 2);
+          if (t0 + NSLOT + 2 < n_tiles) split_x(t0 + NSLOT + 2);
         }
         // ---- then the stores
-        emit(t0, false);
-        if (two) {
+        emit(t0);
+        if (n_in > 1) {
+          if (has_y) load_y(t0 + 1);
           park(1, t0 + 1);
-          asm volatile("cp.async.wait_all;" ::: "memory");
-          emit(t0 + 1, true);
+          emit(t0 + 1);
+        }
+        if (n_in > 2) {
+          if (has_y) load_y(t0 + 2);
+          park(2, t0 + 2);
+          emit(t0 + 2);
         }
       }
     }
@@ -879,10 +881,10 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.pair_ofs = ofs; ofs += 4 * TILE * 4;
   a.bar_ofs = ofs; ofs += 128;
   ofs = gb::round_up(ofs, 1024);
-  a.xbox_ofs = ofs; ofs += 4 * BOX_BYTES;            // two tile slots x two 32-column boxes
-  a.stage_ofs = ofs; ofs += OUT_WARPS * 2 * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box + a y box of the same shape
+  a.xbox_ofs = ofs; ofs += 2 * NSLOT * BOX_BYTES;    // NSLOT tile slots x two 32-column boxes
+  a.stage_ofs = ofs; ofs += OUT_WARPS * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box
   const size_t smem = (size_t)ofs;
-  GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
+  GB_REQUIRE(smem + 4 * TRACE_SLOTS * 8 + 64 <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
 
   int dev = 0, sms = 148;
   GB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -892,7 +894,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.n_jobs = n_jobs;
   a.pstride = (long)gb_ffnet_param_stride(net);
   a.param_bytes = (int)(gb_ffnet_param_stride(net) * sizeof(float));  // stride is a multiple of 4 floats
-  GB_REQUIRE(a.param_bytes <= 4 * BOX_BYTES + OUT_WARPS * 2 * OBOX_BYTES, GB_E_SMEM, "parameter vector of %d bytes exceeds the staging scratch", a.param_bytes);
+  GB_REQUIRE(a.param_bytes <= 2 * NSLOT * BOX_BYTES + OUT_WARPS * OBOX_BYTES, GB_E_SMEM, "parameter vector of %d bytes exceeds the staging scratch", a.param_bytes);
   a.bulk_params = (reinterpret_cast<uintptr_t>(params) % 16 == 0) ? 1 : 0;
   a.params = params; a.jobs = jobs; a.y = y; a.scale = scale; a.feat_thr = feat_thr; a.agg_thr = agg_thr;
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_conf = out_conf;

@@ -100,6 +100,8 @@ src = src[:a] + '''              for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi:
 ''' + src[b:]
 sub("          const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);",
     "          const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128), dhb = make_bdesc(sbase + a.whb_ofs, lbo, 128);")
+# the x boxes are re-armed after layer 0 (at l == 1): a one-layer stack would never prefetch
+sub("  if (L > MAXL || net->dims[0] != net->dims[L] ||", "  if (L < 2 || L > MAXL || net->dims[0] != net->dims[L] ||")
 # ---- host: room for the third image
 sub("    a.wlo_ofs[l] = ofs;\n    ofs += a.k16[l] * 16 * a.Np[l] * 2;\n",
     "    a.wlo_ofs[l] = ofs;\n    ofs += a.k16[l] * 16 * a.Np[l] * 2;\n    if (l == 0) {\n      a.whb_ofs = ofs;\n      ofs += a.k16[l] * 16 * a.Np[l] * 2;\n    }\n")
