@@ -336,11 +336,11 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         res = self._score(self, X, y, self.scaler, feat_thr, agg_thr)
 
         out = res["model-output"]
-        data = model_utils.make_base_dataframe(
+        index, frame_blocks, frame_cols = model_utils.base_blocks(
             tags=X.columns, model_input=X.values, model_output=out, target_tag_list=y.columns,
             index=getattr(X, "index", None), frequency=frequency,
         )
-        targets = list(data["model-output"].columns)
+        targets = [sub for top, sub in frame_cols if top == "model-output"]
         blocks, cols = [], []
 
         def add(name, per_tag):
@@ -367,9 +367,9 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             add("anomaly-confidence", True)
         if agg_thr is not None:
             add("total-anomaly-confidence", False)
-        extra = pd.DataFrame(np.concatenate(blocks, axis=1) if blocks else np.empty((len(data), 0)), index=data.index,
-                             columns=pd.MultiIndex.from_tuples(cols))
-        return pd.concat([data, extra], axis=1)
+        if blocks:  # all score columns travel as one float64 block
+            frame_blocks.append(np.concatenate(blocks, axis=1))
+        return model_utils.frame_from_blocks(index, frame_blocks, frame_cols + cols)
 
 
 class DiffBasedKFCVAnomalyDetector(DiffBasedAnomalyDetector):

@@ -282,3 +282,62 @@ def test_scaler_multiplier():
     np.testing.assert_allclose(_scaler_multiplier(RobustScaler().fit(y), 3), 1 / RobustScaler().fit(y).scale_, rtol=1e-6)
     with pytest.raises(ValueError):
         _scaler_multiplier(QuantileTransformer(n_quantiles=10).fit(y), 3)
+
+
+# ---------------------------------------------------------------- frame assembly fast paths
+def test_isoformat_equals_timestamp_isoformat():
+    """The arithmetic ISO formatter against pandas' own ``Timestamp.isoformat`` over the whole 0001..9999 range and the edges."""
+    rng = np.random.default_rng(0)
+    secs = np.concatenate([rng.integers(-62135596800, 253402300799, 5000),
+                           np.array([0, -1, 86399, 86400, -86400, 951782400, 951868800, 4107542400, 1582934400, -62135596800, 253402300799])])
+    for tz in (None, "UTC"):
+        idx = pd.DatetimeIndex(secs.astype("datetime64[s]"), tz=tz)
+        got = model_utils._isoformat(idx)
+        assert got.dtype == object and type(got[0]) is str
+        assert list(got) == [ts.isoformat() for ts in idx]
+    # anything the fast path does not cover falls back to the per-timestamp loop
+    for idx in (pd.date_range("2019-01-01", periods=3, freq="1500ms", tz="UTC"), pd.date_range("2019-03-30", periods=3, freq="12h", tz="Europe/Oslo"),
+                pd.date_range("2019-01-01", periods=0, freq="1h")):
+        assert list(model_utils._isoformat(idx)) == [ts.isoformat() for ts in idx]
+    assert model_utils._iso_seconds(np.array([253402300800]), True) is None  # year 10000
+
+
+@pytest.mark.parametrize("rows,offset,thresholds,window,index_kind", [(1, 0, True, None, "utc"), (40, 3, True, 5, "utc"), (25, 0, False, None, "range"),
+                                                                      (30, 2, False, 4, "naive"), (12, 0, True, None, "sub-second")])
+def test_anomaly_frame_assembly_with_a_mocked_score(rows, offset, thresholds, window, index_kind):
+    """
+    ``anomaly()`` builds its frame in one pass (cached column index, one concat); here the GPU score is replaced by fixed arrays and
+    the result is compared with the frame spelled out the slow way: base frame + one block per column group, concatenated.
+    """
+    T = 3
+    tags = [f"tag {i}" for i in range(T)]
+    idx = {"utc": pd.date_range("2019-01-01", periods=rows, freq="10min", tz="UTC"), "naive": pd.date_range("2019-01-01", periods=rows, freq="10min"),
+           "sub-second": pd.date_range("2019-01-01", periods=rows, freq="1500ms", tz="UTC"), "range": pd.RangeIndex(rows)}[index_kind]
+    rng = np.random.default_rng(rows)
+    X = pd.DataFrame(rng.random((rows, T)), index=idx, columns=tags)
+    det = DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass"), require_thresholds=thresholds, window=window,
+                                   smoothing_method="sma" if window else None)
+    if thresholds:
+        det.feature_thresholds_, det.aggregate_threshold_ = pd.Series(np.ones(T), index=tags), 0.5
+    n = rows - offset
+    res = {"model-output": rng.random((n, T)).astype(np.float32), "tag-anomaly-scaled": rng.random((n, T)).astype(np.float32),
+           "total-anomaly-scaled": rng.random(n).astype(np.float32), "tag-anomaly-unscaled": rng.random((n, T)).astype(np.float32),
+           "total-anomaly-unscaled": rng.random(n).astype(np.float32)}
+    if thresholds:
+        res.update({"anomaly-confidence": rng.random((n, T)).astype(np.float32), "total-anomaly-confidence": rng.random(n).astype(np.float32)})
+    det._score = lambda *a, **k: dict(res)
+    det._smoothing = lambda metric: np.asarray(metric, dtype=np.float32) * 0.5
+    freq = pd.Timedelta("10min")
+    got = det.anomaly(X, X, frequency=freq)
+
+    order = ["tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-unscaled"]
+    groups = list(order) + (["smooth-" + k for k in order] if window else []) + (["anomaly-confidence", "total-anomaly-confidence"] if thresholds else [])
+    pieces = [model_utils.make_base_dataframe(tags=tags, model_input=X.values, model_output=res["model-output"], target_tag_list=tags, index=idx, frequency=freq)]
+    for key in groups:
+        v = np.asarray(res[key[len("smooth-"):]] * 0.5 if key.startswith("smooth-") else res[key], dtype=np.float64)
+        cols = [(key, t) for t in tags] if v.ndim == 2 else [(key, "")]
+        pieces.append(pd.DataFrame(v.reshape(n, -1), index=pieces[0].index, columns=pd.MultiIndex.from_tuples(cols)))
+    want = pd.concat(pieces, axis=1)
+    assert list(got.columns) == list(want.columns) and list(got.dtypes) == list(want.dtypes) and len(got) == n
+    pd.testing.assert_frame_equal(got, want, check_exact=True, check_freq=False)
+    assert got.columns is not det.anomaly(X, X, frequency=freq).columns  # the cached column index is handed out as copies
