@@ -324,6 +324,13 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         thresholds exist]; with ``window`` + ``smoothing_method`` the four ``smooth-*`` blocks come before the confidences.
         Rows follow the model output (shorter than X for LSTM models).
         """
+        return model_utils.frame_from_blocks(*self.anomaly_blocks(X, y, frequency))
+
+    def anomaly_blocks(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None):
+        """
+        The anomaly frame before it becomes a DataFrame: ``(row index, [column blocks], [(top, sub) column names])``.  A caller that
+        only serialises the result (``server.anomaly_prediction``) reads the blocks directly and skips the frame.
+        """
         if not hasattr(X, "values"):
             raise ValueError("Unable to find X.values property")
         if self.require_thresholds and not any(hasattr(self, a) for a in ("feature_thresholds_", "aggregate_threshold_")):
@@ -369,7 +376,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             add("total-anomaly-confidence", False)
         if blocks:  # all score columns travel as one float64 block
             frame_blocks.append(np.concatenate(blocks, axis=1))
-        return model_utils.frame_from_blocks(index, frame_blocks, frame_cols + cols)
+        return index, frame_blocks, frame_cols + cols
 
 
 class DiffBasedKFCVAnomalyDetector(DiffBasedAnomalyDetector):

@@ -178,3 +178,45 @@ def test_views_json_and_parquet_with_a_stand_in_model(tmp_path):
     np.testing.assert_array_equal(out["model-input"].values, X.values)
     as_parquet = server.prediction(store, "echo", files={"X": server.dataframe_into_parquet_bytes(X)}, fmt="parquet")
     assert server.dataframe_from_parquet_bytes(as_parquet.body)["model-output"].shape == (8, 3)
+
+
+@pytest.mark.parametrize("rows,window,thresholds,index_kind", [(1, None, True, "utc"), (30, 5, True, "utc"), (12, 4, False, "naive"), (9, None, False, "range")])
+def test_json_reply_from_blocks_equals_the_frame_route(tmp_path, rows, window, thresholds, index_kind):
+    """
+    This package's detectors answer JSON requests from their column blocks (no DataFrame); the reply must be what the frame route
+    gives -- ``dataframe_to_dict(model.anomaly(...))`` minus the smooth columns unless ``all_columns``.  The GPU score is mocked.
+    """
+    T = 3
+    idx = {"utc": pd.date_range("2019-01-01", periods=rows, freq="10min", tz="UTC"), "naive": pd.date_range("2019-01-01", periods=rows, freq="10min"),
+           "range": pd.RangeIndex(rows)}[index_kind]
+    rng = np.random.default_rng(rows)
+    X = pd.DataFrame(rng.random((rows, T)), index=idx, columns=TAGS)
+    det = DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass"), require_thresholds=thresholds, window=window,
+                                   smoothing_method="sma" if window else None)
+    if thresholds:
+        det.feature_thresholds_, det.aggregate_threshold_ = pd.Series(np.ones(T), index=TAGS), 0.5
+    res = {"model-output": rng.random((rows, T)).astype(np.float32), "tag-anomaly-scaled": rng.random((rows, T)).astype(np.float32),
+           "total-anomaly-scaled": rng.random(rows).astype(np.float32), "tag-anomaly-unscaled": rng.random((rows, T)).astype(np.float32),
+           "total-anomaly-unscaled": rng.random(rows).astype(np.float32)}
+    if thresholds:
+        res.update({"anomaly-confidence": rng.random((rows, T)).astype(np.float32), "total-anomaly-confidence": rng.random(rows).astype(np.float32)})
+    serializer.dump(det, str(tmp_path / "m"), metadata={"name": "m", "dataset": {"tag_list": TAGS, "resolution": "10min"}})
+    store = server.ModelStore(str(tmp_path))
+    model = store.model("m")
+    model._score = lambda *a, **k: dict(res)
+    model._smoothing = lambda metric: np.asarray(metric, dtype=np.float32) * 0.5
+    if index_kind == "range":
+        payload = {"X": X.to_dict(), "y": X.to_dict()}
+        payload = json.loads(json.dumps({k: {c: {str(i): v for i, v in col.items()} for c, col in d.items()} for k, d in payload.items()}))
+    else:
+        payload = json.loads(json.dumps({"X": server.dataframe_to_dict(X), "y": server.dataframe_to_dict(X)}))
+    Xr = server.dataframe_from_dict(payload["X"])
+    frame = model.anomaly(Xr, Xr, frequency=store.frequency("m"))
+    for all_columns in (False, True):
+        reply = server.anomaly_prediction(store, "m", json=payload, all_columns=all_columns)
+        assert reply.status == 200
+        want = frame if all_columns else frame.drop(columns=[c for c in frame.columns if c[0] in server.DELETED_FROM_RESPONSE_COLUMNS])
+        assert json.dumps(reply.body["data"]) == json.dumps(server.dataframe_to_dict(want))
+        as_parquet = server.anomaly_prediction(store, "m", json=payload, all_columns=all_columns, fmt="parquet")
+        pd.testing.assert_frame_equal(server.dataframe_from_parquet_bytes(as_parquet.body), want, check_freq=False)
+    assert bool(window) == any(k.startswith("smooth-") for k in server.anomaly_prediction(store, "m", json=payload, all_columns=True).body["data"])
