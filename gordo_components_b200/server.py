@@ -261,6 +261,14 @@ def _extract_X_y(store: ModelStore, name: str, json: Optional[dict], files: Opti
     return X, y
 
 
+def _frame_is_from_blocks(model) -> bool:
+    """True when ``model.anomaly`` is this package's own (not overridden in a subclass): then ``anomaly_blocks`` is the same result."""
+    from .machine.model.anomaly.diff import DiffBasedAnomalyDetector
+
+    return isinstance(model, DiffBasedAnomalyDetector) and type(model).anomaly is DiffBasedAnomalyDetector.anomaly \
+        and type(model).anomaly_blocks is DiffBasedAnomalyDetector.anomaly_blocks
+
+
 def _respond(frame: pd.DataFrame, fmt: Optional[str], start: float) -> Reply:
     if fmt == "parquet":
         return Reply(200, dataframe_into_parquet_bytes(frame))
@@ -286,7 +294,7 @@ def anomaly_prediction(store: ModelStore, name: str, json: Optional[dict] = None
         return not_a_detector
     skip = () if all_columns else DELETED_FROM_RESPONSE_COLUMNS
     try:
-        if fmt != "parquet" and hasattr(type(model), "anomaly_blocks"):
+        if fmt != "parquet" and _frame_is_from_blocks(model):
             # JSON out of this package's detectors: straight from the column blocks, no DataFrame in between
             data = blocks_to_dict(*model.anomaly_blocks(X, y, frequency=store.frequency(name)), skip=skip)
             return Reply(200, {"data": data, "time-seconds": f"{timeit.default_timer() - start:.4f}"})

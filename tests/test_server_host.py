@@ -220,3 +220,19 @@ def test_json_reply_from_blocks_equals_the_frame_route(tmp_path, rows, window, t
         as_parquet = server.anomaly_prediction(store, "m", json=payload, all_columns=all_columns, fmt="parquet")
         pd.testing.assert_frame_equal(server.dataframe_from_parquet_bytes(as_parquet.body), want, check_freq=False)
     assert bool(window) == any(k.startswith("smooth-") for k in server.anomaly_prediction(store, "m", json=payload, all_columns=True).body["data"])
+
+
+def test_overridden_anomaly_is_respected(tmp_path):
+    """A subclass that changes ``anomaly`` is served through its own method, not through the column-block shortcut."""
+    serializer.dump(_Doubling(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass"), require_thresholds=False), str(tmp_path / "m"),
+                    metadata={"name": "m", "dataset": {"tag_list": TAGS}})
+    store = server.ModelStore(str(tmp_path))
+    assert not server._frame_is_from_blocks(store.model("m")) and server._frame_is_from_blocks(DiffBasedAnomalyDetector())
+    X = server.dataframe_to_dict(_frame())
+    reply = server.anomaly_prediction(store, "m", json={"X": X, "y": X})
+    assert reply.status == 200 and set(reply.body["data"]) == {"only"}
+
+
+class _Doubling(DiffBasedAnomalyDetector):
+    def anomaly(self, X, y, frequency=None):
+        return pd.DataFrame(X.values[:, :1] * 2, index=X.index, columns=pd.MultiIndex.from_tuples([("only", "")]))
