@@ -19,6 +19,7 @@ Nothing is copied: the reference files are executed where they lie.
 from __future__ import annotations
 
 import importlib
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -35,6 +36,7 @@ def reference_available() -> bool:
 
 def _ns_module(name: str, path: str | None = None) -> types.ModuleType:
     mod = types.ModuleType(name)
+    mod.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)  # importlib.util.find_spec() on a stub must not raise (torch probes for tensorflow)
     if path is not None:
         mod.__path__ = [path]  # namespace-style package; its __init__.py is skipped
     sys.modules[name] = mod
