@@ -338,10 +338,18 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
                 f"`require_thresholds={self.require_thresholds}` however `.cross_validate` needs to be called in order "
                 f"to calculate these thresholds before calling `.anomaly`"
             )
+        feat_thr, agg_thr = self._thresholds()
+        return self.blocks_from_scores(self._score(self, X, y, self.scaler, feat_thr, agg_thr), X, y, frequency)
+
+    def _thresholds(self):
         feat_thr = self.feature_thresholds_.values if getattr(self, "feature_thresholds_", None) is not None else None
         agg_thr = self.aggregate_threshold_ if getattr(self, "aggregate_threshold_", None) is not None else None
-        res = self._score(self, X, y, self.scaler, feat_thr, agg_thr)
+        return feat_thr, agg_thr
 
+    def blocks_from_scores(self, res: Dict[str, np.ndarray], X, y, frequency: Optional[timedelta] = None):
+        """``anomaly_blocks`` for score arrays that already exist (``res`` as ``_score`` returns it, e.g. out of a request coalescer)."""
+        feat_thr, agg_thr = self._thresholds()
+        res = dict(res)
         out = res["model-output"]
         index, frame_blocks, frame_cols = model_utils.base_blocks(
             tags=X.columns, model_input=X.values, model_output=out, target_tag_list=y.columns,

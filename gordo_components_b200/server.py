@@ -239,6 +239,58 @@ class ModelStore:
         return None if resolution is None else pd.tseries.frequencies.to_offset(resolution)
 
 
+class ResidentBucket:
+    """
+    The models of a store that share one feed-forward architecture, served through ONE ``serving.AnomalyCoalescer``: their weights,
+    scaler slopes and thresholds sit packed on the device, and whatever requests are waiting -- from any thread, for any of the
+    models -- become one fused launch.  Eligible: this package's ``DiffBasedAnomalyDetector`` around a bare ``KerasAutoEncoder``
+    (no smoothing window, an affine error scaler); pass ``bucket=`` to ``anomaly_prediction`` and every eligible model is answered
+    through it, the rest as before.  The replies are the same bytes either way (rows are independent in the kernel).
+    """
+
+    def __init__(self, store: "ModelStore", names: Optional[List[str]] = None, **coalescer_kwargs):
+        from . import engine
+        from .machine.model.anomaly.diff import _scaler_multiplier
+        from .serving import AnomalyCoalescer
+
+        groups: Dict[Any, List[str]] = {}
+        for name in names if names is not None else store.names():
+            model = store.model(name)
+            if self.eligible(model):
+                spec = model.base_estimator.model.spec
+                has_thr = tuple(t is not None for t in model._thresholds())
+                groups.setdefault((tuple(spec.dims), tuple(spec.acts), tuple(spec.l1), has_thr), []).append(name)
+        if not groups:
+            raise ValueError("no model in the store can be served through a coalescer")
+        self.names = max(groups.values(), key=len)  # the largest architecture group
+        self.slot = {name: i for i, name in enumerate(self.names)}
+        models = [store.model(n) for n in self.names]
+        spec = models[0].base_estimator.model.spec
+        eng = engine.ff_engine_for(spec)
+        torch = engine._torch()
+        params = eng.pack_params([m.base_estimator.model.weights for m in models])
+        to_dev = lambda rows: torch.from_numpy(np.ascontiguousarray(np.stack(rows), dtype=np.float32)).to(eng.device)  # noqa: E731
+        scale = to_dev([_scaler_multiplier(m.scaler, eng.n_out) for m in models])
+        feat, agg = zip(*(m._thresholds() for m in models))
+        feat_thr = to_dev([np.asarray(f, dtype=np.float32) for f in feat]) if feat[0] is not None else None
+        agg_thr = to_dev([np.float32(a) for a in agg]) if agg[0] is not None else None
+        self.coalescer = AnomalyCoalescer(eng, params, scale, feat_thr, agg_thr, **coalescer_kwargs)
+
+    @staticmethod
+    def eligible(model) -> bool:
+        from .machine.model.models import KerasAutoEncoder
+
+        return (_frame_is_from_blocks(model) and type(model.base_estimator) is KerasAutoEncoder and model.base_estimator.model is not None
+                and model.window is None and not (model.require_thresholds and all(t is None for t in model._thresholds())))
+
+    def anomaly_blocks(self, store: "ModelStore", name: str, X: pd.DataFrame, y: pd.DataFrame, frequency=None):
+        scores = self.coalescer.anomaly(self.slot[name], X, y)
+        return store.model(name).blocks_from_scores(scores, X, y, frequency)
+
+    def close(self):
+        self.coalescer.close()
+
+
 # ------------------------------------------------------------------------------------------------ the two POST views
 def _extract_X_y(store: ModelStore, name: str, json: Optional[dict], files: Optional[Dict[str, bytes]]):
     """(X, y) frames of a request -- JSON ``{"X": ..., "y": ...}`` or parquet parts -- or a 400 ``Reply`` (utils.py:250-330)."""
@@ -276,8 +328,11 @@ def _respond(frame: pd.DataFrame, fmt: Optional[str], start: float) -> Reply:
 
 
 def anomaly_prediction(store: ModelStore, name: str, json: Optional[dict] = None, files: Optional[Dict[str, bytes]] = None,
-                       all_columns: bool = False, fmt: Optional[str] = None) -> Reply:
-    """``POST .../<name>/anomaly/prediction`` (anomaly.py:28-122): the anomaly frame of the request's X against its y."""
+                       all_columns: bool = False, fmt: Optional[str] = None, bucket: Optional[ResidentBucket] = None) -> Reply:
+    """
+    ``POST .../<name>/anomaly/prediction`` (anomaly.py:28-122): the anomaly frame of the request's X against its y.  With ``bucket``
+    the models it holds are scored through its request coalescer (one launch for everything that is waiting).
+    """
     start = timeit.default_timer()
     try:
         model = store.model(name)
@@ -294,11 +349,15 @@ def anomaly_prediction(store: ModelStore, name: str, json: Optional[dict] = None
         return not_a_detector
     skip = () if all_columns else DELETED_FROM_RESPONSE_COLUMNS
     try:
-        if fmt != "parquet" and _frame_is_from_blocks(model):
-            # JSON out of this package's detectors: straight from the column blocks, no DataFrame in between
-            data = blocks_to_dict(*model.anomaly_blocks(X, y, frequency=store.frequency(name)), skip=skip)
-            return Reply(200, {"data": data, "time-seconds": f"{timeit.default_timer() - start:.4f}"})
-        frame = model.anomaly(X, y, frequency=store.frequency(name))
+        coalesced = bucket is not None and name in bucket.slot
+        if coalesced or (fmt != "parquet" and _frame_is_from_blocks(model)):
+            # this package's detectors: straight from the column blocks, no DataFrame in between for JSON
+            blocks = bucket.anomaly_blocks(store, name, X, y, store.frequency(name)) if coalesced else model.anomaly_blocks(X, y, frequency=store.frequency(name))
+            if fmt != "parquet":
+                return Reply(200, {"data": blocks_to_dict(*blocks, skip=skip), "time-seconds": f"{timeit.default_timer() - start:.4f}"})
+            frame = model_utils.frame_from_blocks(*blocks)
+        else:
+            frame = model.anomaly(X, y, frequency=store.frequency(name))
     except AttributeError:  # as the reference: also what a detector without its required thresholds answers (anomaly.py:46-52)
         return not_a_detector
     dropped = [c for c in frame.columns if c[0] in skip]

@@ -236,3 +236,53 @@ def test_overridden_anomaly_is_respected(tmp_path):
 class _Doubling(DiffBasedAnomalyDetector):
     def anomaly(self, X, y, frequency=None):
         return pd.DataFrame(X.values[:, :1] * 2, index=X.index, columns=pd.MultiIndex.from_tuples([("only", "")]))
+
+
+def test_requests_through_a_bucket_equal_direct_requests(tmp_path):
+    """``bucket=``: the coalescer's score arrays take the same road into the reply as the detector's own (both mocked here: no GPU)."""
+    T, rows = 3, 6
+    rng = np.random.default_rng(4)
+    res = {"model-output": rng.random((rows, T)).astype(np.float32), "tag-anomaly-scaled": rng.random((rows, T)).astype(np.float32),
+           "total-anomaly-scaled": rng.random(rows).astype(np.float32), "tag-anomaly-unscaled": rng.random((rows, T)).astype(np.float32),
+           "total-anomaly-unscaled": rng.random(rows).astype(np.float32), "anomaly-confidence": rng.random((rows, T)).astype(np.float32),
+           "total-anomaly-confidence": rng.random(rows).astype(np.float32)}
+    for name in ("in-bucket", "outside"):
+        det = DiffBasedAnomalyDetector(base_estimator=KerasAutoEncoder(kind="feedforward_hourglass"))
+        det.feature_thresholds_, det.aggregate_threshold_ = pd.Series(np.ones(T), index=TAGS), 0.5
+        serializer.dump(det, str(tmp_path / name), metadata={"name": name, "dataset": {"tag_list": TAGS, "resolution": "10min"}})
+    store = server.ModelStore(str(tmp_path))
+    for name in store.names():
+        store.model(name)._score = lambda *a, **k: dict(res)
+    calls = []
+
+    class FakeCoalescer:
+        def anomaly(self, slot, X, y):
+            calls.append((slot, X.shape, list(X.columns)))
+            return dict(res)
+
+    bucket = server.ResidentBucket.__new__(server.ResidentBucket)  # the constructor packs weights on the device; the serving logic is what is under test
+    bucket.names, bucket.slot, bucket.coalescer = ["in-bucket"], {"in-bucket": 0}, FakeCoalescer()
+    X = _frame(rows=rows)
+    payload = json.loads(json.dumps({"X": server.dataframe_to_dict(X), "y": server.dataframe_to_dict(X)}))
+    direct = server.anomaly_prediction(store, "in-bucket", json=payload)
+    through = server.anomaly_prediction(store, "in-bucket", json=payload, bucket=bucket)
+    assert calls == [(0, (rows, T), TAGS)] and through.status == 200
+    assert json.dumps(through.body["data"]) == json.dumps(direct.body["data"])
+    pq = server.anomaly_prediction(store, "in-bucket", json=payload, bucket=bucket, fmt="parquet")
+    pd.testing.assert_frame_equal(server.dataframe_from_parquet_bytes(pq.body), server.dataframe_from_parquet_bytes(server.anomaly_prediction(store, "in-bucket", json=payload, fmt="parquet").body))
+    assert len(calls) == 2
+    server.anomaly_prediction(store, "outside", json=payload, bucket=bucket)  # not in the bucket: the model's own path
+    assert len(calls) == 2
+    # which models a bucket takes: this package's detector around a bare fitted auto-encoder, no smoothing window
+    det = store.model("in-bucket")
+    assert not server.ResidentBucket.eligible(det)  # the network has no weights yet
+    det.base_estimator.kwargs.update({"n_features": T, "n_features_out": T})
+    det.base_estimator._prepare_model()
+    assert server.ResidentBucket.eligible(det)
+    det.window = 12
+    assert not server.ResidentBucket.eligible(det)
+    det.window = None
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import MinMaxScaler as MM
+    assert not server.ResidentBucket.eligible(DiffBasedAnomalyDetector(base_estimator=Pipeline([("s", MM()), ("m", det.base_estimator)]), require_thresholds=False))
+    assert not server.ResidentBucket.eligible(EchoDetector())

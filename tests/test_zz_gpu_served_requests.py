@@ -128,3 +128,37 @@ def test_detector_build_equals_the_reference_build(engine, torch):
     np.testing.assert_allclose(np.asarray(anomaly["tag-anomaly-scaled"], dtype=np.float64), arrays["build_detector_tag_scaled"], rtol=1e-4, atol=1e-4 * scale)
     np.testing.assert_allclose(np.asarray(anomaly["total-anomaly-confidence"], dtype=np.float64).ravel(), arrays["build_detector_total_confidence"],
                                rtol=5e-3, atol=1e-4 * float(arrays["build_detector_total_confidence"].max()))
+
+
+def test_bucket_of_resident_models_answers_like_single_requests(engine, torch, tmp_path):
+    """server.ResidentBucket: many threads, several models, one coalescer -- every reply equals the model's own answer."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from gordo_components_b200 import builder, server
+
+    N, T = 240, 4
+    frames = {f"m-{i}": _series(N, T, 10 + i) for i in range(3)}
+    machines = [{"name": n, "model": DETECTOR, "dataset": (f, f)} for n, f in frames.items()]
+    machines.append({"name": "lstm", "model": {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {
+        "gordo.machine.model.models.KerasLSTMAutoEncoder": {"kind": "lstm_hourglass", "lookback_window": 3, "epochs": 1, "encoding_layers": 1}}}},
+        "dataset": (frames["m-0"], frames["m-0"])})
+    builder.FleetModelBuilder(machines).build(str(tmp_path))
+    store = server.ModelStore(str(tmp_path))
+    bucket = server.ResidentBucket(store)
+    try:
+        assert bucket.names == ["m-0", "m-1", "m-2"]  # the LSTM model is served on its own path
+        payloads = {}
+        for n, f in frames.items():
+            X = f.iloc[50:90].astype(np.float64)
+            payloads[n] = {"X": server.dataframe_to_dict(X), "y": server.dataframe_to_dict(X)}
+        want = {n: json.dumps(server.anomaly_prediction(store, n, json=p).body["data"]) for n, p in payloads.items()}
+        order = [n for _ in range(8) for n in payloads]
+        with ThreadPoolExecutor(8) as ex:
+            got = list(ex.map(lambda n: json.dumps(server.anomaly_prediction(store, n, json=payloads[n], bucket=bucket).body["data"]), order))
+        assert got == [want[n] for n in order]
+        assert bucket.coalescer.requests == len(order) and bucket.coalescer.batches <= len(order)
+        Xl = frames["m-0"].iloc[:20].astype(np.float64)
+        lstm = server.anomaly_prediction(store, "lstm", json={"X": server.dataframe_to_dict(Xl), "y": server.dataframe_to_dict(Xl)}, bucket=bucket)
+        assert lstm.status == 200 and len(lstm.body["data"]["total-anomaly-scaled"]["total-anomaly-scaled"]) == 18
+    finally:
+        bucket.close()
