@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--rows", type=int, default=100)
     ap.add_argument("--requests", type=int, default=500)
     ap.add_argument("--threads", type=int, default=8)
+    ap.add_argument("--bucket", action="store_true", help="serve through server.ResidentBucket (one coalescer for all models)")
     a = ap.parse_args()
     import numpy as np
     import pandas as pd
@@ -48,6 +49,7 @@ def main():
     with tempfile.TemporaryDirectory() as out:
         builder.FleetModelBuilder(machines).build(out)
         store = server.ModelStore(out)
+        bucket = server.ResidentBucket(store) if a.bucket else None
         bodies = []
         for m in range(a.machines):
             X = machines[m]["dataset"].frame.iloc[: a.rows].astype(np.float64)
@@ -57,7 +59,7 @@ def main():
         def one(i):
             name, body = bodies[i % len(bodies)]
             t0 = time.perf_counter()
-            reply = server.anomaly_prediction(store, name, json=json.loads(body))
+            reply = server.anomaly_prediction(store, name, json=json.loads(body), bucket=bucket)
             text = json.dumps(reply.body)
             return time.perf_counter() - t0, reply.status, len(text)
 
@@ -69,11 +71,15 @@ def main():
         with ThreadPoolExecutor(a.threads) as ex:
             res = list(ex.map(one, range(a.requests)))
         wall = time.perf_counter() - t0
+        launches = (bucket.coalescer.batches, bucket.coalescer.requests) if bucket else None
+        if bucket:
+            bucket.close()
     assert all(r[1] == 200 for r in res)
     print(json.dumps({
         "workload": f"{a.requests} JSON anomaly requests x {a.rows} rows x {a.tags} tags over {a.machines} resident models",
         "single_thread_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p95": float(np.percentile(lat, 95) * 1e3), "mean": float(lat.mean() * 1e3)},
         "threads": a.threads, "requests_per_s": a.requests / wall, "windows_per_s": a.requests * a.rows / wall, "reply_bytes": res[0][2],
+        "coalescer_batches_requests": launches,
     }))
 
 

@@ -29,3 +29,4 @@ timeout 60 python -c "import __graft_entry__ as g; g.build()"
 timeout 200 python benchmarks/bench_fleet_builder.py --machines 125 --epochs 10 > gpurun_out/r2_fleet_builder.json 2> gpurun_out/r2_fleet_builder.err; tail -1 gpurun_out/r2_fleet_builder.json
 timeout 200 python benchmarks/bench_fleet_builder.py --machines 125 --epochs 10 --scaled --single 0 > gpurun_out/r2_fleet_builder_scaled.json 2>> gpurun_out/r2_fleet_builder.err; tail -1 gpurun_out/r2_fleet_builder_scaled.json
 timeout 200 python benchmarks/bench_requests.py > gpurun_out/r2_requests.json 2> gpurun_out/r2_requests.err; tail -1 gpurun_out/r2_requests.json
+timeout 200 python benchmarks/bench_requests.py --bucket > gpurun_out/r2_requests_bucket.json 2>> gpurun_out/r2_requests.err; tail -1 gpurun_out/r2_requests_bucket.json
