@@ -213,14 +213,34 @@ def minmax_fit(jobs_dev, n_jobs, max_rows, y, n_out, n_slots, device, return_min
     return scale, offset
 
 
-def thresholds(jobs_dev, n_jobs, max_rows, tag_unscaled, total_scaled, n_out, n_slots, window, device):
-    """rolling(window).min().max() per tag and for the aggregate series: (feat_thr [n_slots, n_out], agg_thr [n_slots])."""
+def minmax_f64(jobs_dev, n_jobs, max_rows, y64, n_slots):
+    """Column (min, max) of float64 targets per job: two [n_slots, n_out] float64 tensors (NaNs skipped, +-inf when a column has none)."""
     torch = _torch()
     lib = _cabi.load_library()
-    feat = torch.full((n_slots, n_out), float("nan"), dtype=torch.float32, device=device)
-    agg = torch.full((n_slots,), float("nan"), dtype=torch.float32, device=device)
+    if y64.dtype != torch.float64:
+        raise ValueError(f"minmax_f64 takes float64 targets, got {y64.dtype}")
+    n_out = y64.shape[1]
+    mm = torch.empty((int(n_slots), 2, n_out), dtype=torch.float64, device=y64.device)
     p = _cabi.ptr
-    _cabi.check(lib.gb_thresholds(p(jobs_dev), int(n_jobs), int(max_rows), p(tag_unscaled), p(total_scaled), int(n_out), int(window),
+    _cabi.check(lib.gb_minmax_f64(p(jobs_dev), int(n_jobs), int(max_rows), p(y64), int(n_out), p(mm), int(n_slots), _stream_ptr()))
+    return mm[:, 0], mm[:, 1]
+
+
+def thresholds(jobs_dev, n_jobs, max_rows, tag_unscaled, total_scaled, n_out, n_slots, window, device):
+    """
+    rolling(window).min().max() per tag and for the aggregate series: (feat_thr [n_slots, n_out], agg_thr [n_slots]).
+    float32 or float64 score arrays (the dtype of ``tag_unscaled`` decides; both arrays must agree).
+    """
+    torch = _torch()
+    lib = _cabi.load_library()
+    dtype = tag_unscaled.dtype
+    if total_scaled.dtype != dtype or dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"thresholds need two float32 or two float64 arrays, got {dtype} / {total_scaled.dtype}")
+    feat = torch.full((n_slots, n_out), float("nan"), dtype=dtype, device=device)
+    agg = torch.full((n_slots,), float("nan"), dtype=dtype, device=device)
+    p = _cabi.ptr
+    fn = lib.gb_thresholds if dtype == torch.float32 else lib.gb_thresholds_f64
+    _cabi.check(fn(p(jobs_dev), int(n_jobs), int(max_rows), p(tag_unscaled), p(total_scaled), int(n_out), int(window),
                                   p(feat), p(agg), int(n_slots), _stream_ptr()))
     return feat, agg
 
@@ -238,11 +258,21 @@ def cv_moments(jobs_dev, n_jobs, yhat, y, n_out):
 
 
 def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_thr=None, agg_thr=None, want=SCORE_KEYS, device=None):
-    """Anomaly columns for predictions that already exist (base estimators that are not ours, LSTM outputs)."""
+    """
+    Anomaly columns for predictions that already exist (base estimators that are not ours, LSTM outputs).  float64 ``yhat`` selects
+    the float64 kernel (the reference's own precision, diff.py:268-300, 350-385): every operand must then be float64 and so are the results.
+    """
     torch = _torch()
     lib = _cabi.load_library()
     device = yhat.device
     total = yhat.shape[0]
+    dtype = yhat.dtype
+    for name, t in (("y", y), ("scale", scale), ("feat_thr", feat_thr), ("agg_thr", agg_thr)):
+        if t is not None and t.dtype != dtype:
+            raise ValueError(f"anomaly_score: {name} is {t.dtype}, yhat is {dtype}")
+    fn = {torch.float32: lib.gb_anomaly_score, torch.float64: lib.gb_anomaly_score_f64}.get(dtype)
+    if fn is None:
+        raise ValueError(f"anomaly_score takes float32 or float64 arrays, not {dtype}")
     sel = set(want)
     if scale is None:
         sel -= {"tag-anomaly-scaled", "total-anomaly-scaled", "total-anomaly-confidence"}
@@ -254,7 +284,7 @@ def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_t
 
     def g(name, shape):
         if name in sel:
-            res[name] = torch.empty(shape, dtype=torch.float32, device=device)
+            res[name] = torch.empty(shape, dtype=dtype, device=device)
             return res[name]
         return None
 
@@ -265,7 +295,7 @@ def anomaly_score(jobs_dev, n_jobs, max_rows, yhat, y, n_out, scale=None, feat_t
     o_conf = g("anomaly-confidence", (total, n_out))
     o_totc = g("total-anomaly-confidence", (total,))
     p = _cabi.ptr
-    _cabi.check(lib.gb_anomaly_score(p(jobs_dev), int(n_jobs), int(max_rows), p(yhat), p(y), int(n_out), p(scale), p(feat_thr), p(agg_thr),
+    _cabi.check(fn(p(jobs_dev), int(n_jobs), int(max_rows), p(yhat), p(y), int(n_out), p(scale), p(feat_thr), p(agg_thr),
                                      p(o_ts), p(o_tu), p(o_tots), p(o_totu), p(o_conf), p(o_totc), _stream_ptr()))
     return res
 

@@ -42,13 +42,13 @@ def _values(a) -> np.ndarray:
 
 
 def _scaler_multiplier(scaler, n_features: int) -> np.ndarray:
-    """Per-feature slope of a fitted affine scaler; ValueError if the transform is not affine per feature."""
+    """Per-feature slope (float64) of a fitted affine scaler; ValueError if the transform is not affine per feature."""
     probe = np.vstack([np.zeros(n_features), np.ones(n_features), np.full(n_features, 2.0)])
     t = np.asarray(scaler.transform(probe), dtype=np.float64)
     slope = t[1] - t[0]
     if not np.allclose(t[2] - t[1], slope, rtol=1e-9, atol=1e-12):
         raise ValueError(f"scaler {scaler!r} is not a per-feature affine transform; the fused anomaly kernels cannot use it")
-    return slope.astype(np.float32)
+    return slope
 
 
 def _affine_of(step, n):
@@ -169,31 +169,50 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         self._fit_scaler(y)
         return self
 
+    def _is_b200_network(self) -> bool:
+        """True when the predictions come out of one of this package's fp32 networks (bare or last step of a Pipeline)."""
+        est = self.base_estimator
+        if isinstance(est, Pipeline) and len(est.steps):
+            est = est.steps[-1][1]
+        return isinstance(est, KerasBaseEstimator)
+
     def _fit_scaler(self, y):
-        """Scaler statistics of the targets.  A default MinMaxScaler is fitted by the gb_minmax_fit kernel."""
+        """
+        Scaler statistics of the targets (diff.py:173 ``self.scaler.fit(y)``).  For a default MinMaxScaler around one of this
+        package's networks the column extrema come from the gb_minmax_f64 kernel -- on the float64 targets, as the reference's
+        scaler sees them -- and sklearn's float64 attribute arithmetic is applied to them on the host, so every fitted attribute
+        equals sklearn's own.  Any other scaler, and any foreign base estimator, is fitted by its own code.
+        """
         sc = self.scaler
         plain_minmax = type(sc) is MinMaxScaler and tuple(sc.feature_range) == (0, 1) and not getattr(sc, "clip", False)
-        if not plain_minmax:
-            sc.fit(y)  # user supplied transformer: its own code owns its statistics
+        yv = _values(y)
+        if not plain_minmax or not self._is_b200_network() or yv.ndim != 2 or yv.shape[1] > 256 or len(yv) == 0 or not np.issubdtype(yv.dtype, np.number):
+            sc.fit(y)  # user supplied transformer / foreign estimator: its own code owns its statistics
             return
         from .... import engine
 
-        yv = _values(y)
         dev = engine.cuda_device()
-        yd = engine.to_device_f32(yv, dev)
+        torch = engine._torch()
+        yd = torch.from_numpy(np.ascontiguousarray(yv, dtype=np.float64)).to(dev)
         n, t = yd.shape
         jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
-        scale, offset = engine.minmax_fit(jobs, 1, n, yd, t, 1, dev)
-        scale = scale[0].cpu().numpy().astype(np.float64)
-        offset = offset[0].cpu().numpy().astype(np.float64)
-        sc.scale_, sc.min_ = scale, offset
-        sc.data_min_ = -offset / scale
-        sc.data_range_ = 1.0 / scale  # (a constant feature reports 1 here where sklearn reports 0; transform is identical)
-        sc.data_max_ = sc.data_min_ + sc.data_range_
-        sc.n_features_in_ = t
+        lo, hi = engine.minmax_f64(jobs, 1, n, yd, 1)
+        lo, hi = lo[0].cpu().numpy(), hi[0].cpu().numpy()
+        if not (np.isfinite(lo).all() and np.isfinite(hi).all()):
+            sc.fit(y)  # all-NaN or infinite columns: sklearn's own error / warning behaviour
+            return
+        # sklearn.preprocessing.MinMaxScaler.partial_fit [3P]: data_range_ = max - min; scale_ = 1 / range with ranges below
+        # 10 * eps taken as 1 (_handle_zeros_in_scale); min_ = 0 - data_min_ * scale_
+        data_range = hi - lo
+        denom = data_range.copy()
+        denom[denom < 10 * np.finfo(np.float64).eps] = 1.0
         sc.n_samples_seen_ = n
-        if hasattr(y, "columns"):
-            sc.feature_names_in_ = np.asarray([str(c) for c in y.columns], dtype=object)
+        sc.n_features_in_ = t
+        sc.data_min_, sc.data_max_, sc.data_range_ = lo, hi, data_range
+        sc.scale_ = 1.0 / denom
+        sc.min_ = 0.0 - lo * sc.scale_
+        if hasattr(y, "columns") and all(isinstance(c, str) for c in y.columns):
+            sc.feature_names_in_ = np.asarray(y.columns, dtype=object)
         elif hasattr(sc, "feature_names_in_"):
             del sc.feature_names_in_
 
@@ -220,11 +239,14 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         n_out = yv.shape[1]
         mult = _scaler_multiplier(scaler, n_out)
         torch = engine._torch()
-        scale_d = torch.from_numpy(mult.reshape(1, -1)).to(dev)
-        ft_d = torch.from_numpy(np.asarray(feat_thr, dtype=np.float32).reshape(1, -1)).to(dev) if feat_thr is not None else None
-        at_d = torch.tensor([float(agg_thr)], dtype=torch.float32, device=dev) if agg_thr is not None else None
         fused = estimator_owner._fused_target()
-        if fused is not None and fused[1].model is not None:
+        fused = fused if fused is not None and fused[1].model is not None else None
+        # the fused launch is fp32 like the network; predictions that come from elsewhere are scored in float64 like the reference
+        dt, npdt = (torch.float32, np.float32) if fused is not None else (torch.float64, np.float64)
+        scale_d = torch.from_numpy(np.ascontiguousarray(mult.reshape(1, -1), dtype=npdt)).to(dev)
+        ft_d = torch.from_numpy(np.asarray(feat_thr, dtype=npdt).reshape(1, -1)).to(dev) if feat_thr is not None else None
+        at_d = torch.tensor([float(agg_thr)], dtype=dt, device=dev) if agg_thr is not None else None
+        if fused is not None:
             pre, ae = fused
             eng = ae._engine()
             affine = _compose_affine(pre, eng.n_in)
@@ -246,10 +268,13 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             yd = engine.to_device_f32(yv, dev)
             res = eng.infer_score(ae._device_params(), jobs, 1, n, xd, yd, scale_d, ft_d, at_d, want=want)
         else:
+            # diff.py:350-385: pandas arithmetic on float64 y and the (float32- or float64-valued) predictions widened to float64
             pred = np.asarray(estimator_owner.predict(X) if hasattr(estimator_owner, "predict") else estimator_owner.transform(X))
             n = len(pred)
-            pd_ = engine.to_device_f32(pred, dev)
-            yd = engine.to_device_f32(yv[-n:] if n else yv[:0], dev)
+            p64 = np.ascontiguousarray(pred, dtype=np.float64)
+            p64 = p64.reshape(n, -1)
+            pd_ = torch.from_numpy(p64).to(dev)
+            yd = torch.from_numpy(np.ascontiguousarray(yv[-n:] if n else yv[:0], dtype=np.float64)).to(dev)
             jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
             res = engine.anomaly_score(jobs, 1, n, pd_, yd, n_out, scale_d, ft_d, at_d, want=want) if n else {}
             res["model-output"] = pred
@@ -281,8 +306,8 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
                 fold.scaler.fit(y_test)
             res = self._score(fold, X_test, y_test, fold.scaler, want=("tag-anomaly-unscaled", "total-anomaly-scaled"))
             n = len(res["model-output"])
-            tu = torch.from_numpy(np.ascontiguousarray(res["tag-anomaly-unscaled"], dtype=np.float32)).to(dev)
-            ts = torch.from_numpy(np.ascontiguousarray(res["total-anomaly-scaled"], dtype=np.float32)).to(dev)
+            tu = torch.from_numpy(np.ascontiguousarray(res["tag-anomaly-unscaled"])).to(dev)  # float32 (fused network) or float64
+            ts = torch.from_numpy(np.ascontiguousarray(res["total-anomaly-scaled"], dtype=res["tag-anomaly-unscaled"].dtype)).to(dev)
             jobs = engine.jobs_to_device(engine.make_jobs([0], [n], [0]), dev)
             f, a = engine.thresholds(jobs, 1, n, tu, ts, tu.shape[1], 1, 6, dev)
             feat = pd.Series(f[0].cpu().numpy().astype(np.float64), index=columns, name=f"fold-{i}")

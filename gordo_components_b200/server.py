@@ -280,8 +280,16 @@ class ResidentBucket:
     def eligible(model) -> bool:
         from .machine.model.models import KerasAutoEncoder
 
-        return (_frame_is_from_blocks(model) and type(model.base_estimator) is KerasAutoEncoder and model.base_estimator.model is not None
-                and model.window is None and not (model.require_thresholds and all(t is None for t in model._thresholds())))
+        if not (_frame_is_from_blocks(model) and type(model.base_estimator) is KerasAutoEncoder and model.base_estimator.model is not None
+                and model.window is None and not (model.require_thresholds and all(t is None for t in model._thresholds()))):
+            return False
+        from .machine.model.anomaly.diff import _scaler_multiplier
+
+        try:  # a non-affine error scaler (clip=True, QuantileTransformer, ...) is served on the per-request path, not refused for the whole store
+            _scaler_multiplier(model.scaler, model.base_estimator.model.spec.dims[-1])
+        except (ValueError, AttributeError):
+            return False
+        return True
 
     def anomaly_blocks(self, store: "ModelStore", name: str, X: pd.DataFrame, y: pd.DataFrame, frequency=None):
         scores = self.coalescer.anomaly(self.slot[name], X, y)

@@ -119,11 +119,26 @@ int gb_anomaly_score(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const
                      float* out_tag_scaled, float* out_tag_unscaled, float* out_total_scaled,
                      float* out_total_unscaled, float* out_conf, float* out_total_conf, void* stream);
 
+/* The same arithmetic in float64, as the reference does it (pandas on float64 y: diff.py:268-300 `_scaled_mse_per_timestep`,
+ * `_absolute_error`; :350-385, 420-444 in `anomaly`) -- used whenever the predictions did not come out of one of this
+ * package's fp32 networks fused with the scoring (foreign base estimators, LSTM outputs): at data magnitude ~100 a float32
+ * |yhat - y| is uncertain by 7.6e-6, i.e. percents of a small residual.  All arrays double. */
+int gb_anomaly_score_f64(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const double* yhat, const double* y,
+                         int32_t n_out, const double* scale, const double* feat_thr, const double* agg_thr,
+                         double* out_tag_scaled, double* out_tag_unscaled, double* out_total_scaled,
+                         double* out_total_unscaled, double* out_conf, double* out_total_conf, void* stream);
+
 /* ---- K7: MinMaxScaler.fit on the targets (diff.py:173; sklearn MinMaxScaler [3P]) -------
  * per job: scale[slot][j] = 1/(max_j - min_j) (zero range -> 1), offset[slot][j] = -min_j*scale.
  * minmax_ws: workspace [n_slots][2][n_out] floats (overwritten). */
 int gb_minmax_fit(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* y, int32_t n_out,
                   float* scale, float* offset, float* minmax_ws, int32_t n_slots, void* stream);
+
+/* Column extrema of float64 targets, for the scaler of a single detector (`scaler.fit(y)` sees float64 y in the reference):
+ * minmax[slot][0][j] = min, minmax[slot][1][j] = max over the job's rows (NaNs skipped; +inf / -inf when there is no finite
+ * sample).  sklearn's float64 scale_ / min_ arithmetic on them stays on the host. */
+int gb_minmax_f64(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const double* y, int32_t n_out, double* minmax,
+                  int32_t n_slots, void* stream);
 
 /* ---- K5: thresholds of one CV fold (diff.py:222-233) ------------------------------------
  *   feat_thr[slot][j] = max_t min(tag_unscaled[t-window+1 .. t][j])   (rolling(window).min().max())
@@ -133,6 +148,11 @@ int gb_minmax_fit(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const fl
 int gb_thresholds(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* tag_unscaled,
                   const float* total_scaled, int32_t n_out, int32_t window, float* feat_thr,
                   float* agg_thr, int32_t n_slots, void* stream);
+
+/* float64 form for the score arrays of gb_anomaly_score_f64 (min / max select, so the thresholds are exact). */
+int gb_thresholds_f64(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const double* tag_unscaled,
+                      const double* total_scaled, int32_t n_out, int32_t window, double* feat_thr,
+                      double* agg_thr, int32_t n_slots, void* stream);
 
 /* ---- K8: column moments behind the builder's cross-validation metrics (build_model.py:250-289, 378-446) ----
  * For job i, over rows yhat[out_row .. out_row+n_rows) and y[x_row .. x_row+n_rows), with e = yhat - y and

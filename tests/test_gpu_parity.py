@@ -1,11 +1,12 @@
 """
 Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden fixtures.
 
-Tolerance (north_star: "within 1e-4 relative"): model output |got - want| <= 1e-4*|want| + 1e-4*SCALE*eps-floor,
-where the floor covers outputs near zero; quantities formed by subtracting the target (abs diffs, their squares,
+Tolerance (north_star: "within 1e-4 relative"): model output |got - want| <= 1e-4*|want| + 2e-5*magnitude, where the
+second term covers outputs near zero (the split-precision tensor-core path measures ~2e-6 of the magnitude, so a
+regression of its operand scheme shows); quantities formed by subtracting the target (abs diffs, their squares,
 confidences) carry the same *absolute* uncertainty as the model output, so they are compared with
-atol = 1e-4 * (magnitude of y) -- a relative bound on a difference of nearly equal numbers is not meaningful in
-any float32 implementation, the reference's included.
+atol = 2e-5 * (magnitude of y) -- a relative bound on a difference of nearly equal numbers is not meaningful in
+any float32 implementation, the reference's included.  The float64 kernels (foreign base estimators) are held to 1e-9.
 """
 import os
 
@@ -38,11 +39,14 @@ def engine(torch):
     return e
 
 
-def close(got, want, mag=1.0, rtol=RTOL, name="", atol=0.0):
+FLOOR = 2e-5  # absolute part of the tolerance, in units of the data magnitude: the tcgen05 split-precision path measures ~2e-6
+
+
+def close(got, want, mag=1.0, rtol=RTOL, name="", atol=0.0, floor=FLOOR):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, (name, got.shape, want.shape)
     err = np.abs(got - want)
-    tol = rtol * np.abs(want) + rtol * mag + atol
+    tol = rtol * np.abs(want) + floor * mag + atol
     bad = ~(err <= tol) & ~(np.isnan(got) & np.isnan(want))
     assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} outside tolerance; max err {err[bad].max():.3e} (tol {tol[bad].min():.3e})"
 
@@ -300,6 +304,52 @@ def test_thresholds_edge_cases(engine, torch):
     assert np.isnan(feat[2]).all() and np.isnan(agg[2])
 
 
+def test_float64_score_thresholds_and_extrema(engine, torch):
+    """
+    gb_anomaly_score_f64 / gb_thresholds_f64 / gb_minmax_f64 against NumPy float64 at data magnitude ~100 with residuals of ~1e-3,
+    where a float32 |yhat - y| is off by percents (diff.py:268-300, 350-385 are float64 in the reference).  Two ragged jobs.
+    """
+    from oracle import anomaly_math as am
+
+    dev = engine.cuda_device()
+    rng = np.random.default_rng(11)
+    T, lens = 9, [1500, 37]
+    n = sum(lens)
+    y = 100.0 + rng.random((n, T))
+    y[5, 2] = np.nan
+    yhat = y + rng.normal(0, 1e-3, (n, T))
+    starts = np.cumsum([0] + lens[:-1])
+    jobs = engine.jobs_to_device(engine.make_jobs([0, 1], lens, starts), dev)
+    lo, hi = engine.minmax_f64(jobs, 2, max(lens), torch.from_numpy(y).to(dev), 2)
+    for i, (s, m) in enumerate(zip(starts, lens)):
+        np.testing.assert_array_equal(lo[i].cpu().numpy(), np.nanmin(y[s:s + m], axis=0))
+        np.testing.assert_array_equal(hi[i].cpu().numpy(), np.nanmax(y[s:s + m], axis=0))
+    scale = 1.0 / (hi - lo)
+    feat = torch.from_numpy(rng.random((2, T)) * 1e-3 + 1e-4).to(dev)
+    agg = torch.from_numpy(rng.random(2) * 1e-6 + 1e-7).to(dev)
+    res = engine.anomaly_score(jobs, 2, max(lens), torch.from_numpy(yhat).to(dev), torch.from_numpy(y).to(dev), T, scale, feat, agg)
+    assert all(v.dtype == torch.float64 for v in res.values())
+    f_thr, a_thr = engine.thresholds(jobs, 2, max(lens), res["tag-anomaly-unscaled"], res["total-anomaly-scaled"], T, 2, 6, dev)
+    res = {k: v.cpu().numpy() for k, v in res.items()}
+    sc, ft, at = scale.cpu().numpy(), feat.cpu().numpy(), agg.cpu().numpy()
+    for i, (s, m) in enumerate(zip(starts, lens)):
+        sl = slice(s, s + m)
+        d = np.abs(yhat[sl] - y[sl])
+        np.testing.assert_array_equal(res["tag-anomaly-unscaled"][sl], d)
+        np.testing.assert_array_equal(res["tag-anomaly-scaled"][sl], d * sc[i])
+        np.testing.assert_allclose(res["total-anomaly-unscaled"][sl], (d ** 2).mean(axis=1), rtol=1e-13)
+        np.testing.assert_allclose(res["total-anomaly-scaled"][sl], ((d * sc[i]) ** 2).mean(axis=1), rtol=1e-13)
+        np.testing.assert_array_equal(res["anomaly-confidence"][sl], d / ft[i])
+        np.testing.assert_allclose(res["total-anomaly-confidence"][sl], ((d * sc[i]) ** 2).mean(axis=1) / at[i], rtol=1e-13)
+        np.testing.assert_array_equal(f_thr[i].cpu().numpy(), am.rolling_min_then_max(res["tag-anomaly-unscaled"][sl], 6))
+        np.testing.assert_array_equal(float(a_thr[i]), am.rolling_min_then_max(res["total-anomaly-scaled"][sl], 6))
+    # the float32 route on the same data shows why the float64 one exists
+    r32 = engine.anomaly_score(jobs, 2, max(lens), torch.from_numpy(yhat.astype(np.float32)).to(dev), torch.from_numpy(y.astype(np.float32)).to(dev), T,
+                               want=("tag-anomaly-unscaled",))["tag-anomaly-unscaled"].cpu().numpy()
+    rel = np.abs(r32[:lens[0]] - res["tag-anomaly-unscaled"][:lens[0]]) / np.maximum(res["tag-anomaly-unscaled"][:lens[0]], 1e-12)
+    assert np.nanmax(rel) > 1e-3
+
+
 @pytest.mark.parametrize("case", ["anomaly_smm", "anomaly_sma", "anomaly_ewma"])
 def test_smoothing_against_reference_fixture(engine, torch, case):
     """smooth-* columns of the reference frame (pandas rolling median / mean / ewm) from its own unsmoothed columns."""
@@ -431,7 +481,8 @@ def test_lstm_infer_matches_oracle(engine, torch, F, units, lookback):
 
 @pytest.mark.parametrize("F,units,lookback,rows,scale", [(16, [64, 64], 5, [140, 300], 1.0), (128, [256, 128, 64, 64, 128, 256], 20, [57, 190], 1.0),
                                                           (7, [128], 9, [400], 1000.0), (5, [7, 9, 3], 4, [50, 133], 1.0),
-                                                          (128, [107, 85, 64, 64, 85, 107], 12, [150], 1.0)])  # widths padded to 64 internally
+                                                          (128, [107, 85, 64, 64, 85, 107], 12, [150], 1.0),  # widths padded to 64 internally
+                                                          (128, [256, 128, 64, 64, 128, 256], 144, [144 + 39, 144 + 130], 1.0)])  # BASELINE configs[3]: error growth over 144 steps
 def test_lstm_infer_tcgen05_matches_oracle(engine, torch, F, units, lookback, rows, scale):
     """gb_lstm_infer_tc: FP16-pair split operands on the tensor cores, state in HBM, one launch per (layer, timestep).
     Jobs of different lengths (tiles with padding rows), machines sharing the launch, raw inputs of large magnitude (the
@@ -534,18 +585,19 @@ def test_detector_with_foreign_base_estimator(engine, torch):
     model.cross_validate(X=X, y=y)
     model.fit(X, y)
     frame = model.anomaly(X, y)
-    close(model.feature_thresholds_.values, g["feature_thresholds"], rtol=1e-4, mag=1e-4, name="feature thresholds")
-    close(model.aggregate_threshold_, g["aggregate_threshold"], rtol=1e-4, mag=1e-5, name="aggregate threshold")
+    # a foreign estimator's predictions are scored in float64 like the reference (gb_anomaly_score_f64 / gb_thresholds_f64)
+    np.testing.assert_allclose(model.feature_thresholds_.values, g["feature_thresholds"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(model.aggregate_threshold_, g["aggregate_threshold"], rtol=1e-9, atol=1e-13)
     for top in ("model-output", "tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-unscaled",
                 "anomaly-confidence", "total-anomaly-confidence"):
         want = g[f"frame_{top}"]
         got = frame[top].values
-        close(got.reshape(want.shape), want, float(np.abs(want).max()), name=top)
+        np.testing.assert_allclose(got.reshape(want.shape), want, rtol=1e-9, atol=1e-13, err_msg=top)
     # RobustScaler (reference test parametrisation): slope = 1/scale_
     m2 = DiffBasedAnomalyDetector(base_estimator=MultiOutputRegressor(LinearRegression()), scaler=RobustScaler(), require_thresholds=False)
     f2 = m2.fit(X, y).anomaly(X, y)
     want = np.abs(m2.scaler.transform(m2.predict(X)) - m2.scaler.transform(y))
-    close(f2["tag-anomaly-scaled"].values, want, float(np.abs(want).max()), name="robust scaled")
+    np.testing.assert_allclose(f2["tag-anomaly-scaled"].values, want, rtol=1e-9, atol=1e-12, err_msg="robust scaled")
     assert "anomaly-confidence" not in f2.columns
 
 

@@ -278,7 +278,13 @@ def test_requests_through_a_bucket_equal_direct_requests(tmp_path):
     assert not server.ResidentBucket.eligible(det)  # the network has no weights yet
     det.base_estimator.kwargs.update({"n_features": T, "n_features_out": T})
     det.base_estimator._prepare_model()
+    assert not server.ResidentBucket.eligible(det)  # the error scaler is not fitted
+    det.scaler.fit(rng.random((8, T)))
     assert server.ResidentBucket.eligible(det)
+    from sklearn.preprocessing import QuantileTransformer
+    affine, det.scaler = det.scaler, QuantileTransformer(n_quantiles=4).fit(rng.random((8, T)))
+    assert not server.ResidentBucket.eligible(det)  # not affine: this model keeps its per-request path, the rest of the store is still served
+    det.scaler = affine
     det.window = 12
     assert not server.ResidentBucket.eligible(det)
     det.window = None
