@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
+# experiment knobs of the kernels (compile-time constants), e.g. GB_DEFINES="GB_TC_NSLOT=2"
+NVCC_FLAGS += ["-D" + d for d in os.environ.get("GB_DEFINES", "").split() if d]
 
 
 def _nvcc() -> str:

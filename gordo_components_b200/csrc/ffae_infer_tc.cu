@@ -37,7 +37,12 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NTHREADS = 576;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17: control of slot 0 / 1
+#ifndef GB_TC_NSLOT
+#define GB_TC_NSLOT 3
+#endif
+constexpr int NSLOT = GB_TC_NSLOT;  // tiles in flight (2 or 3)
+static_assert(NSLOT == 2 || NSLOT == 3, "two or three tile slots");
+constexpr int NTHREADS = 512 + 32 * NSLOT;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17,18: control of slot 0 / 1 / 2
 constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;  // in both groups: warp%4 = TMEM lane quadrant, (warp/4)%2 = column half
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
@@ -45,9 +50,9 @@ constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 row
 constexpr int W = 64;                  // widest feature / hidden width; narrower tag counts T (multiples of 4) ride in zero-padded columns
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
-constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 128, COL_ABF = 192, SLOT_COLS = 224, COL_DX = 448, TMEM_COLS = 512;
+constexpr uint32_t COL_D = 0, COL_ALB = 64, COL_ABF = 96, SLOT_COLS = 128, COL_DX = NSLOT * 128, TMEM_COLS = 512;  // 3 slots + 2 spare accumulators (COL_DX, COL_DX + 64)
 // layers >= 1 keep their two packed-FP16 operand images (32 columns each) where layer 0's TF32-hi image was
-constexpr uint32_t COL_A1 = COL_AHI, COL_A2 = COL_AHI + 32;
+constexpr uint32_t COL_A1 = COL_ALB, COL_A2 = COL_ABF;
 // COL_DX: spare accumulator (absolute column) that receives the OUTPUT layer of slot-1 tiles, so slot 1 can start its next
 // tile while the output warps are still busy with the previous pair (they drain slot 0's accumulator first)
 
@@ -56,6 +61,7 @@ struct TcArgs {
   int n_layers, last_layer;  // layers actually evaluated: 0..last_layer (debug aid; == n_layers-1 in production)
   int K[MAXL], N[MAXL], Np[MAXL], n8[MAXL], k8[MAXL], k16[MAXL], act[MAXL];  // Np = N rounded up to 16 (MMA N), n8 = to 8 (columns evaluated)
   int whi_ofs[MAXL], wlo_ofs[MAXL], bias_ofs[MAXL];  // byte offsets into dynamic smem
+  int whb_ofs;                                       // layer 0: BF16 image of W_hi [K/8][Np][8]
   int pofs[MAXL];                                    // float offsets of W_l in the canonical parameter vector
   int w_bytes;                                       // bytes of the weight+bias region (zero-filled before staging)
   int param_bytes, bulk_params;                      // parameter vector of one slot: bytes (multiple of 16) / 1 = fetch with one bulk copy
@@ -75,7 +81,7 @@ constexpr int DEFAULT_NE = 0;
 
 // debug timeline (gb_debug_set_trace): three recorder threads of CTA 0 (epilogue tid 0, the two control leaders) stamp
 // events into shared memory (one clock read + one store each) and flush them to global memory when the kernel ends
-constexpr int TRACE_SLOTS = 320;
+constexpr int TRACE_SLOTS = 64;  // (scratch/dbg_trace.py must be told: the buffer layout depends on it)
 __device__ __forceinline__ void trace_ev(const TcArgs& a, unsigned long long* ring, int& cnt, int code, int tile, int layer, int slot) {
   if (a.trace == nullptr || blockIdx.x != 0 || cnt >= TRACE_SLOTS || (tile < a.trace_from && tile >= a.trace_head)) return;
   ring[cnt++] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(tile & 0xfff) << 12) | ((layer & 0xf) << 8) | ((slot & 0xf) << 4) | (code & 0xf);  // code < 16
@@ -134,6 +140,25 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t bde
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// A and B from shared memory (layer 0's A_hi is the TMA'd x box itself: the tensor core ignores the low 13 mantissa bits of fp32 data)
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major SWIZZLE_128B operand (a TMA box of 128-byte rows): 8-row groups 1024 bytes apart; K steps advance the start address
+__device__ __forceinline__ uint64_t make_adesc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -213,31 +238,28 @@ __device__ __forceinline__ float tanh_from_scaled_fma(float t) {
 
 // NE: every NE-th element takes the 1-MUFU tanh (0: never) -- the knob that trades SFU against FMA-pipe load
 
-// layer 0: split NC (16) inputs into the three A operands (TF32 hi, fp32 remainder, packed BF16) at column `col`
+// layer 0: NC (16) inputs -> packed BF16 images of A_lo = A - trunc_tf32(A) and of A itself, at column `col`
+// (A_hi is not stored: the tensor core reads it straight from the x box)
 template <int NC>
 __device__ __forceinline__ void store_a_operands(uint32_t slot_lane, int col, const float* a) {
-  uint32_t hi[NC], lo[NC], bf[NC / 2];
-#pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const uint32_t h = __float_as_uint(a[i]) & 0xffffe000u;
-    hi[i] = h;
-    lo[i] = __float_as_uint(a[i] - __uint_as_float(h));
-  }
+  uint32_t lb[NC / 2], bf[NC / 2];
 #pragma unroll
   for (int i = 0; i < NC / 2; ++i) {
-    const __nv_bfloat162 p = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);  // low half = even k (the order the MMA expects)
-    bf[i] = *reinterpret_cast<const uint32_t*>(&p);
+    const float l0 = a[2 * i] - __uint_as_float(__float_as_uint(a[2 * i]) & 0xffffe000u);
+    const float l1 = a[2 * i + 1] - __uint_as_float(__float_as_uint(a[2 * i + 1]) & 0xffffe000u);
+    const __nv_bfloat162 pl = __floats2bfloat162_rn(l0, l1);  // low half = even k (the order the MMA expects)
+    const __nv_bfloat162 pa = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+    lb[i] = *reinterpret_cast<const uint32_t*>(&pl);
+    bf[i] = *reinterpret_cast<const uint32_t*>(&pa);
   }
   constexpr int C8 = NC / 8, R4 = (NC % 8) / 4;  // NC = 8*C8 + 4*R4
 #pragma unroll
   for (int c = 0; c < C8; ++c) {
-    tmem_st8(slot_lane + COL_AHI + col + 8 * c, hi + 8 * c);
-    tmem_st8(slot_lane + COL_ALO + col + 8 * c, lo + 8 * c);
+    tmem_st4(slot_lane + COL_ALB + ((col + 8 * c) >> 1), lb + 4 * c);
     tmem_st4(slot_lane + COL_ABF + ((col + 8 * c) >> 1), bf + 4 * c);
   }
   if (R4) {
-    tmem_st4(slot_lane + COL_AHI + col + 8 * C8, hi + 8 * C8);
-    tmem_st4(slot_lane + COL_ALO + col + 8 * C8, lo + 8 * C8);
+    tmem_st2(slot_lane + COL_ALB + ((col + 8 * C8) >> 1), lb + 4 * C8);
     tmem_st2(slot_lane + COL_ABF + ((col + 8 * C8) >> 1), bf + 4 * C8);
   }
 }
@@ -326,13 +348,13 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t sbase = smem_u32(smem);
   // mbarriers, two of each (tile slot 0/1): x_full, a_ready, d_ready (hidden-layer MMAs), f_ready (output-layer MMAs), d_free
   const uint32_t bars = sbase + a.bar_ofs;
-  const uint32_t BX = 0, BA = 16, BD = 32, BF = 48, BE = 64, BW = 80;  // BW: bulk copy of a slot's parameter vector
+  const uint32_t BX = 0, BA = 24, BD = 48, BF = 72, BE = 96, BW = 120;  // 8 bytes per tile slot each; BW: bulk copy of a slot's parameter vector
   const bool has_y = a.y != nullptr;
   const int TP = FULL ? W : a.T;  // tags per row = row pitch of x / y / per-tag outputs
   const int L = a.last_layer + 1;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bars + BX + 8 * s, 1);
       mbar_init(bars + BA + 8 * s, MAIN_WARPS);
       mbar_init(bars + BD + 8 * s, 1);
@@ -353,7 +375,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
 
   // phase parities (each role uses the subset it waits on)
-  uint32_t ph_x0 = 0, ph_x1 = 0, ph_a = 0, ph_d0 = 0, ph_d1 = 0, ph_f0 = 0, ph_f1 = 0, ph_e = 0, ph_w = 0;
+  uint32_t ph_x = 0, ph_d = 0, ph_f = 0;  // one parity bit per tile slot
+  uint32_t ph_a = 0, ph_e = 0, ph_w = 0;
   int cur_slot = -1;
   // Work split.  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so work items are as long as
   // possible: whole jobs, dealt round-robin in waves of gridDim.x (neighbouring CTAs stream neighbouring jobs: cutting the whole
@@ -418,6 +441,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         const float* Ws = scratch + a.pofs[l];
         float* whi = reinterpret_cast<float*>(smem + a.whi_ofs[l]);
         __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>(smem + a.wlo_ofs[l]);
+        __nv_bfloat16* whb = reinterpret_cast<__nv_bfloat16*>(smem + a.whb_ofs);
         // one warp per weight row k, lanes over n: coalesced reads of the scratch copy, no index division
         for (int k = warp; k < K; k += NTHREADS / 32) {
           const float w0 = lane < N ? Ws[k * N + lane] : 0.f, w1v = lane + 32 < N ? Ws[k * N + lane + 32] : 0.f;
@@ -430,6 +454,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
                 const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xffffe000u);  // round to nearest TF32
                 whi[((k >> 2) * Np + n) * 4 + (k & 3)] = hi;
                 wlo[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2bfloat16_rn(w - hi);
+                whb[((k >> 3) * Np + n) * 8 + (k & 7)] = __float2bfloat16_rn(hi);
               } else {  // two FP16 images, both [K/8][Np][8]
                 const __half w1 = __float2half_rn(w);
                 reinterpret_cast<__half*>(whi)[((k >> 3) * Np + n) * 8 + (k & 7)] = w1;
@@ -462,43 +487,51 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
                      bar_e = bars + BE + 8 * s;
       const uint32_t xdst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
       const uint32_t tb = tmem + s * SLOT_COLS;
+      // the y rows of a tile are read ~7 layers after its x rows: ask for them in L2 now, so the output warps' loads do not wait on DRAM
+      auto prefetch_y = [&](int t) {
+        if (!has_y) return;
+        const int nrows = min(TILE, row_end - (row_begin + t * TILE));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.y + (xrow0 + (long)t * TILE) * TP), "r"((uint32_t)(nrows * TP * 4)) : "memory");
+      };
       if (s < n_tiles && leader) {
         mbar_expect_tx(bar_x, 2 * BOX_BYTES);
         tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)s * TILE), bar_x);
         tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)s * TILE), bar_x);
+        prefetch_y(s);
       }
-      for (int t = s; t < n_tiles; t += 2) {
+      for (int t = s; t < n_tiles; t += NSLOT) {
         for (int l = 0; l < L; ++l) {
           const int Np = a.Np[l], k8 = a.k8[l], k16 = a.k16[l];
           const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(l == 0 ? 1 : 0, Np);  // kind::f16 inputs: BF16 (layer 0) / FP16
           const uint32_t lbo = (uint32_t)Np * 16u;
           const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
-          const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128);
+          const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128), dhb = make_bdesc(sbase + a.whb_ofs, lbo, 128);
           mbar_wait(bar_a, ph_a);
           ph_a ^= 1;
           // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
           // layer (wait before layer 0); slot 1 sends only its output layer to the spare accumulator (wait before that layer)
-          if (t >= 2 && l == (s == 0 ? 0 : L - 1)) {
+          if (t >= NSLOT && l == (s == 0 ? 0 : L - 1)) {
             mbar_wait(bar_e, ph_e);
             ph_e ^= 1;
           }
-          const uint32_t dcol = (s == 1 && l == L - 1) ? tmem + COL_DX : tb + COL_D;
+          const uint32_t dcol = (s >= 1 && l == L - 1) ? tmem + COL_DX + (uint32_t)(s - 1) * 64u : tb + COL_D;
           tc_fence_after();
           if (leader && s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
           if (leader) {
-            if (l == 0 && t + 2 < n_tiles) {  // A0 is in TMEM => this slot's x boxes are free
+            if (l == 1 && t + NSLOT < n_tiles) {  // layer 0's MMAs (which read the x boxes) are complete => the boxes are free
               mbar_expect_tx(bar_x, 2 * BOX_BYTES);
-              tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
-              tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + 2) * TILE), bar_x);
+              tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)(t + NSLOT) * TILE), bar_x);
+              tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + NSLOT) * TILE), bar_x);
+              prefetch_y(t + NSLOT);
             }
             // straight-line issue (K <= 64 => at most 8 / 8 / 4 steps): measured 49 cycles per MMA against 73 for a rolled loop
             if (l == 0) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks)  // A_lo * W_hi (first MMA overwrites the accumulator)
-                if (ks < k8) mma_tf32_ts(dcol, tb + COL_ALO + ks * 8, dhi + (uint64_t)(ks * dstep), id32, ks > 0);
+              for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi: A is the x box (SWIZZLE_128B, 32 columns per box, 32 bytes per K step); first MMA overwrites
+                if (ks < k8) mma_tf32_ss(dcol, make_adesc_sw128(xdst + (ks >> 2) * BOX_BYTES) + (uint64_t)((ks & 3) * 2), dhi + (uint64_t)(ks * dstep), id32, ks > 0);
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi
-                if (ks < k8) mma_tf32_ts(dcol, tb + COL_AHI + ks * 8, dhi + (uint64_t)(ks * dstep), id32, 1);
+              for (int ks = 0; ks < 4; ++ks)  // bf16(A_lo) * bf16(W_hi)
+                if (ks < k16) mma_bf16_ts(dcol, tb + COL_ALB + ks * 8, dhb + (uint64_t)(ks * dstep), id16, 1);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)  // bf16(A) * bf16(W_lo)
                 if (ks < k16) mma_bf16_ts(dcol, tb + COL_ABF + ks * 8, dlo + (uint64_t)(ks * dstep), id16, 1);
@@ -526,17 +559,17 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
       // =========================================== layer-epilogue warps (SFU-bound): hidden layers only
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
+      for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
         // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
         for (int l = 0; l + 1 < L; ++l) {
           const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
           const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < NSLOT; ++s) {
             if (t0 + s >= n_tiles) continue;
             if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, s ? ph_d1 : ph_d0);
-            if (s) ph_d1 ^= 1; else ph_d0 ^= 1;
+            mbar_wait(bars + BD + 8 * s, (ph_d >> s) & 1u);
+            ph_d ^= 1u << s;
             tc_fence_after();
             if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
             const uint32_t sl = lane_base + s * SLOT_COLS;
@@ -570,8 +603,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // Only the accumulator has to change layout (TMEM gives one thread = one row): it goes once through this warp's swizzled
       // staging box; y is loaded straight into the transposed layout and every output column is formed and stored there.
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * 2 * OBOX_BYTES;  // transpose staging of the accumulator
-      const uint32_t ybox = stage + OBOX_BYTES;                                           // y rows of the second tile of a pair
+      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * OBOX_BYTES;  // transpose staging of the accumulator
       float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2 halves][2][TILE] row sums
       const int tr = lane >> 3, tc = lane & 7;
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
@@ -583,10 +615,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 
       // x -> A operand of layer 0 of tile `tt` (slot tt & 1): these warps have the slack, the layer warps do not
       auto split_x = [&](int tt) {
-        const int s = tt & 1;
+        const int s = tt % NSLOT;
         const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-        mbar_wait(bars + BX + 8 * s, s ? ph_x1 : ph_x0);
-        if (s) ph_x1 ^= 1; else ph_x0 ^= 1;
+        mbar_wait(bars + BX + 8 * s, (ph_x >> s) & 1u);
+        ph_x ^= 1u << s;
 #pragma unroll
         for (int piece = 0; piece < 4; ++piece) {  // 8 columns at a time keeps the register footprint small (y rows are live)
           float v[8];
@@ -606,7 +638,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // accumulator of the output layer -> this warp's staging box ("one thread = one row" -> row-major lines), accumulator freed
       auto park = [&](int s, int t) {
         float acc[32];
-        const uint32_t sl = lane_base + (s == 1 ? COL_DX : COL_D) + h * 32;
+        const uint32_t sl = lane_base + (s >= 1 ? COL_DX + (uint32_t)(s - 1) * 64u : COL_D) + h * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
 #pragma unroll
@@ -625,7 +657,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       float4 yt[8];
       // every output column of tile t from the staged accumulator; y comes from registers (first tile of a pair) or from the
       // warp's y box in shared memory (second tile, fetched with cp.async while the first was being written)
-      auto emit = [&](int t, bool y_smem) {
+      auto emit = [&](int t) {
         const int trow = row_begin + t * TILE;
         const int nrows = min(TILE, row_end - trow);
         const long grow0 = job.out_row + trow;
@@ -637,7 +669,6 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           float4 yh, yv = yt[i];
           const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
-          if (y_smem) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yv.x), "=f"(yv.y), "=f"(yv.z), "=f"(yv.w) : "r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u));
           if (!in_cols) yv = make_float4(0.f, 0.f, 0.f, 0.f);  // zero-padded columns (T < 64): model output is 0 there too
           yh.x += b4.x; yh.y += b4.y; yh.z += b4.z; yh.w += b4.w;  // output layer is linear
           if (!in_cols) yh = make_float4(0.f, 0.f, 0.f, 0.f);     // columns beyond T: the accumulator holds stale values there
@@ -657,7 +688,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
         __syncwarp();  // staging box reusable
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t & 1);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t % NSLOT);
         if (totals) {
           // row sums: 8 lanes (tc) hold the 32 columns of this half; halves meet in shared memory
 #pragma unroll
@@ -681,55 +712,57 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
           named_bar_sync(1 + q, 64);
         }
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t & 1);
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t % NSLOT);
+      };
+
+      // y rows of tile t -> registers (transposed layout), requested as early as the registers are free
+      auto load_y = [&](int t) {
+        const int trow = row_begin + t * TILE;
+        const int nrows = min(TILE, row_end - trow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = min(q * 32 + i * 4 + tr, nrows - 1);
+          yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto wait_f = [&](int s, int t) {
+        mbar_wait(bars + BF + 8 * s, (ph_f >> s) & 1u);
+        ph_f ^= 1u << s;
+        tc_fence_after();
+        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
       };
 
       split_x(0);
       if (n_tiles > 1) split_x(1);
+      if (NSLOT > 2 && n_tiles > 2) split_x(2);
 
-      for (int t0 = 0; t0 < n_tiles; t0 += 2) {
-        const bool two = t0 + 1 < n_tiles;
-        if (has_y) {
-          if (two) {  // y rows of the pair's second tile -> y box (asynchronously; needed only after the first tile is written)
-            const int trow = row_begin + (t0 + 1) * TILE;
-            const int nrows = min(TILE, row_end - trow);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + tr;
-              const float* src = a.y + (job.x_row + trow + min(q * 32 + r, nrows - 1)) * (long)TP + (in_cols ? h * 32 + tc * 4 : 0);
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ybox + (uint32_t)r * 128u + (uint32_t)tc * 16u), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-          }
-          const int trow = row_begin + t0 * TILE;
-          const int nrows = min(TILE, row_end - trow);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {  // y rows of the first tile -> registers, requested before its accumulator is ready
-            const int r = min(q * 32 + i * 4 + tr, nrows - 1);
-            yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed both slots their next tiles
+      for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
+        const int n_in = min(NSLOT, n_tiles - t0);
+        if (has_y) load_y(t0);  // requested before the tile's accumulator is ready
+        // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed every slot its next tile
         if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t0, L - 1, 0);
-        mbar_wait(bars + BF, ph_f0);
-        ph_f0 ^= 1;
-        tc_fence_after();
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0, L - 1, 0);
+        wait_f(0, t0);
         park(0, t0);
-        if (t0 + 2 < n_tiles) split_x(t0 + 2);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
-        if (two) {
-          mbar_wait(bars + BF + 8, ph_f1);
-          ph_f1 ^= 1;
-          tc_fence_after();
-          if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t0 + 1, L - 1, 1);
-          if (t0 + 3 < n_tiles) split_x(t0 + 3);  // slot 1's output sits in the spare accumulator until the stores below are done
+        if (t0 + NSLOT < n_tiles) split_x(t0 + NSLOT);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
+        if (n_in > 1) {
+          wait_f(1, t0 + 1);
+          if (t0 + NSLOT + 1 < n_tiles) split_x(t0 + NSLOT + 1);  // slots 1 and 2 keep their output in a spare accumulator until parked below
+        }
+        if (n_in > 2) {
+          wait_f(2, t0 + 2);
+          if (t0 + NSLOT + 2 < n_tiles) split_x(t0 + NSLOT + 2);
         }
         // ---- then the stores
-        emit(t0, false);
-        if (two) {
+        emit(t0);
+        if (n_in > 1) {
+          if (has_y) load_y(t0 + 1);
           park(1, t0 + 1);
-          asm volatile("cp.async.wait_all;" ::: "memory");
-          emit(t0 + 1, true);
+          emit(t0 + 1);
+        }
+        if (n_in > 2) {
+          if (has_y) load_y(t0 + 2);
+          park(2, t0 + 2);
+          emit(t0 + 2);
         }
       }
     }
@@ -797,7 +830,7 @@ extern "C" int gb_debug_set_trace(void* dev_buf, int capacity) {
 extern "C" int gb_ffae_tc_supported(const gb_ffnet* net) {
   if (gb::validate_ffnet(net) != GB_OK) return GB_E_SHAPE;
   const int L = net->n_layers;
-  if (L > MAXL || net->dims[0] != net->dims[L] || net->dims[0] > W || net->dims[0] < 24 || (net->dims[0] & 3)) {
+  if (L < 2 || L > MAXL || net->dims[0] != net->dims[L] || net->dims[0] > W || net->dims[0] < 24 || (net->dims[0] & 3)) {
     gb::set_error("tcgen05 variant covers autoencoders of 24..%d tags (a multiple of 4) with at most %d layers", W, MAXL);
     return GB_E_SHAPE;
   }
@@ -845,6 +878,10 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
     ofs += l == 0 ? a.k8[l] * 8 * a.Np[l] * 4 : a.k16[l] * 16 * a.Np[l] * 2;
     a.wlo_ofs[l] = ofs;
     ofs += a.k16[l] * 16 * a.Np[l] * 2;
+    if (l == 0) {
+      a.whb_ofs = ofs;
+      ofs += a.k16[l] * 16 * a.Np[l] * 2;
+    }
   }
   for (int l = 0; l < L; ++l) {
     a.bias_ofs[l] = ofs;
@@ -856,10 +893,10 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.pair_ofs = ofs; ofs += 4 * TILE * 4;
   a.bar_ofs = ofs; ofs += 128;
   ofs = gb::round_up(ofs, 1024);
-  a.xbox_ofs = ofs; ofs += 4 * BOX_BYTES;            // two tile slots x two 32-column boxes
-  a.stage_ofs = ofs; ofs += OUT_WARPS * 2 * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box + a y box of the same shape
+  a.xbox_ofs = ofs; ofs += 2 * NSLOT * BOX_BYTES;    // NSLOT tile slots x two 32-column boxes
+  a.stage_ofs = ofs; ofs += OUT_WARPS * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box
   const size_t smem = (size_t)ofs;
-  GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
+  GB_REQUIRE(smem + 4 * TRACE_SLOTS * 8 + 64 <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory in the tcgen05 variant", smem);
 
   int dev = 0, sms = 148;
   GB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -869,7 +906,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   a.n_jobs = n_jobs;
   a.pstride = (long)gb_ffnet_param_stride(net);
   a.param_bytes = (int)(gb_ffnet_param_stride(net) * sizeof(float));  // stride is a multiple of 4 floats
-  GB_REQUIRE(a.param_bytes <= 4 * BOX_BYTES + OUT_WARPS * 2 * OBOX_BYTES, GB_E_SMEM, "parameter vector of %d bytes exceeds the staging scratch", a.param_bytes);
+  GB_REQUIRE(a.param_bytes <= 2 * NSLOT * BOX_BYTES + OUT_WARPS * OBOX_BYTES, GB_E_SMEM, "parameter vector of %d bytes exceeds the staging scratch", a.param_bytes);
   a.bulk_params = (reinterpret_cast<uintptr_t>(params) % 16 == 0) ? 1 : 0;
   a.params = params; a.jobs = jobs; a.y = y; a.scale = scale; a.feat_thr = feat_thr; a.agg_thr = agg_thr;
   a.o_model = out_model; a.o_ts = out_tag_scaled; a.o_tu = out_tag_unscaled; a.o_conf = out_conf;

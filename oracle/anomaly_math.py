@@ -72,7 +72,10 @@ def rolling_min_then_max(a: np.ndarray, window: int) -> np.ndarray:
         res = np.full(a.shape[1], np.nan)
     else:
         win = np.lib.stride_tricks.sliding_window_view(a, window, axis=0)  # [n-w+1, cols, w]
-        res = win.min(axis=-1).max(axis=0)
+        mins = win.min(axis=-1)  # a window holding a NaN gives NaN (pandas rolling min with min_periods=window) ...
+        with np.errstate(all="ignore"), __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore", RuntimeWarning)
+            res = np.nanmax(mins, axis=0)  # ... which DataFrame.max() skips; a column without one complete window stays NaN
     return res[0] if one_d else res
 
 

@@ -180,3 +180,36 @@ def test_fleet_model_builder_end_to_end(engine, torch, tmp_path):
     # cross_val_only stops before the final fit (build_model.py:291-306)
     only, m = builder.ModelBuilder({**machines[0], "evaluation": {"cv_mode": "cross_val_only"}}).build()
     assert set(m["metadata"]["build_metadata"]["model"]) == {"cross_validation"} and m["metadata"]["build_metadata"]["model"]["cross_validation"]["scores"]
+
+
+def test_dropin_definition_on_the_gpu(engine, torch):
+    """
+    tests/test_reference_dropin.py runs the INTEGRATION.md definition through the REFERENCE'S from_definition / ModelBuilder._build /
+    serializer.dumps+loads (possible only where /root/reference exists, with the kernels mocked by the oracle) and commits the metadata
+    key tree and the anomaly frame's columns it produced (tests/golden/dropin.json).  Here the same definition and data run on the
+    real kernels -- per machine (`ModelBuilder`) and through the batched fleet path -- and must produce the same tree and columns.
+    """
+    import pickle
+
+    from test_reference_dropin import frame, key_tree
+
+    from gordo_components_b200 import builder
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "dropin.json")) as f:
+        want = json.load(f)
+    data = frame(**want["frame"])
+    machine = {"name": "dropin-machine", "model": want["definition"], "dataset": (data, data), "evaluation": want["evaluation"]}
+    single = builder.ModelBuilder(dict(machine)).build()
+    fleet = builder.FleetModelBuilder([dict(machine)]).build()[0]
+    for model, built in (single, fleet):
+        mb = dict(built["metadata"]["build_metadata"]["model"])
+        for k in ("model_creation_date", "model_training_duration_sec"):
+            mb.pop(k, None)
+        tree = json.loads(json.dumps(key_tree(mb)))
+        tree["cross_validation"].pop("cv_duration_sec", None)
+        assert tree == want["model_build_metadata_keys"]
+        model = pickle.loads(pickle.dumps(model))  # gordo/serializer/serializer.py:22-64 is pickle
+        X = data.iloc[-40:]
+        got = model.anomaly(X, X, frequency=pd.Timedelta("10min"))
+        assert [list(c) for c in got.columns] == want["anomaly_columns"]
+        assert np.isfinite(got["total-anomaly-confidence"].values).all() and len(got) == 40
