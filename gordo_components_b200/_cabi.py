@@ -93,7 +93,7 @@ def _declare(lib):
     lib.gb_thresholds_f64.restype = C.c_int
     lib.gb_cv_moments.argtypes = [_P, C.c_int32, _P, _P, C.c_int32, _P, _P]
     lib.gb_cv_moments.restype = C.c_int
-    lib.gb_smooth.argtypes = [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]
+    lib.gb_smooth.argtypes = [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]
     lib.gb_smooth.restype = C.c_int
     lib.gb_quantile.argtypes = [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_float, _P, _P]
     lib.gb_quantile.restype = C.c_int
@@ -128,8 +128,8 @@ def load_library():
                 )
             lib = C.CDLL(LIB_PATH)
             _declare(lib)
-            if lib.gb_abi_version() != 1:
-                raise GordoB200Error(f"ABI version mismatch: library {lib.gb_abi_version()}, binding 1")
+            if lib.gb_abi_version() != 2:
+                raise GordoB200Error(f"ABI version mismatch: library {lib.gb_abi_version()}, binding 2")
             _lib = lib
     return _lib
 

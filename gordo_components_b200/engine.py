@@ -325,8 +325,11 @@ def affine_f64(jobs_dev, n_jobs, max_rows, x64, a, b, out_rows=None):
 SMOOTH_METHODS = {"smm": 0, "sma": 1, "ewma": 2}
 
 
-def smooth(jobs_dev, n_jobs, arr, window: int, method: str):
-    """Rolling median / mean / EWMA of every column of ``arr`` ([rows] or [rows, cols]) per job (pandas semantics)."""
+def smooth(jobs_dev, n_jobs, arr, window: int, method: str, max_rows: Optional[int] = None):
+    """
+    Rolling median / mean / EWMA of every column of ``arr`` ([rows] or [rows, cols]) per job (pandas semantics, NaNs included).
+    ``max_rows``: longest job (defaults to the length of ``arr``, always an upper bound).
+    """
     torch = _torch()
     lib = _cabi.load_library()
     if method not in SMOOTH_METHODS:
@@ -334,7 +337,8 @@ def smooth(jobs_dev, n_jobs, arr, window: int, method: str):
     n_cols = 1 if arr.dim() == 1 else arr.shape[1]
     out = torch.full_like(arr, float("nan"))
     p = _cabi.ptr
-    _cabi.check(lib.gb_smooth(p(jobs_dev), int(n_jobs), p(arr), int(n_cols), int(window), SMOOTH_METHODS[method], p(out), _stream_ptr()))
+    _cabi.check(lib.gb_smooth(p(jobs_dev), int(n_jobs), int(max_rows if max_rows is not None else arr.shape[0]), p(arr), int(n_cols), int(window),
+                              SMOOTH_METHODS[method], p(out), _stream_ptr()))
     return out
 
 

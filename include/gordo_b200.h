@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 1
+#define GB_ABI_VERSION 2
 #define GB_MAX_LAYERS 16
 #define GB_MAX_WIDTH 256 /* widest layer / feature count (the feedforward_model / feedforward_symmetric defaults are 256-128-64) */
 
@@ -163,14 +163,18 @@ int gb_cv_moments(const gb_job* jobs, int32_t n_jobs, const float* yhat, const f
                   double* out, void* stream);
 
 /* ---- K6: optional smoothing of anomaly columns (diff.py:302-308, 387-415) ------------------
- * method 0 = smm rolling(window).median(), 1 = sma rolling(window).mean() (first window-1 rows NaN),
- * 2 = ewma ewm(span=window).mean() (adjust=True).  arr / out: [rows][n_cols], rows taken at [out_row, out_row+n_rows). */
-int gb_smooth(const gb_job* jobs, int32_t n_jobs, const float* arr, int32_t n_cols, int32_t window, int32_t method,
+ * method 0 = smm rolling(window).median(), 1 = sma rolling(window).mean() (first window-1 rows NaN; a window holding a NaN
+ * gives NaN), 2 = ewma ewm(span=window).mean() (adjust=True, ignore_na=False: a NaN adds no observation, ages the weights and the
+ * previous average is carried forward).  arr / out: [rows][n_cols], rows taken at [out_row, out_row+n_rows); max_rows = max n_rows
+ * over jobs (sizes the row-chunk grid of the rolling kernels).  The rolling median keeps one sorted window per thread in shared
+ * memory: windows up to 51 200 rows. */
+int gb_smooth(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* arr, int32_t n_cols, int32_t window, int32_t method,
               float* out, void* stream);
 
 /* ---- K9: percentile thresholds of DiffBasedKFCVAnomalyDetector (diff.py:623-635: smoothed validation metric
  * .quantile(threshold_percentile)).  out[job][c] = q-quantile (linear interpolation, NaNs skipped -- pandas
- * semantics) of column c of rows [out_row, out_row+n_rows) of arr [rows][n_cols]; at most 32768 rows per job. */
+ * semantics) of column c of rows [out_row, out_row+n_rows) of arr [rows][n_cols].  Jobs of up to 32768 rows are sorted in shared
+ * memory; longer ones (a year of 10-minute data is ~52k rows) find the two order statistics by radix selection over L2. */
 int gb_quantile(const gb_job* jobs, int32_t n_jobs, int32_t max_rows, const float* arr, int32_t n_cols, float q,
                 float* out, void* stream);
 

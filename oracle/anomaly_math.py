@@ -92,13 +92,24 @@ def smoothing(metric: np.ndarray, window: int, method: str) -> np.ndarray:
             win = np.lib.stride_tricks.sliding_window_view(a, window, axis=0)
             out[window - 1 :] = np.median(win, axis=-1) if method == "smm" else win.mean(axis=-1)
     elif method == "ewma":
+        # pandas/_libs/window/aggregations.pyx ewm() [3P, pandas 1.5.3]: adjust=True, ignore_na=False, min_periods=0 -- a NaN adds no
+        # observation but ages the weights, the previous average is carried forward, leading NaNs stay NaN
         alpha = 2.0 / (window + 1.0)
-        num = np.zeros(a.shape[1])
-        den = 0.0
-        for t in range(n):
-            num = num * (1 - alpha) + a[t]
-            den = den * (1 - alpha) + 1.0
-            out[t] = num / den
+        for c in range(a.shape[1]):
+            weighted, old_wt = a[0, c] if n else np.nan, 1.0
+            if n:
+                out[0, c] = weighted
+            for t in range(1, n):
+                cur = a[t, c]
+                if weighted == weighted:
+                    old_wt *= 1.0 - alpha
+                    if cur == cur:
+                        if weighted != cur:
+                            weighted = (old_wt * weighted + cur) / (old_wt + 1.0)
+                        old_wt += 1.0
+                elif cur == cur:
+                    weighted = cur
+                out[t, c] = weighted
     else:
         raise ValueError(method)
     return out[:, 0] if one_d else out

@@ -143,7 +143,7 @@ def _affine_f64(jobs_dev, n_jobs, max_rows, x64, a, b, out_rows=None):
     return torch.from_numpy(out)
 
 
-def _smooth(jobs_dev, n_jobs, arr, window, method):
+def _smooth(jobs_dev, n_jobs, arr, window, method, max_rows=None):
     a = _np(arr)
     out = np.full_like(a, np.nan)
     for job in _jobs(jobs_dev)[:n_jobs]:

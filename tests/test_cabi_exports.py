@@ -33,7 +33,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_struct_layout(lib):
-    assert lib.gb_abi_version() == 1
+    assert lib.gb_abi_version() == 2
     assert C.sizeof(_cabi.GbJob) == 24
     assert C.sizeof(_cabi.GbFFNet) == 4 + 4 * 17 + 4 * 16 + 4 * 16
     assert C.sizeof(_cabi.GbFitHParams) == 48

@@ -368,6 +368,34 @@ def test_smoothing_against_reference_fixture(engine, torch, case):
         close(got, want, float(np.nanmax(np.abs(want))), rtol=1e-5, name=f"{case} smooth-{top}")
 
 
+@pytest.mark.parametrize("method", ["smm", "sma", "ewma"])
+def test_smoothing_with_interior_nans_matches_pandas(engine, torch, method):
+    """
+    Missing sensor values reach the smoothing kernels through requests (the reference tolerates them): pandas' semantics are a NaN
+    window for rolling median / mean while the NaN is inside, and for ewm (adjust=True, ignore_na=False) no observation, aged weights
+    and the previous average carried forward.  Two ragged jobs crossing the 128-row chunk boundary, even and odd windows, a window
+    longer than a job, a wide window (fewer columns per CTA).
+    """
+    dev = engine.cuda_device()
+    rng = np.random.default_rng(17)
+    lens = [700, 45]
+    n, cols = sum(lens), 5
+    a = rng.random((n, cols)).astype(np.float32)
+    a[[3, 130, 131, 400, 699, 710], 1] = np.nan      # interior NaNs, one at a job's last row
+    a[:7, 2] = np.nan                                # leading NaNs
+    a[100:260, 3] = np.nan                           # a gap longer than the window
+    a[:, 4] = np.nan                                 # nothing but NaNs
+    starts = np.cumsum([0] + lens[:-1])
+    jobs = engine.jobs_to_device(engine.make_jobs([0, 1], lens, starts), dev)
+    for window in ((6, 13, 144, 1000) if method != "smm" else (6, 13, 144, 900)):
+        got = engine.smooth(jobs, 2, torch.from_numpy(a).to(dev), window, method, max_rows=max(lens)).cpu().numpy()
+        for s0, m in zip(starts, lens):
+            frame = pd.DataFrame(a[s0:s0 + m].astype(np.float64))
+            want = {"smm": lambda: frame.rolling(window).median(), "sma": lambda: frame.rolling(window).mean(), "ewma": lambda: frame.ewm(span=window).mean()}[method]().values
+            assert np.array_equal(np.isnan(got[s0:s0 + m]), np.isnan(want)), (method, window)
+            np.testing.assert_allclose(got[s0:s0 + m], want, rtol=2e-6, atol=1e-7, err_msg=f"{method} window {window}")
+
+
 def test_detector_with_window_like_reference_tests(engine, torch):
     """test_anomaly_detectors.py:123-371: window/smoothing_method add four smooth-* blocks with window-1 leading NaNs."""
     from sklearn.linear_model import LinearRegression
@@ -858,8 +886,11 @@ def test_kfcv_detector_against_reference_generated_fixture(engine, torch, case):
 def test_quantile_kernel_matches_pandas(engine, torch):
     rng = np.random.default_rng(0)
     dev = engine.cuda_device()
-    for n, cols in [(1, 3), (2, 1), (777, 5), (4096, 2), (10000, 3)]:
+    # up to 32768 rows: bitonic sort in shared memory; beyond (a year of 10-minute data is ~52k rows): radix selection over L2
+    for n, cols in [(1, 3), (2, 1), (777, 5), (4096, 2), (10000, 3), (32768, 2), (32769, 2), (52560, 3)]:
         a = rng.normal(size=(n, cols)).astype(np.float32)
+        if n > 30000:
+            a[:, -1] = np.round(a[:, -1], 1)  # heavy ties: both order statistics inside one run of equal values
         a[rng.random(a.shape) < 0.1] = np.nan
         if n > 100:
             a[:, 0] = np.nan  # an all-NaN column stays NaN
