@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sma_kernel(const gb_job* jo
   float* dst = out + job.out_row * (long)n_cols + j;
   double sum = 0.0;
   int bad = 0;  // NaNs currently inside the window
-  for (int t = max(0, t0 - window + 1); t < t0; ++t) {  // rows of the first window that precede the chunk
+  for (int t = max(0, t0 - window); t < t0; ++t) {  // window state as the row before the chunk left it: rows [t0 - window, t0)
     const float v = src[(long)t * n_cols];
     if (v == v) sum += (double)v; else ++bad;
   }
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_median_kernel(const gb_job*
     for (int i = lo; i + 1 < count; ++i) win[i * nthr] = win[(i + 1) * nthr];
     --count;
   };
-  for (int t = max(0, t0 - window + 1); t < t0; ++t) insert(src[(long)t * n_cols]);
+  for (int t = max(0, t0 - window); t < t0; ++t) insert(src[(long)t * n_cols]);  // window state as the row before the chunk left it
   for (int t = t0; t < t1; ++t) {
     if (t >= window) remove(src[(long)(t - window) * n_cols]);
     insert(src[(long)t * n_cols]);

@@ -163,7 +163,8 @@ class FleetBuild:
     """
 
     def __init__(self, eng, n_machines, n_splits, params, scale, offset, feat_thr, agg_thr, loss, acc, fold_loss, fold_feat_thr, fold_agg_thr,
-                 fold_params=None, cv_moments=None, in_scale=None, in_offset=None, fold_in_scale=None, fold_in_offset=None):
+                 fold_params=None, cv_moments=None, in_scale=None, in_offset=None, fold_in_scale=None, fold_in_offset=None, steps_per_epoch=None):
+        self.steps_per_epoch = steps_per_epoch                                 # optimizer steps per epoch of the final fit (keras History.params["steps"])
         # float64 scale_ / min_ of the MinMaxScaler in front of the network ([M, T]; per CV fold [M, K, T]); None without one
         self.in_scale, self.in_offset, self.fold_in_scale, self.fold_in_offset = in_scale, in_offset, fold_in_scale, fold_in_offset
         self.eng, self.n_machines, self.n_splits = eng, n_machines, n_splits
@@ -221,7 +222,7 @@ class FleetBuild:
             spec = FFNetSpec(list(eng.dims), list(eng.acts), list(eng.l1))
             ae.model = FittedNet(spec, eng.unpack_params(self.params[m : m + 1])[0])
         hist = {"loss": [float(v) for v in self.loss[m].cpu().numpy()], "accuracy": [float(v) for v in self.acc[m].cpu().numpy()]}
-        ae._history = History(hist, {"verbose": 0, "epochs": len(hist["loss"]), "steps": None}, list(range(len(hist["loss"]))))
+        ae._history = History(hist, {"verbose": 0, "epochs": len(hist["loss"]), "steps": self.steps_per_epoch}, list(range(len(hist["loss"]))))
         sc = self._fill_minmax(MinMaxScaler(), self.scale[m].cpu().numpy().astype(np.float64), self.offset[m].cpu().numpy().astype(np.float64), None)
         if template is not None:
             det = template
@@ -347,4 +348,5 @@ def build_fleet(eng: "engine.FFEngine", x, y, rows: int, epochs: int = 1, batch_
                       fold_params=fold_params, cv_moments=moments,
                       in_scale=None if in_scale is None else in_scale[:M].contiguous(), in_offset=None if in_offset is None else in_offset[:M].contiguous(),
                       fold_in_scale=None if in_scale is None else in_scale[M:].view(K, M, -1).permute(1, 0, 2).contiguous(),
-                      fold_in_offset=None if in_offset is None else in_offset[M:].view(K, M, -1).permute(1, 0, 2).contiguous())
+                      fold_in_offset=None if in_offset is None else in_offset[M:].view(K, M, -1).permute(1, 0, 2).contiguous(),
+                      steps_per_epoch=(N + int(batch_size) - 1) // int(batch_size))
