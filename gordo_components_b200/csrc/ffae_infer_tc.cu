@@ -38,7 +38,10 @@ namespace {
 
 constexpr int TILE = 128;
 #ifndef GB_TC_NSLOT
-#define GB_TC_NSLOT 3
+#define GB_TC_NSLOT 2  // measured (profiles/r02_*): three slots convoy behind the in-order layer warps and run 40 % slower than two
+#endif
+#ifndef GB_TC_STATIC
+#define GB_TC_STATIC 1  // 0: always the generic instantiation (A/B measurements)
 #endif
 constexpr int NSLOT = GB_TC_NSLOT;  // tiles in flight (2 or 3)
 static_assert(NSLOT == 2 || NSLOT == 3, "two or three tile slots");
@@ -323,9 +326,58 @@ __device__ __forceinline__ void hidden_epilogue_pair(uint32_t slot_lane, int c0,
   if (C2 > 0) hidden_epilogue<(C2 > 0 ? C2 : 4), NE>(slot_lane, c0 + C1, bias_all + c0 + C1);
 }
 
+// One lane of a converged warp.  Code under `if (elect_one())` lets ptxas prove that a single thread executes it: the
+// tcgen05.mma / TMA instructions inside become straight-line uniform-datapath SASS (UTCHMMA back to back), whereas `if (lane == 0)`
+// wraps every one of them in an ELECT / BRA.U.ANY loop over the possibly-active lanes (~20 SASS instructions per MMA, measured
+// 90-120 cycles per MMA in situ against ~30 for the tensor pipe itself).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- layer tables.  The generic kernel reads per-layer sizes and shared-memory offsets from TcArgs (uniform loads, runtime loop
+// bounds).  For the BASELINE architecture, feedforward_hourglass(64) = 64-53-43-32-32-43-53-64, the same numbers are compile-time
+// constants (STATIC instantiation): the layer loops unroll, MMA counts / descriptors / epilogue widths fold, and the control
+// warp's per-layer issue block is a handful of uniform adds between UTCHMMAs.  The table mirrors the host-side layout code in
+// gb_ffae_infer_score_tc, which verifies the match before choosing the STATIC kernel.
+template <int V> struct IC { static constexpr int value = V; };
+constexpr int HG_L = 7;
+constexpr int HG_DIMS[HG_L + 1] = {64, 53, 43, 32, 32, 43, 53, 64};
+constexpr int hg_ru(int v, int m) { return (v + m - 1) / m * m; }
+template <int l> struct HGL {
+  static constexpr int K = HG_DIMS[l], N = HG_DIMS[l + 1];
+  static constexpr int Np = hg_ru(N, 16), n8 = hg_ru(N, 8), k8 = hg_ru(K, 8) / 8, k16 = hg_ru(K, 16) / 16;
+  static constexpr int whi_bytes = l == 0 ? k8 * 8 * Np * 4 : k16 * 16 * Np * 2, wlo_bytes = k16 * 16 * Np * 2, whb_bytes = l == 0 ? k16 * 16 * Np * 2 : 0;
+  static constexpr int whi_ofs = HGL<l - 1>::end_ofs, wlo_ofs = whi_ofs + whi_bytes, whb_ofs = wlo_ofs + wlo_bytes, end_ofs = whb_ofs + whb_bytes;
+};
+template <> struct HGL<-1> { static constexpr int end_ofs = 0; };
+template <int l> constexpr int HG_BIAS_OFS = HGL<HG_L - 1>::end_ofs + 64 * 4 * l;  // biases follow the last weight image, 64 floats per layer
+
+struct LayerP { int K, N, Np, n8, k8, k16, whi_ofs, wlo_ofs, bias_ofs; };
+template <int V> __device__ __forceinline__ LayerP layer_of(const TcArgs&, IC<V>) {
+  return LayerP{HGL<V>::K, HGL<V>::N, HGL<V>::Np, HGL<V>::n8, HGL<V>::k8, HGL<V>::k16, HGL<V>::whi_ofs, HGL<V>::wlo_ofs, HG_BIAS_OFS<V>};
+}
+__device__ __forceinline__ LayerP layer_of(const TcArgs& a, int l) {
+  return LayerP{a.K[l], a.N[l], a.Np[l], a.n8[l], a.k8[l], a.k16[l], a.whi_ofs[l], a.wlo_ofs[l], a.bias_ofs[l]};
+}
+template <int V> __device__ __forceinline__ constexpr int layer_index(IC<V>) { return V; }
+__device__ __forceinline__ int layer_index(int l) { return l; }
+// f(l) for l = 0 .. n-1: compile-time indices (n == HG_L or HG_L - 1) in the STATIC kernel, a runtime loop otherwise
+template <bool STATIC, bool HIDDEN_ONLY, class F>
+__device__ __forceinline__ void for_layers(int n, F&& f) {
+  if constexpr (STATIC) {
+    f(IC<0>{}); f(IC<1>{}); f(IC<2>{}); f(IC<3>{}); f(IC<4>{}); f(IC<5>{});
+    if constexpr (!HIDDEN_ONLY) f(IC<6>{});
+  } else {
+    for (int l = 0; l < n; ++l) f(l);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 // FULL: 64 tags (the row pitch and every column guard fold to constants -- the BASELINE workload); otherwise T < 64 rides in padded columns
-template <int NE, bool FULL>
+// STATIC (implies FULL): the feedforward_hourglass(64) stack with every layer constant folded (see the layer tables above)
+template <int NE, bool FULL, bool STATIC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap map_x) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -351,7 +403,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t BX = 0, BA = 24, BD = 48, BF = 72, BE = 96, BW = 120;  // 8 bytes per tile slot each; BW: bulk copy of a slot's parameter vector
   const bool has_y = a.y != nullptr;
   const int TP = FULL ? W : a.T;  // tags per row = row pitch of x / y / per-tag outputs
-  const int L = a.last_layer + 1;
+  const int L = STATIC ? HG_L : a.last_layer + 1;
 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
@@ -481,50 +533,46 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // =========================================== control warp of tile slot s: TMA producer + MMA issuer.
       // The whole warp walks the (warp-uniform) control flow; one elected lane issues the asynchronous instructions.
       const int s = warp - EPI_WARPS;
-      const bool leader = lane == 0;
       const long xrow0 = job.x_row + row_begin;
       const uint32_t bar_x = bars + BX + 8 * s, bar_a = bars + BA + 8 * s, bar_d = bars + BD + 8 * s, bar_f = bars + BF + 8 * s,
                      bar_e = bars + BE + 8 * s;
       const uint32_t xdst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
       const uint32_t tb = tmem + s * SLOT_COLS;
-      // the y rows of a tile are read ~7 layers after its x rows: ask for them in L2 now, so the output warps' loads do not wait on DRAM
-      auto prefetch_y = [&](int t) {
-        if (!has_y) return;
-        const int nrows = min(TILE, row_end - (row_begin + t * TILE));
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.y + (xrow0 + (long)t * TILE) * TP), "r"((uint32_t)(nrows * TP * 4)) : "memory");
-      };
-      if (s < n_tiles && leader) {
+      const uint32_t whb_ofs = STATIC ? HGL<0>::whb_ofs : a.whb_ofs;
+      // x boxes of tile t by TMA; its y rows are read ~7 layers later: ask for them in L2 now, so the output warps' loads do not wait on DRAM
+      auto fetch_tile = [&](int t) {
         mbar_expect_tx(bar_x, 2 * BOX_BYTES);
-        tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)s * TILE), bar_x);
-        tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)s * TILE), bar_x);
-        prefetch_y(s);
-      }
+        tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)t * TILE), bar_x);
+        tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)t * TILE), bar_x);
+        if (has_y) {
+          const int nrows = min(TILE, row_end - (row_begin + t * TILE));
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.y + (xrow0 + (long)t * TILE) * TP), "r"((uint32_t)(nrows * TP * 4)) : "memory");
+        }
+      };
+      if (s < n_tiles && elect_one()) fetch_tile(s);
+      __syncwarp();
       for (int t = s; t < n_tiles; t += NSLOT) {
-        for (int l = 0; l < L; ++l) {
-          const int Np = a.Np[l], k8 = a.k8[l], k16 = a.k16[l];
+        for_layers<STATIC, false>(L, [&](auto lc) {
+          const int l = layer_index(lc);
+          const LayerP P = layer_of(a, lc);
+          const int Np = P.Np, k8 = P.k8, k16 = P.k16;
           const uint32_t id32 = make_idesc(2, Np), id16 = make_idesc(l == 0 ? 1 : 0, Np);  // kind::f16 inputs: BF16 (layer 0) / FP16
           const uint32_t lbo = (uint32_t)Np * 16u;
           const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
-          const uint64_t dhi = make_bdesc(sbase + a.whi_ofs[l], lbo, 128), dlo = make_bdesc(sbase + a.wlo_ofs[l], lbo, 128), dhb = make_bdesc(sbase + a.whb_ofs, lbo, 128);
+          const uint64_t dhi = make_bdesc(sbase + P.whi_ofs, lbo, 128), dlo = make_bdesc(sbase + P.wlo_ofs, lbo, 128), dhb = make_bdesc(sbase + whb_ofs, lbo, 128);
           mbar_wait(bar_a, ph_a);
           ph_a ^= 1;
           // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
-          // layer (wait before layer 0); slot 1 sends only its output layer to the spare accumulator (wait before that layer)
+          // layer (wait before layer 0); the other slots send only their output layer to a spare accumulator (wait before that layer)
           if (t >= NSLOT && l == (s == 0 ? 0 : L - 1)) {
             mbar_wait(bar_e, ph_e);
             ph_e ^= 1;
           }
           const uint32_t dcol = (s >= 1 && l == L - 1) ? tmem + COL_DX + (uint32_t)(s - 1) * 64u : tb + COL_D;
           tc_fence_after();
-          if (leader && s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
-          if (leader) {
-            if (l == 1 && t + NSLOT < n_tiles) {  // layer 0's MMAs (which read the x boxes) are complete => the boxes are free
-              mbar_expect_tx(bar_x, 2 * BOX_BYTES);
-              tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)(t + NSLOT) * TILE), bar_x);
-              tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)(t + NSLOT) * TILE), bar_x);
-              prefetch_y(t + NSLOT);
-            }
-            // straight-line issue (K <= 64 => at most 8 / 8 / 4 steps): measured 49 cycles per MMA against 73 for a rolled loop
+          if (elect_one()) {
+            if (s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
+            if (l == 1 && t + NSLOT < n_tiles) fetch_tile(t + NSLOT);  // layer 0's MMAs (which read the x boxes) are complete => the boxes are free
             if (l == 0) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)  // A_hi * W_hi: A is the x box (SWIZZLE_128B, 32 columns per box, 32 bytes per K step); first MMA overwrites
@@ -554,16 +602,18 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             if (s == 0) trace_ev(a, ring, trace_cnt, 2, t, l, s);
           }
           __syncwarp();
-        }
+        });
       }
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
       // =========================================== layer-epilogue warps (SFU-bound): hidden layers only
       for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
         // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
-        for (int l = 0; l + 1 < L; ++l) {
-          const int half = a.n8[l] >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
-          const float* bl = reinterpret_cast<const float*>(smem + a.bias_ofs[l]);
+        for_layers<STATIC, true>(L - 1, [&](auto lc) {
+          const int l = layer_index(lc);
+          const LayerP P = layer_of(a, lc);
+          const int half = P.n8 >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
+          const float* bl = reinterpret_cast<const float*>(smem + P.bias_ofs);
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s) {
             if (t0 + s >= n_tiles) continue;
@@ -584,10 +634,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
               case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
               default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
             }
-            if (h == 1 && a.n8[l] < a.Np[l]) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
+            if (h == 1 && P.n8 < P.Np) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
               const uint32_t z[4] = {0u, 0u, 0u, 0u};
-              tmem_st4(sl + COL_A1 + (a.n8[l] >> 1), z);
-              tmem_st4(sl + COL_A2 + (a.n8[l] >> 1), z);
+              tmem_st4(sl + COL_A1 + (P.n8 >> 1), z);
+              tmem_st4(sl + COL_A2 + (P.n8 >> 1), z);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -595,7 +645,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
             if (lane == 0) mbar_arrive(bars + BA + 8 * s);
             if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t0 + s, l, s);
           }
-        }
+        });
       }
     } else {
       // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
@@ -608,7 +658,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const int tr = lane >> 3, tc = lane & 7;
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
       const float4 rt4 = *reinterpret_cast<const float4*>(vec + W + h * 32 + tc * 4);
-      const float4 b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + a.bias_ofs[L - 1]) + h * 32 + tc * 4);
+      const float4 b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + (STATIC ? HG_BIAS_OFS<HG_L - 1> : a.bias_ofs[L - 1])) + h * 32 + tc * 4);
       const float inv_w = 1.0f / (float)TP;
       const bool in_cols = FULL || h * 32 + tc * 4 < TP;  // this lane's four columns exist (T is a multiple of 4)
       const bool totals = has_y && (a.o_tots || a.o_totu || a.o_totconf);
@@ -925,7 +975,18 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
     kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx);
     return GB_OK;
   };
-  rc = a.T == W ? launch(ffae_tc_kernel<DEFAULT_NE, true>) : launch(ffae_tc_kernel<DEFAULT_NE, false>);  // NE = 2..4 (part of the tanh evaluations on the FMA pipe) measured 1-5 % slower
+  // the BASELINE stack runs the constant-folded instantiation when the host layout above equals the compile-time table
+  bool hg = GB_TC_STATIC && L == HG_L && a.last_layer == L - 1 && a.whb_ofs == HGL<0>::whb_ofs;
+  for (int l = 0; hg && l <= L; ++l) hg = net->dims[l] == HG_DIMS[l];
+  {
+    const int want_whi[HG_L] = {HGL<0>::whi_ofs, HGL<1>::whi_ofs, HGL<2>::whi_ofs, HGL<3>::whi_ofs, HGL<4>::whi_ofs, HGL<5>::whi_ofs, HGL<6>::whi_ofs};
+    const int want_wlo[HG_L] = {HGL<0>::wlo_ofs, HGL<1>::wlo_ofs, HGL<2>::wlo_ofs, HGL<3>::wlo_ofs, HGL<4>::wlo_ofs, HGL<5>::wlo_ofs, HGL<6>::wlo_ofs};
+    const int want_bias[HG_L] = {HG_BIAS_OFS<0>, HG_BIAS_OFS<1>, HG_BIAS_OFS<2>, HG_BIAS_OFS<3>, HG_BIAS_OFS<4>, HG_BIAS_OFS<5>, HG_BIAS_OFS<6>};
+    for (int l = 0; hg && l < L; ++l) hg = a.whi_ofs[l] == want_whi[l] && a.wlo_ofs[l] == want_wlo[l] && a.bias_ofs[l] == want_bias[l];
+  }
+  // NE = 2..4 (part of the tanh evaluations on the FMA pipe) measured 1-5 % slower
+  rc = hg ? launch(ffae_tc_kernel<DEFAULT_NE, true, true>)
+          : (a.T == W ? launch(ffae_tc_kernel<DEFAULT_NE, true, false>) : launch(ffae_tc_kernel<DEFAULT_NE, false, false>));
   if (rc != GB_OK) return rc;
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
