@@ -45,8 +45,16 @@ constexpr int TILE = 128;
 #endif
 constexpr int NSLOT = GB_TC_NSLOT;  // tiles in flight (2 or 3)
 static_assert(NSLOT == 2 || NSLOT == 3, "two or three tile slots");
-constexpr int NTHREADS = 512 + 32 * NSLOT;  // warps 0-7: layer epilogues (SFU-bound); 8-15: output epilogue (LSU-bound); 16,17,18: control of slot 0 / 1 / 2
-constexpr int MAIN_WARPS = 8, OUT_WARPS = 8, EPI_WARPS = MAIN_WARPS + OUT_WARPS;  // in both groups: warp%4 = TMEM lane quadrant, (warp/4)%2 = column half
+#ifndef GB_TC_DEDICATED
+#define GB_TC_DEDICATED 0  // 1: every tile slot has its own eight layer warps (26 warps: 72 registers per thread, measured 40 % slower: the output warps spill and starve); 0: one group of eight serves the slots in turn
+#endif
+// Warp roles.  Layer warps (SFU-bound hidden-layer epilogues): MAIN_WARPS per group, one group per tile slot (DEDICATED) or one
+// group for all slots; then OUT_WARPS output warps (LSU-bound: x split, accumulator parking, anomaly columns); then one control warp
+// per slot.  In every group warp%4 = TMEM lane quadrant and (warp/4)%2 = column half.  With one shared group the slots' epilogues
+// serialise (the timeline showed each MMA commit waiting 1.2-2.1k cycles for the group to finish the other slot, with the SFU only
+// ~40 % busy); dedicated groups let both slots' epilogues run at once.
+constexpr int MAIN_WARPS = 8, LAYER_GROUPS = GB_TC_DEDICATED ? NSLOT : 1, OUT0 = MAIN_WARPS * LAYER_GROUPS, OUT_WARPS = 8, EPI_WARPS = OUT0 + OUT_WARPS;
+constexpr int NTHREADS = 32 * (EPI_WARPS + NSLOT);
 constexpr int MAXL = 8;
 constexpr int BOX_BYTES = TILE * 128;  // x box: 128 rows x 32 fp32 (SWIZZLE_128B)
 constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 rows x 32 fp32
@@ -84,7 +92,7 @@ constexpr int DEFAULT_NE = 0;
 
 // debug timeline (gb_debug_set_trace): three recorder threads of CTA 0 (epilogue tid 0, the two control leaders) stamp
 // events into shared memory (one clock read + one store each) and flush them to global memory when the kernel ends
-constexpr int TRACE_SLOTS = 64;  // (scratch/dbg_trace.py must be told: the buffer layout depends on it)
+constexpr int TRACE_SLOTS = 256;  // events per recorder (gb_debug_trace_slots() tells the reader: the buffer layout depends on it)
 __device__ __forceinline__ void trace_ev(const TcArgs& a, unsigned long long* ring, int& cnt, int code, int tile, int layer, int slot) {
   if (a.trace == nullptr || blockIdx.x != 0 || cnt >= TRACE_SLOTS || (tile < a.trace_from && tile >= a.trace_head)) return;
   ring[cnt++] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(tile & 0xfff) << 12) | ((layer & 0xf) << 8) | ((slot & 0xf) << 4) | (code & 0xf);  // code < 16
@@ -393,7 +401,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     a.trace[4 + 4 * TRACE_SLOTS + 2] = (long long)ns;
   }
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction (lets the compiler use uniform registers)
-  const bool is_ctrl = warp >= EPI_WARPS, is_out = !is_ctrl && warp >= MAIN_WARPS;
+  const bool is_ctrl = warp >= EPI_WARPS, is_out = !is_ctrl && warp >= OUT0;
   unsigned long long* ring = s_trace[is_ctrl ? (warp == EPI_WARPS ? 1 : 0) : (is_out ? (warp == EPI_WARPS - 1 ? 2 : 3) : 0)];
   const int q = warp & 3, h = (warp >> 2) & 1;  // TMEM lane quadrant (rows 32q..) / column half
   const int row = q * 32 + lane;                // tile row owned by this thread in the "one thread = one row" layout
@@ -607,8 +615,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       if (s < n_tiles) ph_e ^= 1;  // the last tile's d_free phase completes before the item-end barrier and is never waited on
     } else if (!is_out) {
       // =========================================== layer-epilogue warps (SFU-bound): hidden layers only
+      // D -> bias, tanh -> next layer's A operand.  A dedicated group owns slot `grp` (tiles grp, grp + NSLOT, ...); a shared group
+      // visits the slots in turn, layer by layer (one slot's epilogue then overlaps the other slot's MMAs).
+      const int grp = GB_TC_DEDICATED ? warp / MAIN_WARPS : 0;
       for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
-        // D -> bias, tanh -> next layer's A operand (tile s' epilogue overlaps tile 1-s' MMAs)
         for_layers<STATIC, true>(L - 1, [&](auto lc) {
           const int l = layer_index(lc);
           const LayerP P = layer_of(a, lc);
@@ -616,7 +626,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           const float* bl = reinterpret_cast<const float*>(smem + P.bias_ofs);
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s) {
-            if (t0 + s >= n_tiles) continue;
+            if (t0 + s >= n_tiles || (GB_TC_DEDICATED && s != grp)) continue;
             if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
             mbar_wait(bars + BD + 8 * s, (ph_d >> s) & 1u);
             ph_d ^= 1u << s;
@@ -653,7 +663,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // Only the accumulator has to change layout (TMEM gives one thread = one row): it goes once through this warp's swizzled
       // staging box; y is loaded straight into the transposed layout and every output column is formed and stored there.
       const float* vec = reinterpret_cast<const float*>(smem + a.vec_ofs);
-      const uint32_t stage = sbase + a.stage_ofs + (warp - MAIN_WARPS) * OBOX_BYTES;  // transpose staging of the accumulator
+      const uint32_t stage = sbase + a.stage_ofs + (warp - OUT0) * OBOX_BYTES;  // transpose staging of the accumulator
       float* pair = reinterpret_cast<float*>(smem + a.pair_ofs);  // [2 halves][2][TILE] row sums
       const int tr = lane >> 3, tc = lane & 7;
       const float4 sc4 = *reinterpret_cast<const float4*>(vec + h * 32 + tc * 4);
@@ -683,7 +693,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-        if (lane == 0 && warp == MAIN_WARPS) trace_ev(a, ring, trace_cnt, 3, tt, 0, s);
+        if (lane == 0 && warp == OUT0) trace_ev(a, ring, trace_cnt, 3, tt, 0, s);
       };
       // accumulator of the output layer -> this warp's staging box ("one thread = one row" -> row-major lines), accumulator freed
       auto park = [&](int s, int t) {
@@ -696,7 +706,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BE + 8 * s);  // the slot's accumulator may be overwritten by the next tile
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 10, t, L - 1, s);
+        if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 10, t, L - 1, s);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t addr = stage + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4);
@@ -738,7 +748,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
         }
         __syncwarp();  // staging box reusable
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t % NSLOT);
+        if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 12, t, L - 1, t % NSLOT);
         if (totals) {
           // row sums: 8 lanes (tc) hold the 32 columns of this half; halves meet in shared memory
 #pragma unroll
@@ -762,7 +772,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           }
           named_bar_sync(1 + q, 64);
         }
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t % NSLOT);
+        if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t % NSLOT);
       };
 
       // y rows of tile t -> registers (transposed layout), requested as early as the registers are free
@@ -779,7 +789,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         mbar_wait(bars + BF + 8 * s, (ph_f >> s) & 1u);
         ph_f ^= 1u << s;
         tc_fence_after();
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
+        if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
       };
 
       split_x(0);
@@ -790,7 +800,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         const int n_in = min(NSLOT, n_tiles - t0);
         if (has_y) load_y(t0);  // requested before the tile's accumulator is ready
         // ---- first what the layer pipeline waits for: free slot 0's accumulator, feed every slot its next tile
-        if (lane == 0 && (warp == MAIN_WARPS || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t0, L - 1, 0);
+        if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 7, t0, L - 1, 0);
         wait_f(0, t0);
         park(0, t0);
         if (t0 + NSLOT < n_tiles) split_x(t0 + NSLOT);  // the output-layer MMA of tile t0 is complete: nothing reads slot 0's A operands
@@ -826,7 +836,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     a.trace[4 + 4 * TRACE_SLOTS + 1] = clock64();
     a.trace[4 + 4 * TRACE_SLOTS + 3] = (long long)ns;
   }
-  if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MAIN_WARPS || warp == EPI_WARPS - 1 || warp == EPI_WARPS)) {
+  if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == OUT0 || warp == EPI_WARPS - 1 || warp == EPI_WARPS)) {
     const int role = is_ctrl ? 1 : (is_out ? (warp == EPI_WARPS - 1 ? 2 : 3) : 0);
     a.trace[role] = trace_cnt;
     for (int i = 0; i < trace_cnt; ++i) a.trace[4 + role * TRACE_SLOTS + i] = (long long)ring[i];
@@ -871,6 +881,7 @@ int g_trace_cap = 0;
 }  // namespace
 
 // debug aid (not part of the public header): timeline of CTA 0 into a device buffer of 4 + 4*capacity int64 (zeroed by the caller)
+extern "C" int gb_debug_trace_slots(void) { return TRACE_SLOTS; }
 extern "C" int gb_debug_set_trace(void* dev_buf, int capacity) {
   g_trace = static_cast<long long*>(dev_buf);
   g_trace_cap = capacity;
