@@ -40,6 +40,14 @@ constexpr int TILE = 128;
 #ifndef GB_TC_NSLOT
 #define GB_TC_NSLOT 2  // measured (profiles/r02_*): three slots convoy behind the in-order layer warps and run 40 % slower than two
 #endif
+#ifndef GB_TC_YPREF
+#define GB_TC_YPREF 2  // y rows of a tile into L2 ahead of the output warps' loads: 0 never (0.702 of the HBM peak), 1 with the tile's x boxes
+                       // (0.655: ~60 % of the lines are evicted again before use and read twice, ncu dram__bytes_read +30 %), 2 when layer
+                       // GB_TC_YPREF_LAYER is issued (0.720; same box, back to back)
+#endif
+#ifndef GB_TC_YPREF_LAYER
+#define GB_TC_YPREF_LAYER 4
+#endif
 #ifndef GB_TC_STATIC
 #define GB_TC_STATIC 1  // 0: always the generic instantiation (A/B measurements)
 #endif
@@ -547,15 +555,18 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const uint32_t xdst = sbase + a.xbox_ofs + s * 2 * BOX_BYTES;
       const uint32_t tb = tmem + s * SLOT_COLS;
       const uint32_t whb_ofs = STATIC ? HGL<0>::whb_ofs : a.whb_ofs;
-      // x boxes of tile t by TMA; its y rows are read ~7 layers later: ask for them in L2 now, so the output warps' loads do not wait on DRAM
-      auto fetch_tile = [&](int t) {
-        mbar_expect_tx(bar_x, 2 * BOX_BYTES);
-        tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)t * TILE), bar_x);
-        tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)t * TILE), bar_x);
+      auto prefetch_y = [&](int t) {
         if (has_y) {
           const int nrows = min(TILE, row_end - (row_begin + t * TILE));
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.y + (xrow0 + (long)t * TILE) * TP), "r"((uint32_t)(nrows * TP * 4)) : "memory");
         }
+      };
+      // x boxes of tile t by TMA; its y rows are read ~7 layers later: ask for them in L2 ahead of time, so the output warps' loads do not wait on DRAM
+      auto fetch_tile = [&](int t) {
+        mbar_expect_tx(bar_x, 2 * BOX_BYTES);
+        tma_load_2d(xdst, &map_x, 0, (int)(xrow0 + (long)t * TILE), bar_x);
+        tma_load_2d(xdst + BOX_BYTES, &map_x, 32, (int)(xrow0 + (long)t * TILE), bar_x);
+        if (GB_TC_YPREF == 1) prefetch_y(t);
       };
       if (s < n_tiles && elect_one()) fetch_tile(s);
       __syncwarp();
@@ -580,6 +591,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           tc_fence_after();
           if (elect_one()) {
             if (s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
+            if (GB_TC_YPREF == 2 && l == (L > GB_TC_YPREF_LAYER ? GB_TC_YPREF_LAYER : 0)) prefetch_y(t);
             if (l == 1 && t + NSLOT < n_tiles) fetch_tile(t + NSLOT);  // layer 0's MMAs (which read the x boxes) are complete => the boxes are free
             if (l == 0) {
 #pragma unroll
