@@ -29,6 +29,7 @@
 // Reference arithmetic replaced: keras Dense under Model.predict (gordo/machine/model/models.py:289-300) and
 // DiffBasedAnomalyDetector.anomaly (gordo/machine/model/anomaly/diff.py:350-385, 420-444).
 #include <cuda.h>
+#include <atomic>
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -91,6 +92,7 @@ struct TcArgs {
   const gb_job* jobs;
   const float *y, *scale, *feat_thr, *agg_thr;
   float *o_model, *o_ts, *o_tu, *o_conf, *o_tots, *o_totu, *o_totconf;
+  unsigned long long* work_ctr;  // global tile counter of this launch (zeroed by the launcher, stream-ordered)
   long long* trace;  // debug: (event, clock) pairs of CTA 0 (gb_debug_set_trace); NULL in production
   int trace_cap, trace_from, trace_head;  // record events of tiles >= trace_from or < trace_head only
 };
@@ -142,15 +144,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 
 // D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -357,7 +350,7 @@ __device__ __forceinline__ bool elect_one() {
 // constants (STATIC instantiation): the layer loops unroll, MMA counts / descriptors / epilogue widths fold, and the control
 // warp's per-layer issue block is a handful of uniform adds between UTCHMMAs.  The table mirrors the host-side layout code in
 // gb_ffae_infer_score_tc, which verifies the match before choosing the STATIC kernel.
-template <int V> struct IC { static constexpr int value = V; };
+template <int V> struct IC {};
 constexpr int HG_L = 7;
 constexpr int HG_DIMS[HG_L + 1] = {64, 53, 43, 32, 32, 43, 53, 64};
 constexpr int hg_ru(int v, int m) { return (v + m - 1) / m * m; }
@@ -402,11 +395,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   int trace_cnt = 0;
 
   const int tid = threadIdx.x, lane = tid & 31;
-  if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) {
+  if (a.trace != nullptr && tid == 0) {  // every CTA: start / end of its life in nanoseconds (how evenly the SMs finish)
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-    a.trace[4 + 4 * TRACE_SLOTS + 0] = clock64();
-    a.trace[4 + 4 * TRACE_SLOTS + 2] = (long long)ns;
+    a.trace[8 + 4 * TRACE_SLOTS + 2 * blockIdx.x] = (long long)ns;
+    if (blockIdx.x == 0) {
+      a.trace[4 + 4 * TRACE_SLOTS + 0] = clock64();
+      a.trace[4 + 4 * TRACE_SLOTS + 2] = (long long)ns;
+    }
   }
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction (lets the compiler use uniform registers)
   const bool is_ctrl = warp >= EPI_WARPS, is_out = !is_ctrl && warp >= OUT0;
@@ -446,31 +442,39 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   uint32_t ph_x = 0, ph_d = 0, ph_f = 0;  // one parity bit per tile slot
   uint32_t ph_a = 0, ph_e = 0, ph_w = 0;
   int cur_slot = -1;
-  // Work split.  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so work items are as long as
-  // possible: whole jobs, dealt round-robin in waves of gridDim.x (neighbouring CTAs stream neighbouring jobs: cutting the whole
-  // fleet into gridDim.x distant ranges instead measured 18 % slower, the 148 x 9 far-apart streams thrash the TLB); the jobs of
-  // the last, partial wave are cut into gridDim.x equal contiguous tile ranges so that all CTAs finish together.
-  const int wave_jobs = (a.n_jobs / (int)gridDim.x) * (int)gridDim.x;
-  const long tail_total = (long)(a.n_jobs - wave_jobs) * a.tiles_per_job;
-  long g = tail_total * blockIdx.x / gridDim.x;
-  const long g_end = tail_total * (blockIdx.x + 1) / gridDim.x;
-  int next_wave_job = blockIdx.x;
+  // Work distribution.  Tiles are numbered job by job (global tile G = job * tiles_per_job + tile) and handed out from a global
+  // counter in contiguous ranges whose size shrinks as the work runs out (guided self-scheduling: remaining / (2 * CTAs), at most
+  // one job, at least MIN_CHUNK tiles).  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so for most
+  // of the launch a range is exactly one whole job, taken in order -- neighbouring CTAs stream neighbouring jobs, which keeps
+  // the TLB footprint small (cutting the fleet into gridDim.x distant static ranges measured 18 % slower).  Why dynamic: with an
+  // equal static share per CTA the SMs finish up to 14 % apart (measured per-CTA lifetimes 2.83 / 2.94 / 3.29 ms min / mean / max
+  // at the BASELINE size: SMs differ in their distance to the memory partitions), and the launch lasts as long as its slowest CTA.
+  __shared__ long s_range[2];
+  constexpr long MIN_CHUNK = 8;
+  const long tpj = a.tiles_per_job, g_total = (long)a.n_jobs * tpj;
+  long g = 0, g_end = 0;
 
   while (true) {
-    int job_id, tile_begin, tile_end;
-    if (next_wave_job < wave_jobs) {
-      job_id = next_wave_job;
-      tile_begin = 0;
-      tile_end = a.tiles_per_job;
-      next_wave_job += gridDim.x;
-    } else if (g < g_end) {
-      job_id = wave_jobs + (int)(g / a.tiles_per_job);
-      tile_begin = (int)(g - (long)(job_id - wave_jobs) * a.tiles_per_job);
-      tile_end = (int)min((long)a.tiles_per_job, tile_begin + (g_end - g));
-      g += tile_end - tile_begin;
-    } else {
-      break;
+    if (g >= g_end) {
+      if (tid == 0) {
+        const long seen = (long)*reinterpret_cast<volatile unsigned long long*>(a.work_ctr);
+        long size = (g_total - seen) / (2 * (long)gridDim.x);
+        size = size > tpj ? tpj : (size < MIN_CHUNK ? MIN_CHUNK : size);
+        if (size > tpj - seen % tpj && seen % tpj != 0) size = tpj - seen % tpj;  // (stale `seen` at worst mis-sizes a range; every tile is still handed out once)
+        const long got = (long)atomicAdd(a.work_ctr, (unsigned long long)size);
+        s_range[0] = got;
+        s_range[1] = got + size < g_total ? got + size : g_total;
+      }
+      __syncthreads();
+      g = s_range[0];
+      g_end = s_range[1];
+      __syncthreads();  // s_range is rewritten only after every thread has read it
+      if (g >= g_total) break;
     }
+    const int job_id = (int)(g / tpj);
+    const int tile_begin = (int)(g - (long)job_id * tpj);
+    const int tile_end = (int)min(tpj, tile_begin + (g_end - g));
+    g += tile_end - tile_begin;
     const gb_job job = a.jobs[job_id];
     const int row_begin = tile_begin * TILE;
     if (row_begin >= job.n_rows) continue;  // uniform across the CTA
@@ -842,11 +846,14 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     __syncthreads();
   }
 
-  if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) {  // SM clock actually delivered over the kernel: cycles and nanoseconds
+  if (a.trace != nullptr && tid == 0) {  // SM clock actually delivered over the kernel: cycles and nanoseconds
     unsigned long long ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-    a.trace[4 + 4 * TRACE_SLOTS + 1] = clock64();
-    a.trace[4 + 4 * TRACE_SLOTS + 3] = (long long)ns;
+    a.trace[8 + 4 * TRACE_SLOTS + 2 * blockIdx.x + 1] = (long long)ns;
+    if (blockIdx.x == 0) {
+      a.trace[4 + 4 * TRACE_SLOTS + 1] = clock64();
+      a.trace[4 + 4 * TRACE_SLOTS + 3] = (long long)ns;
+    }
   }
   if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == OUT0 || warp == EPI_WARPS - 1 || warp == EPI_WARPS)) {
     const int role = is_ctrl ? 1 : (is_out ? (warp == EPI_WARPS - 1 ? 2 : 3) : 0);
@@ -887,12 +894,18 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int
   return GB_OK;
 }
 
+// tile counters of the launches in flight: a ring of static device words, one per launch, zeroed stream-ordered before the kernel
+// (no allocation; launches more than WORK_CTRS apart on the host never overlap on the device in practice)
+constexpr int WORK_CTRS = 1024;
+__device__ unsigned long long g_work_ctr[WORK_CTRS];
+
 long long* g_trace = nullptr;  // 4 + 4*TRACE_SLOTS int64
 int g_trace_cap = 0;
 
 }  // namespace
 
-// debug aid (not part of the public header): timeline of CTA 0 into a device buffer of 4 + 4*capacity int64 (zeroed by the caller)
+// debug aid (not part of the public header): timeline of CTA 0 into a device buffer of 8 + 4*gb_debug_trace_slots() + 2*grid int64
+// (zeroed by the caller): per-role event counts, events, CTA 0's clock/ns at start and end, then every CTA's start/end in ns
 extern "C" int gb_debug_trace_slots(void) { return TRACE_SLOTS; }
 extern "C" int gb_debug_set_trace(void* dev_buf, int capacity) {
   g_trace = static_cast<long long*>(dev_buf);
@@ -993,6 +1006,13 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
 
   const long g_total = (long)n_jobs * tiles_per_job;
   const int grid = (int)(g_total < sms ? g_total : sms);
+  {
+    static std::atomic<unsigned> next_ctr{0};
+    void* base = nullptr;
+    GB_CUDA_CHECK(cudaGetSymbolAddress(&base, g_work_ctr));
+    a.work_ctr = static_cast<unsigned long long*>(base) + (next_ctr.fetch_add(1) % WORK_CTRS);
+    GB_CUDA_CHECK(cudaMemsetAsync(a.work_ctr, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  }
   auto launch = [&](auto kern) -> int {
     GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, mx);

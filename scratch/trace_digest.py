@@ -20,13 +20,19 @@ for _ in range(3): eng.infer_score(params, jobs, M, R, x, y, scale, feat, agg, o
 torch.cuda.synchronize()
 lib = _cabi.load_library()
 SLOTS = lib.gb_debug_trace_slots()
-buf = torch.zeros(8 + 4 * SLOTS, dtype=torch.int64, device=dev)
+buf = torch.zeros(8 + 4 * SLOTS + 2 * 148, dtype=torch.int64, device=dev)
 lib.gb_debug_set_trace(C.c_void_p(buf.data_ptr()), SLOTS)
 eng.infer_score(params, jobs, M, R, x, y, scale, feat, agg, out=out)
 torch.cuda.synchronize()
 lib.gb_debug_set_trace(None, 0)
 b = buf.cpu().numpy()
 c0, c1, n0, n1 = [int(v) for v in b[4 + 4 * SLOTS: 8 + 4 * SLOTS]]
+cta = b[8 + 4 * SLOTS:].reshape(-1, 2).astype(np.float64)
+cta = cta[cta[:, 0] > 0]
+if len(cta):
+    start0, dur = cta[:, 0].min(), cta[:, 1] - cta[:, 0]
+    print(f'{len(cta)} CTAs: life min/mean/max {dur.min() / 1e3:.1f} / {dur.mean() / 1e3:.1f} / {dur.max() / 1e3:.1f} us; last end - first start {(cta[:, 1].max() - start0) / 1e3:.1f} us; '
+          f'deciles {np.round(np.quantile(dur, [0.1, 0.3, 0.5, 0.7, 0.9]) / 1e3, 1)}')
 print(f'kernel: {c1 - c0} cycles in {n1 - n0} ns -> {(c1 - c0) / max(1, n1 - n0):.3f} GHz; tiles per CTA {M * R // 128 / 148:.1f}')
 rec = []
 for role in range(4):
