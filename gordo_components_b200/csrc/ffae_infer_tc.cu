@@ -92,7 +92,7 @@ struct TcArgs {
   const gb_job* jobs;
   const float *y, *scale, *feat_thr, *agg_thr;
   float *o_model, *o_ts, *o_tu, *o_conf, *o_tots, *o_totu, *o_totconf;
-  unsigned long long* work_ctr;  // global tile counter of this launch (zeroed by the launcher, stream-ordered)
+  unsigned int* work_ctr;  // global tile counter of this launch (zeroed by the launcher, stream-ordered)
   long long* trace;  // debug: (event, clock) pairs of CTA 0 (gb_debug_set_trace); NULL in production
   int trace_cap, trace_from, trace_head;  // record events of tiles >= trace_from or < trace_head only
 };
@@ -443,41 +443,50 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   uint32_t ph_a = 0, ph_e = 0, ph_w = 0;
   int cur_slot = -1;
   // Work distribution.  Tiles are numbered job by job (global tile G = job * tiles_per_job + tile) and handed out from a global
-  // counter in contiguous ranges whose size shrinks as the work runs out (guided self-scheduling: remaining / (2 * CTAs), at most
-  // one job, at least MIN_CHUNK tiles).  Every change of job costs a pipeline drain + refill (~30k cycles, measured), so for most
-  // of the launch a range is exactly one whole job, taken in order -- neighbouring CTAs stream neighbouring jobs, which keeps
-  // the TLB footprint small (cutting the fleet into gridDim.x distant static ranges measured 18 % slower).  Why dynamic: with an
-  // equal static share per CTA the SMs finish up to 14 % apart (measured per-CTA lifetimes 2.83 / 2.94 / 3.29 ms min / mean / max
-  // at the BASELINE size: SMs differ in their distance to the memory partitions), and the launch lasts as long as its slowest CTA.
-  __shared__ long s_range[2];
-  constexpr long MIN_CHUNK = 8;
-  const long tpj = a.tiles_per_job, g_total = (long)a.n_jobs * tpj;
-  long g = 0, g_end = 0;
+  // counter in contiguous ranges: whole jobs, in order, for most of the launch -- every change of job costs a pipeline drain +
+  // refill (~30k cycles, measured), and neighbouring CTAs streaming neighbouring jobs keep the TLB footprint small (cutting the
+  // fleet into gridDim.x distant static ranges measured 18 % slower) -- then thirds and sixths of a job for the last ~1.5 jobs per
+  // CTA.  Why dynamic: with an equal static share per CTA the SMs finish up to 14 % apart (measured per-CTA lifetimes 2.83 / 2.94 /
+  // 3.29 ms min / mean / max at the BASELINE size: SMs differ in their distance to the memory partitions) and the launch lasts as
+  // long as its slowest CTA; but ranges must stay long -- a first version that shrank them to 8 tiles spent more in drains than it won.
+  // The scheduler state lives in shared memory (thread 0 only touches it between items): registers are what this kernel is short of.
+  __shared__ int s_item[4];  // [0] job, [1] first tile, [2] end tile of the item all threads work on next; [3] unused
+  __shared__ int s_range[2];  // thread 0: tiles [g, g_end) of the range it holds
+  if (tid == 0) s_range[0] = s_range[1] = 0;
 
   while (true) {
-    if (g >= g_end) {
-      if (tid == 0) {
-        const long seen = (long)*reinterpret_cast<volatile unsigned long long*>(a.work_ctr);
-        long size = (g_total - seen) / (2 * (long)gridDim.x);
-        size = size > tpj ? tpj : (size < MIN_CHUNK ? MIN_CHUNK : size);
-        if (size > tpj - seen % tpj && seen % tpj != 0) size = tpj - seen % tpj;  // (stale `seen` at worst mis-sizes a range; every tile is still handed out once)
-        const long got = (long)atomicAdd(a.work_ctr, (unsigned long long)size);
-        s_range[0] = got;
-        s_range[1] = got + size < g_total ? got + size : g_total;
+    if (tid == 0) {
+      const int tpj = a.tiles_per_job, g_total = a.n_jobs * tpj;  // (the launcher refuses fleets beyond 2^31 tiles)
+      int g = s_range[0], g_end = s_range[1];
+      if (g >= g_end) {
+        const int seen = (int)*reinterpret_cast<volatile unsigned int*>(a.work_ctr);
+        const int left = g_total - seen, per_cta = left / (int)gridDim.x;
+        int size = per_cta * 2 >= 3 * tpj ? tpj : (per_cta >= tpj / 3 ? (tpj + 2) / 3 : (tpj + 5) / 6);
+        if (size < 1) size = 1;
+        if (seen % tpj != 0 && size > tpj - seen % tpj) size = tpj - seen % tpj;  // ranges end at job boundaries (a stale `seen` at worst mis-sizes one)
+        g = (int)atomicAdd(a.work_ctr, (unsigned int)size);
+        g_end = g + size < g_total ? g + size : g_total;
       }
-      __syncthreads();
-      g = s_range[0];
-      g_end = s_range[1];
-      __syncthreads();  // s_range is rewritten only after every thread has read it
-      if (g >= g_total) break;
+      if (g >= g_total) {
+        s_item[0] = -1;
+      } else {
+        const int job_id = g / tpj, tile_begin = g - job_id * tpj;
+        const int tile_end = min(tpj, tile_begin + (g_end - g));
+        s_item[0] = job_id; s_item[1] = tile_begin; s_item[2] = tile_end;
+        g += tile_end - tile_begin;
+      }
+      s_range[0] = g; s_range[1] = g_end;
     }
-    const int job_id = (int)(g / tpj);
-    const int tile_begin = (int)(g - (long)job_id * tpj);
-    const int tile_end = (int)min(tpj, tile_begin + (g_end - g));
-    g += tile_end - tile_begin;
+    __syncthreads();
+    const int job_id = s_item[0], tile_begin = s_item[1], tile_end = s_item[2];
+    if (job_id < 0) break;
+    // (s_item is rewritten only after the item's closing __syncthreads)
     const gb_job job = a.jobs[job_id];
     const int row_begin = tile_begin * TILE;
-    if (row_begin >= job.n_rows) continue;  // uniform across the CTA
+    if (row_begin >= job.n_rows) {  // uniform across the CTA
+      __syncthreads();              // every thread has read s_item before thread 0 writes the next one
+      continue;
+    }
     const int row_end = min(job.n_rows, tile_end * TILE);
     const int n_tiles = (row_end - row_begin + TILE - 1) / TILE;
 
@@ -897,7 +906,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int
 // tile counters of the launches in flight: a ring of static device words, one per launch, zeroed stream-ordered before the kernel
 // (no allocation; launches more than WORK_CTRS apart on the host never overlap on the device in practice)
 constexpr int WORK_CTRS = 1024;
-__device__ unsigned long long g_work_ctr[WORK_CTRS];
+__device__ unsigned int g_work_ctr[WORK_CTRS];
 
 long long* g_trace = nullptr;  // 4 + 4*TRACE_SLOTS int64
 int g_trace_cap = 0;
@@ -1010,8 +1019,9 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
     static std::atomic<unsigned> next_ctr{0};
     void* base = nullptr;
     GB_CUDA_CHECK(cudaGetSymbolAddress(&base, g_work_ctr));
-    a.work_ctr = static_cast<unsigned long long*>(base) + (next_ctr.fetch_add(1) % WORK_CTRS);
-    GB_CUDA_CHECK(cudaMemsetAsync(a.work_ctr, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    GB_REQUIRE(g_total < (1L << 31), GB_E_ARG, "%ld tiles in one launch: split the fleet", g_total);
+    a.work_ctr = static_cast<unsigned int*>(base) + (next_ctr.fetch_add(1) % WORK_CTRS);
+    GB_CUDA_CHECK(cudaMemsetAsync(a.work_ctr, 0, sizeof(unsigned int), (cudaStream_t)stream));
   }
   auto launch = [&](auto kern) -> int {
     GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
