@@ -41,6 +41,9 @@ constexpr int TILE = 128;
 #ifndef GB_TC_NSLOT
 #define GB_TC_NSLOT 2  // measured (profiles/r02_*): three slots convoy behind the in-order layer warps and run 40 % slower than two
 #endif
+#ifndef GB_TC_OOO
+#define GB_TC_OOO 1  // 1: the layer warps serve whichever tile slot's MMAs have committed; 0: fixed order (slot by slot, layer by layer)
+#endif
 #ifndef GB_TC_YPREF
 #define GB_TC_YPREF 2  // y rows of a tile into L2 ahead of the output warps' loads: 0 never (0.702 of the HBM peak), 1 with the tile's x boxes
                        // (0.655: ~60 % of the lines are evicted again before use and read twice, ncu dram__bytes_read +30 %), 2 when layer
@@ -102,7 +105,7 @@ constexpr int DEFAULT_NE = 0;
 
 // debug timeline (gb_debug_set_trace): three recorder threads of CTA 0 (epilogue tid 0, the two control leaders) stamp
 // events into shared memory (one clock read + one store each) and flush them to global memory when the kernel ends
-constexpr int TRACE_SLOTS = 256;  // events per recorder (gb_debug_trace_slots() tells the reader: the buffer layout depends on it)
+constexpr int TRACE_SLOTS = NSLOT == 2 ? 256 : 32;  // events per recorder (gb_debug_trace_slots() tells the reader: the buffer layout depends on it)
 __device__ __forceinline__ void trace_ev(const TcArgs& a, unsigned long long* ring, int& cnt, int code, int tile, int layer, int slot) {
   if (a.trace == nullptr || blockIdx.x != 0 || cnt >= TRACE_SLOTS || (tile < a.trace_from && tile >= a.trace_head)) return;
   ring[cnt++] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(tile & 0xfff) << 12) | ((layer & 0xf) << 8) | ((slot & 0xf) << 4) | (code & 0xf);  // code < 16
@@ -131,6 +134,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
+}
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -643,44 +652,88 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // D -> bias, tanh -> next layer's A operand.  A dedicated group owns slot `grp` (tiles grp, grp + NSLOT, ...); a shared group
       // visits the slots in turn, layer by layer (one slot's epilogue then overlaps the other slot's MMAs).
       const int grp = GB_TC_DEDICATED ? warp / MAIN_WARPS : 0;
-      for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
-        for_layers<STATIC, true>(L - 1, [&](auto lc) {
-          const int l = layer_index(lc);
-          const LayerP P = layer_of(a, lc);
-          const int half = P.n8 >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
-          const float* bl = reinterpret_cast<const float*>(smem + P.bias_ofs);
+      // one hidden layer `lc` of the tile `t` in slot `s`: accumulator -> bias, tanh -> FP16-pair A operand of the next layer
+      auto serve = [&](int s, int t, auto lc) {
+        const int l = layer_index(lc);
+        const LayerP P = layer_of(a, lc);
+        const int half = P.n8 >> 1;  // columns this warp owns: [h*half, (h+1)*half), a multiple of 4, as two chunks
+        const float* bl = reinterpret_cast<const float*>(smem + P.bias_ofs);
+        tc_fence_after();
+        if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t, l, s);
+        const uint32_t sl = lane_base + s * SLOT_COLS;
+        const int c0 = h * half;
+        switch (half) {
+          case 32: hidden_epilogue_pair<16, 16, NE>(sl, c0, bl); break;
+          case 28: hidden_epilogue_pair<16, 12, NE>(sl, c0, bl); break;
+          case 24: hidden_epilogue_pair<12, 12, NE>(sl, c0, bl); break;
+          case 20: hidden_epilogue_pair<12, 8, NE>(sl, c0, bl); break;
+          case 16: hidden_epilogue_pair<8, 8, NE>(sl, c0, bl); break;
+          case 12: hidden_epilogue_pair<8, 4, NE>(sl, c0, bl); break;
+          case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
+          default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
+        }
+        if (h == 1 && P.n8 < P.Np) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};
+          tmem_st4(sl + COL_A1 + (P.n8 >> 1), z);
+          tmem_st4(sl + COL_A2 + (P.n8 >> 1), z);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+        if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t, l, s);
+      };
+      if (GB_TC_OOO && !GB_TC_DEDICATED) {
+        // Out-of-order service: whichever slot's MMAs have committed is served next.  (Visiting the slots in a fixed order, layer by
+        // layer, locks them into the same phase: with three slots the pipeline ran as a convoy -- all MMAs, then three epilogues in
+        // a row -- and was 40 % slower than with two.)  Per slot: st = tiles done * 8 + next hidden layer.
+        int st0 = 0, st1 = 0, st2 = 0, rr = 0;
+        int remaining = n_tiles * (L - 1);
+        while (remaining > 0) {
+          int s = -1, sst = 0;
 #pragma unroll
-          for (int s = 0; s < NSLOT; ++s) {
-            if (t0 + s >= n_tiles || (GB_TC_DEDICATED && s != grp)) continue;
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, l, s);
-            mbar_wait(bars + BD + 8 * s, (ph_d >> s) & 1u);
-            ph_d ^= 1u << s;
-            tc_fence_after();
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 5, t0 + s, l, s);
-            const uint32_t sl = lane_base + s * SLOT_COLS;
-            const int c0 = h * half;
-            switch (half) {
-              case 32: hidden_epilogue_pair<16, 16, NE>(sl, c0, bl); break;
-              case 28: hidden_epilogue_pair<16, 12, NE>(sl, c0, bl); break;
-              case 24: hidden_epilogue_pair<12, 12, NE>(sl, c0, bl); break;
-              case 20: hidden_epilogue_pair<12, 8, NE>(sl, c0, bl); break;
-              case 16: hidden_epilogue_pair<8, 8, NE>(sl, c0, bl); break;
-              case 12: hidden_epilogue_pair<8, 4, NE>(sl, c0, bl); break;
-              case 8: hidden_epilogue_pair<4, 4, NE>(sl, c0, bl); break;
-              default: hidden_epilogue_pair<4, 0, NE>(sl, c0, bl); break;
-            }
-            if (h == 1 && P.n8 < P.Np) {  // K padding of the next layer (8 columns): zeros, so stale operands never meet the MMA
-              const uint32_t z[4] = {0u, 0u, 0u, 0u};
-              tmem_st4(sl + COL_A1 + (P.n8 >> 1), z);
-              tmem_st4(sl + COL_A2 + (P.n8 >> 1), z);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-            if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t0 + s, l, s);
+          for (int k = 0; k < NSLOT; ++k) {
+            int c = rr + k;
+            if (c >= NSLOT) c -= NSLOT;
+            const int cst = c == 0 ? st0 : (c == 1 ? st1 : st2);
+            if (s < 0 && c + NSLOT * (cst >> 3) < n_tiles && mbar_test(bars + BD + 8 * c, (ph_d >> c) & 1u)) { s = c; sst = cst; }
           }
-        });
+          if (s < 0) {
+            __nanosleep(32);
+            continue;
+          }
+          ph_d ^= 1u << s;
+          const int t = s + NSLOT * (sst >> 3), l = sst & 7;
+          if constexpr (STATIC) {
+            switch (l) {
+              case 0: serve(s, t, IC<0>{}); break;
+              case 1: serve(s, t, IC<1>{}); break;
+              case 2: serve(s, t, IC<2>{}); break;
+              case 3: serve(s, t, IC<3>{}); break;
+              case 4: serve(s, t, IC<4>{}); break;
+              default: serve(s, t, IC<5>{}); break;
+            }
+          } else {
+            serve(s, t, l);
+          }
+          const int nst = (l + 1 == L - 1) ? ((sst >> 3) + 1) << 3 : sst + 1;
+          if (s == 0) st0 = nst; else if (s == 1) st1 = nst; else st2 = nst;
+          rr = s + 1 == NSLOT ? 0 : s + 1;
+          --remaining;
+        }
+      } else {
+        for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
+          for_layers<STATIC, true>(L - 1, [&](auto lc) {
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+              if (t0 + s >= n_tiles || (GB_TC_DEDICATED && s != grp)) continue;
+              if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, layer_index(lc), s);
+              mbar_wait(bars + BD + 8 * s, (ph_d >> s) & 1u);
+              ph_d ^= 1u << s;
+              serve(s, t0 + s, lc);
+            }
+          });
+        }
       }
     } else {
       // =========================================== output warps (LSU-bound): last layer -> model output + anomaly columns
