@@ -459,6 +459,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   // 3.29 ms min / mean / max at the BASELINE size: SMs differ in their distance to the memory partitions) and the launch lasts as
   // long as its slowest CTA; but ranges must stay long -- a first version that shrank them to 8 tiles spent more in drains than it won.
   // The scheduler state lives in shared memory (thread 0 only touches it between items): registers are what this kernel is short of.
+  __shared__ int s_pick[2];  // out-of-order service: the slot the layer warps take next (double-buffered by round)
   __shared__ int s_item[4];  // [0] job, [1] first tile, [2] end tile of the item all threads work on next; [3] unused
   __shared__ int s_range[2];  // thread 0: tiles [g, g_end) of the range it holds
   if (tid == 0) s_range[0] = s_range[1] = 0;
@@ -687,21 +688,28 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         // Out-of-order service: whichever slot's MMAs have committed is served next.  (Visiting the slots in a fixed order, layer by
         // layer, locks them into the same phase: with three slots the pipeline ran as a convoy -- all MMAs, then three epilogues in
         // a row -- and was 40 % slower than with two.)  Per slot: st = tiles done * 8 + next hidden layer.
-        int st0 = 0, st1 = 0, st2 = 0, rr = 0;
+        // The eight warps must take the slots in the SAME order (a slot's epilogue is complete when its last warp is done: warps that
+        // chose independently left every slot waiting 1-1.3k cycles for stragglers): warp 0 picks, a named barrier publishes the pick.
+        int st0 = 0, st1 = 0, st2 = 0, rr = 0, round = 0;
         int remaining = n_tiles * (L - 1);
         while (remaining > 0) {
-          int s = -1, sst = 0;
+          if (warp == 0) {
+            int pick = -1;
+            while (pick < 0) {
 #pragma unroll
-          for (int k = 0; k < NSLOT; ++k) {
-            int c = rr + k;
-            if (c >= NSLOT) c -= NSLOT;
-            const int cst = c == 0 ? st0 : (c == 1 ? st1 : st2);
-            if (s < 0 && c + NSLOT * (cst >> 3) < n_tiles && mbar_test(bars + BD + 8 * c, (ph_d >> c) & 1u)) { s = c; sst = cst; }
+              for (int k = 0; k < NSLOT; ++k) {
+                int c = rr + k;
+                if (c >= NSLOT) c -= NSLOT;
+                const int cst = c == 0 ? st0 : (c == 1 ? st1 : st2);
+                if (pick < 0 && c + NSLOT * (cst >> 3) < n_tiles && mbar_test(bars + BD + 8 * c, (ph_d >> c) & 1u)) pick = c;
+              }
+            }
+            if (lane == 0) s_pick[round & 1] = pick;
           }
-          if (s < 0) {
-            __nanosleep(32);
-            continue;
-          }
+          named_bar_sync(5, MAIN_WARPS * 32);
+          const int s = s_pick[round & 1];
+          ++round;
+          const int sst = s == 0 ? st0 : (s == 1 ? st1 : st2);
           ph_d ^= 1u << s;
           const int t = s + NSLOT * (sst >> 3), l = sst & 7;
           if constexpr (STATIC) {
