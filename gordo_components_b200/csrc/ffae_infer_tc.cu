@@ -41,9 +41,6 @@ constexpr int TILE = 128;
 #ifndef GB_TC_NSLOT
 #define GB_TC_NSLOT 2  // measured (profiles/r02_*): three slots convoy behind the in-order layer warps and run 40 % slower than two
 #endif
-#ifndef GB_TC_OOO
-#define GB_TC_OOO 1  // 1: the layer warps serve whichever tile slot's MMAs have committed; 0: fixed order (slot by slot, layer by layer)
-#endif
 #ifndef GB_TC_YPREF
 #define GB_TC_YPREF 2  // y rows of a tile into L2 ahead of the output warps' loads: 0 never (0.702 of the HBM peak), 1 with the tile's x boxes
                        // (0.655: ~60 % of the lines are evicted again before use and read twice, ncu dram__bytes_read +30 %), 2 when layer
@@ -134,12 +131,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
-}
-// non-blocking probe of an mbarrier phase
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -459,7 +450,6 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   // 3.29 ms min / mean / max at the BASELINE size: SMs differ in their distance to the memory partitions) and the launch lasts as
   // long as its slowest CTA; but ranges must stay long -- a first version that shrank them to 8 tiles spent more in drains than it won.
   // The scheduler state lives in shared memory (thread 0 only touches it between items): registers are what this kernel is short of.
-  __shared__ int s_pick[2];  // out-of-order service: the slot the layer warps take next (double-buffered by round)
   __shared__ int s_item[4];  // [0] job, [1] first tile, [2] end tile of the item all threads work on next; [3] unused
   __shared__ int s_range[2];  // thread 0: tiles [g, g_end) of the range it holds
   if (tid == 0) s_range[0] = s_range[1] = 0;
@@ -684,52 +674,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         if (lane == 0) mbar_arrive(bars + BA + 8 * s);
         if (tid == 0) trace_ev(a, ring, trace_cnt, 6, t, l, s);
       };
-      if (GB_TC_OOO && !GB_TC_DEDICATED) {
-        // Out-of-order service: whichever slot's MMAs have committed is served next.  (Visiting the slots in a fixed order, layer by
-        // layer, locks them into the same phase: with three slots the pipeline ran as a convoy -- all MMAs, then three epilogues in
-        // a row -- and was 40 % slower than with two.)  Per slot: st = tiles done * 8 + next hidden layer.
-        // The eight warps must take the slots in the SAME order (a slot's epilogue is complete when its last warp is done: warps that
-        // chose independently left every slot waiting 1-1.3k cycles for stragglers): warp 0 picks, a named barrier publishes the pick.
-        int st0 = 0, st1 = 0, st2 = 0, rr = 0, round = 0;
-        int remaining = n_tiles * (L - 1);
-        while (remaining > 0) {
-          if (warp == 0) {
-            int pick = -1;
-            while (pick < 0) {
-#pragma unroll
-              for (int k = 0; k < NSLOT; ++k) {
-                int c = rr + k;
-                if (c >= NSLOT) c -= NSLOT;
-                const int cst = c == 0 ? st0 : (c == 1 ? st1 : st2);
-                if (pick < 0 && c + NSLOT * (cst >> 3) < n_tiles && mbar_test(bars + BD + 8 * c, (ph_d >> c) & 1u)) pick = c;
-              }
-            }
-            if (lane == 0) s_pick[round & 1] = pick;
-          }
-          named_bar_sync(5, MAIN_WARPS * 32);
-          const int s = s_pick[round & 1];
-          ++round;
-          const int sst = s == 0 ? st0 : (s == 1 ? st1 : st2);
-          ph_d ^= 1u << s;
-          const int t = s + NSLOT * (sst >> 3), l = sst & 7;
-          if constexpr (STATIC) {
-            switch (l) {
-              case 0: serve(s, t, IC<0>{}); break;
-              case 1: serve(s, t, IC<1>{}); break;
-              case 2: serve(s, t, IC<2>{}); break;
-              case 3: serve(s, t, IC<3>{}); break;
-              case 4: serve(s, t, IC<4>{}); break;
-              default: serve(s, t, IC<5>{}); break;
-            }
-          } else {
-            serve(s, t, l);
-          }
-          const int nst = (l + 1 == L - 1) ? ((sst >> 3) + 1) << 3 : sst + 1;
-          if (s == 0) st0 = nst; else if (s == 1) st1 = nst; else st2 = nst;
-          rr = s + 1 == NSLOT ? 0 : s + 1;
-          --remaining;
-        }
-      } else {
+      // Fixed service order: slot by slot, layer by layer.  Serving whichever slot has committed (each warp polling on its own, or
+      // warp 0 picking and a named barrier publishing the pick) measured 15-25 % slower with two slots and did not cure the
+      // three-slot convoy either (profiles/r02_kernel_experiments.md).
+      {
         for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
           for_layers<STATIC, true>(L - 1, [&](auto lc) {
 #pragma unroll
