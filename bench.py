@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-machines", type=int, default=2, help="machines in the one-core cpu_baseline sample")
+    ap.add_argument("--cpu-machines", type=int, default=150, help="machines in the one-core cpu_baseline sample (~10 s of CPU work)")
     ap.add_argument("--secondary", type=int, default=1, help="0: skip the configs[2]/[3]/[4] block")
     ap.add_argument("--numa", type=int, default=1, help="0: do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()

@@ -279,10 +279,12 @@ extern "C" int gb_ffae_infer_score_fma(const gb_ffnet* net, const float* params,
   tiles_per_chunk = min(tiles_per_chunk, 16);
   a.rows_per_chunk = tiles_per_chunk * ROWS;
   const int chunks = (tiles_per_job + tiles_per_chunk - 1) / tiles_per_chunk;
-  GB_REQUIRE(n_jobs <= 65535, GB_E_ARG, "n_jobs=%d exceeds 65535 per launch", n_jobs);
   auto launch = [&](auto kern) -> int {
     GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(chunks, n_jobs), THREADS, smem, (cudaStream_t)stream>>>(a);
+    for (int j0 = 0; j0 < n_jobs; j0 += 65535) {  // gridDim.y carries the job index: larger fleets go out as several launches
+      a.jobs = jobs + j0;
+      kern<<<dim3(chunks, n_jobs - j0 < 65535 ? n_jobs - j0 : 65535), THREADS, smem, (cudaStream_t)stream>>>(a);
+    }
     return GB_OK;
   };
   int rc = rt == 4 ? launch(ffae_infer_fma_kernel<4>) : rt == 2 ? launch(ffae_infer_fma_kernel<2>) : launch(ffae_infer_fma_kernel<1>);

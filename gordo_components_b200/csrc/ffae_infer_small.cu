@@ -173,11 +173,13 @@ extern "C" int gb_ffae_infer_score_small(const gb_ffnet* net, const float* param
   a.o_totu = out_total_unscaled; a.o_conf = out_conf; a.o_totconf = out_total_conf;
   int wmax = 0;
   for (int l = 0; l <= net->n_layers; ++l) wmax = net->dims[l] > wmax ? net->dims[l] : wmax;
-  const dim3 grid((max_rows + CHUNK - 1) / CHUNK, n_jobs);
-  GB_REQUIRE(n_jobs <= 65535, GB_E_ARG, "n_jobs=%d exceeds the grid limit of this variant", n_jobs);
-  if (wmax <= 4) ffae_infer_small_kernel<4><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
-  else if (wmax <= 8) ffae_infer_small_kernel<8><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
-  else ffae_infer_small_kernel<16><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {  // gridDim.y carries the job index: larger fleets go out as several launches
+    a.jobs = jobs + j0;
+    const dim3 grid((max_rows + CHUNK - 1) / CHUNK, n_jobs - j0 < 65535 ? n_jobs - j0 : 65535);
+    if (wmax <= 4) ffae_infer_small_kernel<4><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+    else if (wmax <= 8) ffae_infer_small_kernel<8><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+    else ffae_infer_small_kernel<16><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+  }
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }

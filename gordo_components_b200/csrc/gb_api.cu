@@ -122,7 +122,7 @@ int gb_ffae_infer_score(const gb_ffnet* net, const float* params, const gb_job* 
     return gb_ffae_infer_score_tc(net, params, jobs, n_jobs, max_rows, n_x_rows, n_out_rows, x, y, scale, feat_thr, agg_thr,
                                   out_model, out_tag_scaled, out_tag_unscaled, out_total_scaled, out_total_unscaled, out_conf,
                                   out_total_conf, tc_flags, stream);
-  const bool small_ok = gb_ffae_small_supported(net) == GB_OK && n_jobs <= 65535;
+  const bool small_ok = gb_ffae_small_supported(net) == GB_OK;
   if (variant == 3 && !small_ok) return GB_E_SHAPE;
   if (variant == 3 || (variant == 0 && small_ok))
     return gb_ffae_infer_score_small(net, params, jobs, n_jobs, max_rows, x, y, scale, feat_thr, agg_thr, out_model, out_tag_scaled,
