@@ -558,6 +558,29 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     __syncthreads();
     if (tid == 0) trace_ev(a, ring, trace_cnt, 14, 0xfff, 0, 0);
 
+    // x -> A operand of layer 0 of tile `tt` (slot tt % NSLOT): done by the output warps (shared layer group: they have the slack) or
+    // by the slot's own layer warps (DEDICATED); one thread = one row, warp/4 = column half in either group
+    auto split_x = [&](int tt) {
+      const int s = tt % NSLOT;
+      const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
+      mbar_wait(bars + BX + 8 * s, (ph_x >> s) & 1u);
+      ph_x ^= 1u << s;
+#pragma unroll
+      for (int piece = 0; piece < 4; ++piece) {  // 8 columns at a time keeps the register footprint small (y rows are live)
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t addr = xbox + ((uint32_t)((piece * 2 + c) ^ (row & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
+        }
+        store_a_operands<8>(lane_base + s * SLOT_COLS, h * 32 + piece * 8, v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+      if (lane == 0 && (warp == OUT0 || (GB_TC_DEDICATED && warp == 0))) trace_ev(a, ring, trace_cnt, 3, tt, 0, s);
+    };
     if (is_ctrl) {
       // =========================================== control warp of tile slot s: TMA producer + MMA issuer.
       // The whole warp walks the (warp-uniform) control flow; one elected lane issues the asynchronous instructions.
@@ -596,11 +619,13 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           ph_a ^= 1;
           // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
           // layer (wait before layer 0); the other slots send only their output layer to a spare accumulator (wait before that layer)
-          if (t >= NSLOT && l == (s == 0 ? 0 : L - 1)) {
+          // (DEDICATED: every slot sends its output layer to a spare accumulator -- the output warps take the tiles strictly in turn
+          // there and may park a tile late)
+          if (t >= NSLOT && l == ((s == 0 && !GB_TC_DEDICATED) ? 0 : L - 1)) {
             mbar_wait(bar_e, ph_e);
             ph_e ^= 1;
           }
-          const uint32_t dcol = (s >= 1 && l == L - 1) ? tmem + COL_DX + (uint32_t)(s - 1) * 64u : tb + COL_D;
+          const uint32_t dcol = (l == L - 1 && (GB_TC_DEDICATED || s >= 1)) ? tmem + COL_DX + (uint32_t)(GB_TC_DEDICATED ? s : s - 1) * 64u : tb + COL_D;
           tc_fence_after();
           if (elect_one()) {
             if (s == 0) trace_ev(a, ring, trace_cnt, 1, t, l, s);
@@ -677,12 +702,31 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // Fixed service order: slot by slot, layer by layer.  Serving whichever slot has committed (each warp polling on its own, or
       // warp 0 picking and a named barrier publishing the pick) measured 15-25 % slower with two slots and did not cure the
       // three-slot convoy either (profiles/r02_kernel_experiments.md).
-      {
+      if (GB_TC_DEDICATED) {
+        // this group owns slot `grp`: it also prepares the layer-0 operands of its tiles (the output warps only park and store)
+        for (int t = grp; t < n_tiles; t += NSLOT) {
+          if (t >= NSLOT) {  // the previous tile's output-layer MMAs are complete: nothing reads the slot's operand columns any more
+            mbar_wait(bars + BF + 8 * grp, (ph_f >> grp) & 1u);
+            ph_f ^= 1u << grp;
+            tc_fence_after();
+          }
+          split_x(t);
+          for_layers<STATIC, true>(L - 1, [&](auto lc) {
+            mbar_wait(bars + BD + 8 * grp, (ph_d >> grp) & 1u);
+            ph_d ^= 1u << grp;
+            serve(grp, t, lc);
+          });
+        }
+        if (grp < n_tiles) {  // consume the last tile's output-layer phase too, so that the parity is right in the next work item
+          mbar_wait(bars + BF + 8 * grp, (ph_f >> grp) & 1u);
+          ph_f ^= 1u << grp;
+        }
+      } else {
         for (int t0 = 0; t0 < n_tiles; t0 += NSLOT) {
           for_layers<STATIC, true>(L - 1, [&](auto lc) {
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
-              if (t0 + s >= n_tiles || (GB_TC_DEDICATED && s != grp)) continue;
+              if (t0 + s >= n_tiles) continue;
               if (tid == 0) trace_ev(a, ring, trace_cnt, 4, t0 + s, layer_index(lc), s);
               mbar_wait(bars + BD + 8 * s, (ph_d >> s) & 1u);
               ph_d ^= 1u << s;
@@ -707,32 +751,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       const bool in_cols = FULL || h * 32 + tc * 4 < TP;  // this lane's four columns exist (T is a multiple of 4)
       const bool totals = has_y && (a.o_tots || a.o_totu || a.o_totconf);
 
-      // x -> A operand of layer 0 of tile `tt` (slot tt & 1): these warps have the slack, the layer warps do not
-      auto split_x = [&](int tt) {
-        const int s = tt % NSLOT;
-        const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
-        mbar_wait(bars + BX + 8 * s, (ph_x >> s) & 1u);
-        ph_x ^= 1u << s;
-#pragma unroll
-        for (int piece = 0; piece < 4; ++piece) {  // 8 columns at a time keeps the register footprint small (y rows are live)
-          float v[8];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t addr = xbox + ((uint32_t)((piece * 2 + c) ^ (row & 7)) << 4);
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
-          }
-          store_a_operands<8>(lane_base + s * SLOT_COLS, h * 32 + piece * 8, v);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + BA + 8 * s);
-        if (lane == 0 && warp == OUT0) trace_ev(a, ring, trace_cnt, 3, tt, 0, s);
-      };
       // accumulator of the output layer -> this warp's staging box ("one thread = one row" -> row-major lines), accumulator freed
       auto park = [&](int s, int t) {
         float acc[32];
-        const uint32_t sl = lane_base + (s >= 1 ? COL_DX + (uint32_t)(s - 1) * 64u : COL_D) + h * 32;
+        const uint32_t sl = lane_base + ((GB_TC_DEDICATED || s >= 1) ? COL_DX + (uint32_t)(GB_TC_DEDICATED ? s : s - 1) * 64u : COL_D) + h * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld8_nowait(sl + 8 * c, acc + 8 * c);
 #pragma unroll
@@ -748,9 +770,16 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         }
         __syncwarp();
       };
-      float4 yt[8];
-      // every output column of tile t from the staged accumulator; y comes from registers (first tile of a pair) or from the
-      // warp's y box in shared memory (second tile, fetched with cp.async while the first was being written)
+      // y rows in the transposed layout: row i*4 + tr of this warp's 32, 16-byte chunk tc of this column half
+      auto y_row = [&](int t, int i) -> float4 {
+        const int trow = row_begin + t * TILE;
+        const int r = min(q * 32 + i * 4 + tr, min(TILE, row_end - trow) - 1);
+        return in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      constexpr int YW = 3;  // DEDICATED: rolling window of y rows (the L2 prefetch makes three iterations of lookahead enough; 12 registers, not 32)
+      float4 yt[GB_TC_DEDICATED ? YW : 8];
+      // every output column of tile t from the staged accumulator against y (registers: all eight rows requested before the
+      // accumulator is ready, or the rolling window)
       auto emit = [&](int t) {
         const int trow = row_begin + t * TILE;
         const int nrows = min(TILE, row_end - trow);
@@ -760,7 +789,8 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + tr;
-          float4 yh, yv = yt[i];
+          float4 yh, yv = yt[GB_TC_DEDICATED ? i % YW : i];
+          if (GB_TC_DEDICATED && has_y && i + YW < 8) yt[i % YW] = y_row(t, i + YW);
           const uint32_t addr = stage + (uint32_t)r * 128u + ((uint32_t)(tc ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(yh.x), "=f"(yh.y), "=f"(yh.z), "=f"(yh.w) : "r"(addr));
           if (!in_cols) yv = make_float4(0.f, 0.f, 0.f, 0.f);  // zero-padded columns (T < 64): model output is 0 there too
@@ -809,15 +839,10 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 9, t, L - 1, t % NSLOT);
       };
 
-      // y rows of tile t -> registers (transposed layout), requested as early as the registers are free
+      // y rows of tile t -> registers, requested as early as the registers are free
       auto load_y = [&](int t) {
-        const int trow = row_begin + t * TILE;
-        const int nrows = min(TILE, row_end - trow);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = min(q * 32 + i * 4 + tr, nrows - 1);
-          yt[i] = in_cols ? __ldg(reinterpret_cast<const float4*>(a.y + (job.x_row + trow + r) * (long)TP + h * 32) + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < (GB_TC_DEDICATED ? YW : 8); ++i) yt[i] = y_row(t, i);
       };
       auto wait_f = [&](int s, int t) {
         mbar_wait(bars + BF + 8 * s, (ph_f >> s) & 1u);
@@ -826,6 +851,16 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
         if (lane == 0 && (warp == OUT0 || warp == EPI_WARPS - 1)) trace_ev(a, ring, trace_cnt, 8, t, L - 1, s);
       };
 
+      if (GB_TC_DEDICATED) {
+        // the slots' own layer warps feed the pipeline; these warps take the finished tiles strictly in turn
+        for (int t = 0; t < n_tiles; ++t) {
+          const int s = t % NSLOT;
+          if (has_y) load_y(t);
+          wait_f(s, t);
+          park(s, t);
+          emit(t);
+        }
+      } else {
       split_x(0);
       if (n_tiles > 1) split_x(1);
       if (NSLOT > 2 && n_tiles > 2) split_x(2);
@@ -858,6 +893,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           park(2, t0 + 2);
           emit(t0 + 2);
         }
+      }
       }
     }
     fence_proxy_async();  // this item's generic accesses to the x boxes / staging precede the next item's bulk copy and TMA loads
