@@ -70,9 +70,13 @@ constexpr int OBOX_BYTES = 32 * 128;   // staging box of one output warp: 32 row
 constexpr int W = 64;                  // widest feature / hidden width; narrower tag counts T (multiples of 4) ride in zero-padded columns
 
 // TMEM column map of one tile slot (fp32 columns); slot s starts at s * SLOT_COLS
-constexpr uint32_t COL_D = 0, COL_ALB = 64, COL_ABF = 96, SLOT_COLS = 128, COL_DX = NSLOT * 128, TMEM_COLS = 512;  // 3 slots + 2 spare accumulators (COL_DX, COL_DX + 64)
+// Shared layer group: accumulator 64 | operand images 64 (layer 0's BF16 pair and the later layers' FP16 pair share the columns).
+// DEDICATED: layer 0's images get their own 64 columns, so the slot's layer warps can prepare the NEXT tile's layer-0 operands
+// while the current tile is still in its hidden layers.
+constexpr uint32_t COL_D = 0, COL_A1 = 64, COL_A2 = 96, COL_ALB = GB_TC_DEDICATED ? 128 : 64, COL_ABF = GB_TC_DEDICATED ? 160 : 96,
+                   SLOT_COLS = GB_TC_DEDICATED ? 192 : 128, COL_DX = NSLOT * SLOT_COLS, TMEM_COLS = 512;
+static_assert(COL_DX + (GB_TC_DEDICATED ? NSLOT : NSLOT - 1) * 64 <= TMEM_COLS, "tile slots + spare accumulators exceed the 512 TMEM columns");
 // layers >= 1 keep their two packed-FP16 operand images (32 columns each) where layer 0's TF32-hi image was
-constexpr uint32_t COL_A1 = COL_ALB, COL_A2 = COL_ABF;
 // COL_DX: spare accumulator (absolute column) that receives the OUTPUT layer of slot-1 tiles, so slot 1 can start its next
 // tile while the output warps are still busy with the previous pair (they drain slot 0's accumulator first)
 
@@ -412,7 +416,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
   const uint32_t sbase = smem_u32(smem);
   // mbarriers, two of each (tile slot 0/1): x_full, a_ready, d_ready (hidden-layer MMAs), f_ready (output-layer MMAs), d_free
   const uint32_t bars = sbase + a.bar_ofs;
-  const uint32_t BX = 0, BA = 24, BD = 48, BF = 72, BE = 96, BW = 120;  // 8 bytes per tile slot each; BW: bulk copy of a slot's parameter vector
+  const uint32_t BX = 0, BA = 24, BD = 48, BF = 72, BE = 96, BW = 120, BA0 = 128;  // 8 bytes per tile slot each; BW: bulk copy of a slot's parameter vector; BA0: layer-0 operands ready (DEDICATED)
   const bool has_y = a.y != nullptr;
   const int TP = FULL ? W : a.T;  // tags per row = row pitch of x / y / per-tag outputs
   const int L = STATIC ? HG_L : a.last_layer + 1;
@@ -421,6 +425,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bars + BX + 8 * s, 1);
       mbar_init(bars + BA + 8 * s, MAIN_WARPS);
+      mbar_init(bars + BA0 + 8 * s, MAIN_WARPS);
       mbar_init(bars + BD + 8 * s, 1);
       mbar_init(bars + BF + 8 * s, 1);
       mbar_init(bars + BE + 8 * s, OUT_WARPS);
@@ -440,7 +445,7 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 
   // phase parities (each role uses the subset it waits on)
   uint32_t ph_x = 0, ph_d = 0, ph_f = 0;  // one parity bit per tile slot
-  uint32_t ph_a = 0, ph_e = 0, ph_w = 0;
+  uint32_t ph_a = 0, ph_a0 = 0, ph_e = 0, ph_w = 0;
   int cur_slot = -1;
   // Work distribution.  Tiles are numbered job by job (global tile G = job * tiles_per_job + tile) and handed out from a global
   // counter in contiguous ranges: whole jobs, in order, for most of the launch -- every change of job costs a pipeline drain +
@@ -560,26 +565,35 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
 
     // x -> A operand of layer 0 of tile `tt` (slot tt % NSLOT): done by the output warps (shared layer group: they have the slack) or
     // by the slot's own layer warps (DEDICATED); one thread = one row, warp/4 = column half in either group
-    auto split_x = [&](int tt) {
+    auto split_wait_x = [&](int tt) {  // the x boxes of tile tt have landed
       const int s = tt % NSLOT;
-      const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
       mbar_wait(bars + BX + 8 * s, (ph_x >> s) & 1u);
       ph_x ^= 1u << s;
+    };
+    auto split_piece = [&](int tt, int piece) {  // 8 columns of this thread's row: BF16 images of A_lo and A into the slot's layer-0 columns
+      const int s = tt % NSLOT;
+      const uint32_t xbox = sbase + a.xbox_ofs + (2 * s + h) * BOX_BYTES + (uint32_t)row * 128u;
+      float v[8];
 #pragma unroll
-      for (int piece = 0; piece < 4; ++piece) {  // 8 columns at a time keeps the register footprint small (y rows are live)
-        float v[8];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t addr = xbox + ((uint32_t)((piece * 2 + c) ^ (row & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
-        }
-        store_a_operands<8>(lane_base + s * SLOT_COLS, h * 32 + piece * 8, v);
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t addr = xbox + ((uint32_t)((piece * 2 + c) ^ (row & 7)) << 4);
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(addr));
       }
+      store_a_operands<8>(lane_base + s * SLOT_COLS, h * 32 + piece * 8, v);
+    };
+    auto split_done = [&](int tt) {  // operands visible to the tensor core; one arrival per warp
+      const int s = tt % NSLOT;
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BA + 8 * s);
+      if (lane == 0) mbar_arrive(bars + (GB_TC_DEDICATED ? BA0 : BA) + 8 * s);
       if (lane == 0 && (warp == OUT0 || (GB_TC_DEDICATED && warp == 0))) trace_ev(a, ring, trace_cnt, 3, tt, 0, s);
+    };
+    auto split_x = [&](int tt) {
+      split_wait_x(tt);
+#pragma unroll
+      for (int piece = 0; piece < 4; ++piece) split_piece(tt, piece);  // 8 columns at a time keeps the register footprint small
+      split_done(tt);
     };
     if (is_ctrl) {
       // =========================================== control warp of tile slot s: TMA producer + MMA issuer.
@@ -615,8 +629,13 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
           const uint32_t lbo = (uint32_t)Np * 16u;
           const uint32_t dstep = 2u * (uint32_t)Np;  // K-step in 16-byte units (two chunks); stays inside the address field
           const uint64_t dhi = make_bdesc(sbase + P.whi_ofs, lbo, 128), dlo = make_bdesc(sbase + P.wlo_ofs, lbo, 128), dhb = make_bdesc(sbase + whb_ofs, lbo, 128);
-          mbar_wait(bar_a, ph_a);
-          ph_a ^= 1;
+          if (GB_TC_DEDICATED && l == 0) {  // the slot's layer warps prepared this tile's layer-0 operands during the previous tile
+            mbar_wait(bars + BA0 + 8 * s, ph_a0);
+            ph_a0 ^= 1;
+          } else {
+            mbar_wait(bar_a, ph_a);
+            ph_a ^= 1;
+          }
           // the output warps must have drained the accumulator this MMA chain overwrites: slot 0 reuses its own D for every
           // layer (wait before layer 0); the other slots send only their output layer to a spare accumulator (wait before that layer)
           // (DEDICATED: every slot sends its output layer to a spare accumulator -- the output warps take the tiles strictly in turn
@@ -703,18 +722,31 @@ ffae_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtenso
       // warp 0 picking and a named barrier publishing the pick) measured 15-25 % slower with two slots and did not cure the
       // three-slot convoy either (profiles/r02_kernel_experiments.md).
       if (GB_TC_DEDICATED) {
-        // this group owns slot `grp`: it also prepares the layer-0 operands of its tiles (the output warps only park and store)
+        // This group owns slot `grp`.  It also prepares the layer-0 operands of its tiles -- for the NEXT tile already while the
+        // current one is in its hidden layers (a quarter of the row after each of the middle layers' epilogues, into columns of
+        // their own) -- so that the control warp can issue layer 0 of the next tile right behind the output layer of this one:
+        // neither the output layer nor the operand preparation is on the tile-to-tile chain of the slot any more.
+        const int H = L - 1;  // hidden layers
+        if (grp < n_tiles) split_x(grp);
         for (int t = grp; t < n_tiles; t += NSLOT) {
-          if (t >= NSLOT) {  // the previous tile's output-layer MMAs are complete: nothing reads the slot's operand columns any more
-            mbar_wait(bars + BF + 8 * grp, (ph_f >> grp) & 1u);
-            ph_f ^= 1u << grp;
-            tc_fence_after();
-          }
-          split_x(t);
-          for_layers<STATIC, true>(L - 1, [&](auto lc) {
+          const bool more = t + NSLOT < n_tiles;
+          for_layers<STATIC, true>(H, [&](auto lc) {
+            const int l = layer_index(lc);
             mbar_wait(bars + BD + 8 * grp, (ph_d >> grp) & 1u);
             ph_d ^= 1u << grp;
+            if (l == 0 && t >= NSLOT) {  // the previous tile's output-layer MMAs are complete: nothing reads the FP16 operand columns any more
+              mbar_wait(bars + BF + 8 * grp, (ph_f >> grp) & 1u);
+              ph_f ^= 1u << grp;
+            }
             serve(grp, t, lc);
+            if (more) {
+              const int first = H > 1 ? 1 : 0;                                   // pieces go behind the epilogues of layers first .. H-1
+              const int lo = H > 1 ? 4 * (l - 1) / (H - 1) : 0, hi = H > 1 ? 4 * l / (H - 1) : 4;
+              if (l == first) split_wait_x(t + NSLOT);
+              if (l >= first)
+                for (int piece = lo; piece < hi; ++piece) split_piece(t + NSLOT, piece);
+              if (l == H - 1) split_done(t + NSLOT);
+            }
           });
         }
         if (grp < n_tiles) {  // consume the last tile's output-layer phase too, so that the parity is right in the next work item
@@ -1031,7 +1063,7 @@ extern "C" int gb_ffae_infer_score_tc(const gb_ffnet* net, const float* params, 
   ofs = a.w_bytes;
   a.vec_ofs = ofs; ofs += 2 * W * 4;
   a.pair_ofs = ofs; ofs += 4 * TILE * 4;
-  a.bar_ofs = ofs; ofs += 128;
+  a.bar_ofs = ofs; ofs += 192;
   ofs = gb::round_up(ofs, 1024);
   a.xbox_ofs = ofs; ofs += 2 * NSLOT * BOX_BYTES;    // NSLOT tile slots x two 32-column boxes
   a.stage_ofs = ofs; ofs += OUT_WARPS * OBOX_BYTES;  // per output warp: a 32-row x 32-column staging box
