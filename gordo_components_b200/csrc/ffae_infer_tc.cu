@@ -55,7 +55,10 @@ constexpr int TILE = 128;
 constexpr int NSLOT = GB_TC_NSLOT;  // tiles in flight (2 or 3)
 static_assert(NSLOT == 2 || NSLOT == 3, "two or three tile slots");
 #ifndef GB_TC_DEDICATED
-#define GB_TC_DEDICATED 0  // 1: every tile slot has its own eight layer warps (26 warps: 72 registers per thread, measured 40 % slower: the output warps spill and starve); 0: one group of eight serves the slots in turn
+#define GB_TC_DEDICATED 0  // 1: every tile slot has its own eight layer warps, which also prepare the slot's layer-0 operands one tile ahead
+                           // (26 warps, 72 registers, no spills; parity-green).  Measured: the slot's tile-to-tile chain shortens to
+                           // ~16 k cycles, but the eight output warps -- 8.2 k cycles per tile, taking the tiles strictly in turn --
+                           // become the bottleneck: 0.715-0.757 of the HBM peak against 0.78 for 0 (one shared group), same box.
 #endif
 // Warp roles.  Layer warps (SFU-bound hidden-layer epilogues): MAIN_WARPS per group, one group per tile slot (DEDICATED) or one
 // group for all slots; then OUT_WARPS output warps (LSU-bound: x split, accumulator parking, anomaly columns); then one control warp
