@@ -190,6 +190,34 @@ def test_tc_work_split_many_ragged_jobs(engine, torch):
         close(a[k].cpu().numpy(), b[k].cpu().numpy(), mag=float(b[k].abs().max()), name=f"tcgen05 vs fp32: {k}")
 
 
+def test_more_jobs_than_a_grid_dimension(engine, torch):
+    """70 000 four-row jobs (a 16 384-machine bucket with 3 CV folds is 65 536): the kernels that carry the job index on gridDim.y
+    go out as several launches; every job still gets its own slot's answer."""
+    from oracle import keras_math as km
+
+    J, R, T = 70_000, 4, 8
+    spec, w0 = random_net(km, T, 1)
+    _, w1 = random_net(km, T, 2)
+    rng = np.random.default_rng(0)
+    X = rng.random((J * R, T)).astype(np.float32)
+    eng = engine.FFEngine(spec.dims, spec.acts, spec.l1)
+    dev = eng.device
+    params = eng.pack_params([w0, w1])
+    slots = (np.arange(J) % 2).astype(np.int32)
+    jobs = engine.jobs_to_device(engine.make_jobs(slots, R, np.arange(J, dtype=np.int64) * R), dev)
+    xd = torch.from_numpy(X).to(dev)
+    scale = torch.ones((2, T), device=dev)
+    for variant in (1, 3):  # generic fp32 kernel, row-per-thread kernel
+        res = eng.infer_score(params, jobs, J, R, xd, xd, scale, variant=variant)
+        out = res["model-output"].cpu().numpy().reshape(J, R, T)
+        for j in (0, 1, 65534, 65535, 65536, J - 1):
+            close(out[j], km.ff_forward(spec, (w0, w1)[j % 2], X[j * R:(j + 1) * R], dtype=np.float64), 1.0, name=f"variant {variant} job {j}")
+    feat, agg = engine.thresholds(jobs, J, R, res["tag-anomaly-unscaled"], res["total-anomaly-scaled"], T, 2, 2, dev)
+    assert torch.isfinite(feat).all() and torch.isfinite(agg).all()
+    lo_hi = engine.minmax_fit(jobs, J, R, xd, T, 2, dev, return_minmax=True)
+    np.testing.assert_array_equal(lo_hi[2][0].cpu().numpy(), X.reshape(J, R, T)[0::2].min(axis=(0, 1)))
+
+
 def test_ffae_jobs_slots_and_row_offsets(engine, torch):
     """Jobs may share a slot, read any row range and write anywhere; empty jobs are no-ops; predict-only mode."""
     from oracle import keras_math as km

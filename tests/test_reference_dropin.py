@@ -82,6 +82,27 @@ def reference_build(rc, definition, data):
     return builder._build()
 
 
+def test_model_builder_class_hook():
+    """MODEL_BUILDER_CLASS (gordo/builder/utils.py:8-17, executed from /root/reference): the class path resolves to a subclass of gordo's builder."""
+    import importlib.util
+    import sys
+
+    rc = rl.load_reference_callers()
+    spec = importlib.util.spec_from_file_location("gordo.builder.utils", os.path.join(rl.REFERENCE_ROOT, "gordo", "builder", "utils.py"))
+    utils = importlib.util.module_from_spec(spec)
+    sys.modules["gordo.builder.utils"] = utils
+    spec.loader.exec_module(utils)
+    cls = utils.create_model_builder("gordo_components_b200.gordo_hooks.B200ModelBuilder")
+    assert issubclass(cls, rc.ModelBuilder) and cls is not rc.ModelBuilder and cls._build is rc.ModelBuilder._build
+    builder = cls.__new__(cls)
+    builder.set_seed(3)
+    a = np.random.random()
+    builder.set_seed(3)
+    assert np.random.random() == a
+    with pytest.raises(ValueError):
+        utils.create_model_builder("gordo_components_b200.builder.ModelBuilder")  # the stand-alone builder is not a gordo subclass
+
+
 def test_reference_callers_drive_these_classes():
     rc = rl.load_reference_callers()
     # In an installation gordo is importable when this package is first imported and the registration below happens at import time
