@@ -125,11 +125,23 @@ __device__ __forceinline__ float fast_tanh(float z) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return fmaf(-2.0f, r, 1.0f);
 }
-__device__ __forceinline__ float cell_act(int act, float z) { return act == GB_ACT_TANH ? fast_tanh(z) : gb::apply_act(act, z); }
+// TANH (every factory default): straight-line ex2/rcp code; otherwise the generic activation switch (libdevice calls)
+template <bool TANH>
+__device__ __forceinline__ float cell_act(int act, float z) { return TANH ? fast_tanh(z) : gb::apply_act(act, z); }
+// one lane of a converged warp (lets ptxas emit the tcgen05 / TMA issue as straight-line uniform code, see ffae_infer_tc.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------------------------------------------------------------ one (layer, timestep) for all windows
 // Persistent: gridDim.x CTAs walk the work items (window tile, unit block); the accumulator is double-buffered in TMEM (2 x 256
 // columns), so the MMAs of item i+1 run while the epilogue warps finish the cell of item i; the TMA ring runs ahead across items.
+// FIRST: layer 0 (the additive term is the per-row input projection, read from global memory); TANH: tanh cell / output activation.
+// Both are compile-time so that the epilogue -- the phase an item's time is made of (12-14 us per item whatever K) -- is branch-free:
+// as runtime switches they cost 35 CALLs, ~390 branches and local-memory traffic in the SASS of this kernel.
+template <bool FIRST, bool TANH>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_below_hi, const __grid_constant__ CUtensorMap m_below_lo,
                     const __grid_constant__ CUtensorMap m_own_hi, const __grid_constant__ CUtensorMap m_own_lo,
@@ -177,7 +189,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
 
   if (warp == EPI_WARPS) {
     // ============================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int cc = 0;  // chunks issued so far (ring position)
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int tile, ub, tj;
@@ -214,7 +226,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         const int s = cc % STAGES, round = cc / STAGES;
         mbar_wait(bar_full + 8 * s, round & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = sbase + s * STAGE_BYTES;
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_BOX);
           const uint64_t b_hi = make_desc_sw128(st + 2 * A_BOX), b_lo = make_desc_sw128(st + 2 * A_BOX + B_BOX);
@@ -249,7 +261,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + uh * UH;
       const float* xk = nullptr;
       float* sb = s_bias[buf];
-      if (a.is_first) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
+      if (FIRST) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
         const long xr = min(job.x_row + min(w, job.n_rows - 1) + a.t, a.xk_rows - 1);
         xk = a.xk + ((xr >> 7) * (long)(4 * u) + ub * NCOL + uh * UH) * TILE + (xr & (TILE - 1));
       } else {
@@ -271,7 +283,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int i = 0; i < SL; ++i) ad[b2][g][i] = a.is_first ? __ldg(xk + (g * UB + j0 + i) * TILE) : sb[g * UB + j0 + i];
+          for (int i = 0; i < SL; ++i) ad[b2][g][i] = FIRST ? __ldg(xk + (g * UB + j0 + i) * TILE) : sb[g * UB + j0 + i];
       };
       load_add(0, 0);
       mbar_wait(bar_done + 8 * buf, (n >> 1) & 1);
@@ -295,23 +307,23 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * buf) : "memory");
           }
         }
-        float cn[SL];
-        __align__(8) __half h1[SL], h2[SL];
+        float cn[SL], hv[SL];
 #pragma unroll
         for (int i = 0; i < SL; ++i) {
           const float ig = sigm(z[cur][0][i] + ad[cur][0][i]), fg = sigm(z[cur][1][i] + ad[cur][1][i]);
-          const float gg = cell_act(a.act, z[cur][2][i] + ad[cur][2][i]), og = sigm(z[cur][3][i] + ad[cur][3][i]);
+          const float gg = cell_act<TANH>(a.act, z[cur][2][i] + ad[cur][2][i]), og = sigm(z[cur][3][i] + ad[cur][3][i]);
           cn[i] = fmaf(fg, cp[j0 + i], ig * gg);
-          const float h = og * cell_act(a.act, cn[i]);
-          h1[i] = __float2half_rn(h);
-          h2[i] = __float2half_rn(h - __half2float(h1[i]));
+          hv[i] = og * cell_act<TANH>(a.act, cn[i]);
         }
 #pragma unroll
         for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
 #pragma unroll
-        for (int i = 0; i < SL / 2; ++i) {  // keep the packed halves: a thread's UH units are one full 32-byte sector per image
-          hp1[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(h1 + 2 * i);
-          hp2[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(h2 + 2 * i);
+        for (int i = 0; i < SL / 2; ++i) {  // FP16 pair h = h1 + h2, packed in registers: a thread's UH units are one full 32-byte sector per image
+          const __half2 p1 = __floats2half2_rn(hv[2 * i], hv[2 * i + 1]);  // low half = even unit
+          const float2 f1 = __half22float2(p1);
+          const __half2 p2 = __floats2half2_rn(hv[2 * i] - f1.x, hv[2 * i + 1] - f1.y);
+          hp1[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p1);
+          hp2[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p2);
         }
       }
 #pragma unroll
@@ -558,7 +570,11 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
   int dev = 0, sms = 148;
   GB_CUDA_CHECK(cudaGetDevice(&dev));
   GB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  using StepKernel = void (*)(const TcLayerArgs, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap);
+  const StepKernel kernels[2][2] = {{lstm_tc_step_kernel<false, false>, lstm_tc_step_kernel<false, true>},
+                                    {lstm_tc_step_kernel<true, false>, lstm_tc_step_kernel<true, true>}};
+  for (int f = 0; f < 2; ++f)
+    for (int q = 0; q < 2; ++q) GB_CUDA_CHECK(cudaFuncSetAttribute(kernels[f][q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   // ---- the recurrence: h of (layer, t) is written to buffer t & 1 and read from buffer (t - 1) & 1 (zero at t = 0)
   for (int t = 0; t < p.L; ++t) {
@@ -575,7 +591,7 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
       const int lb = l > 0 ? l - 1 : 0;
       a.n_items = n_jobs * tiles_per_job * (p.u[l] / UB);
       const int grid = a.n_items < sms ? a.n_items : sms;
-      lstm_tc_step_kernel<<<grid, NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1], m_w[l][0], m_w[l][1]);
+      kernels[l == 0][net->act[l] == GB_ACT_TANH]<<<grid, NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1], m_w[l][0], m_w[l][1]);
     }
   }
   const int top = p.nl - 1, fin = (p.L - 1) & 1;
