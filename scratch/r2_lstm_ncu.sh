@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+python gordo_components_b200/csrc/build.py > /dev/null || exit 1
+cat > /tmp/lstm_run.py <<'PY'
+import torch, sys, os
+sys.path.insert(0, os.getcwd())
+import __graft_entry__ as ge; ge.build()
+from gordo_components_b200 import engine
+from benchmarks import secondary as sec
+sec.lstm_share(torch, engine, machines=32, rows=1400, lookback=6)
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_step -s 12 -c 6 -o gpurun_out/prof_lstm_r02 python /tmp/lstm_run.py > gpurun_out/ncu_lstm_r02.log 2>&1; tail -2 gpurun_out/ncu_lstm_r02.log; ls -la gpurun_out/prof_lstm_r02.ncu-rep
