@@ -25,10 +25,17 @@ namespace {
 constexpr int TILE = 128;            // windows per CTA
 constexpr int UB = 64;               // units per CTA
 constexpr int NCOL = 4 * UB;         // gate columns per CTA (accumulator width in TMEM)
-constexpr int KC = 64;               // K elements per pipeline chunk (one 128-byte swizzle row of FP16)
-constexpr int STAGES = 2;
-constexpr int A_BOX = TILE * 128;    // bytes: 128 rows x 64 FP16
-constexpr int B_BOX = NCOL * 128;    // bytes: 256 rows x 64 FP16
+#ifndef GB_LSTM_KC
+#define GB_LSTM_KC 64
+#endif
+// K elements per pipeline chunk = one swizzle row of FP16 (64: SWIZZLE_128B, two 96 KB stages; 32: SWIZZLE_64B, four 48 KB stages --
+// the same shared memory, but the TMA producer runs three chunks ahead of the MMAs instead of one)
+constexpr int KC = GB_LSTM_KC;
+static_assert(KC == 64 || KC == 32, "chunk = one 128- or 64-byte swizzle row");
+constexpr int ROW_BYTES = KC * 2;
+constexpr int STAGES = KC == 64 ? 2 : 4;
+constexpr int A_BOX = TILE * ROW_BYTES;    // bytes: 128 rows x KC FP16
+constexpr int B_BOX = NCOL * ROW_BYTES;    // bytes: 256 rows x KC FP16
 constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_BOX;
 constexpr int EPI_WARPS = 16;        // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which UH of the 64 units
 constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread
@@ -89,9 +96,9 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;  // SBO: 8-row groups
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)(KC == 64 ? 2 : 4) << 61;      // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {  // D fp32, A/B FP16, both K-major, M = 128
@@ -485,7 +492,7 @@ int make_map_f16(CUtensorMap* map, const void* base, long rows, long cols, int b
   cuuint32_t box[2] = {KC, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GB_REQUIRE(r == CUDA_SUCCESS, GB_E_CUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
   return GB_OK;
 }
