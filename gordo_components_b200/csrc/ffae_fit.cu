@@ -28,7 +28,7 @@ struct FitArgs {
   gb_fit_hparams hp;
   int apitch[GB_MAX_LAYERS + 1];  // pitch of activation buffer l (l = 0: x staging)
   int aofs[GB_MAX_LAYERS + 1];    // offset of activation buffer l (l >= 1) in smem floats
-  int xofs[2], yofs[2], dofs[2];
+  int xofs[2], yofs[2], dofs[3];
   int ypitch, dpitch;
   int wfloats, smem_floats;
   int n_in, n_out, max_rows;
@@ -40,6 +40,7 @@ struct FitArgs {
   const float *x, *y;
   const int32_t* perm;
   float *out_loss, *out_acc;
+  long long* trace;  // debug (gb_debug_set_fit_trace): cycles of CTA 0 per phase, summed over the fit; NULL in production
 };
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -67,6 +68,12 @@ __device__ __forceinline__ uint32_t permute_index(uint32_t i, uint32_t n, uint32
   return i;
 }
 
+// float -> unsigned with the same ordering (negative values below positive ones)
+__device__ __forceinline__ unsigned order_key(float x) {
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 __device__ __forceinline__ void adam_update(float& w, float g, float& m, float& v, float alpha, float omb1, float omb2,
                                             float eps) {
   m += (g - m) * omb1;
@@ -83,7 +90,9 @@ template <bool WG>
 __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float s_red[3][NWARPS];
-  __shared__ float s_alpha;
+  __shared__ float s_alpha[2];  // Adam step size of optimizer step t at [t & 1]: written one step ahead, off the critical path
+  __shared__ int s_idx[2][BR];
+  __shared__ long long s_phase[2 * GB_MAX_LAYERS + 4];
 
   const int job_id = blockIdx.x;
   const gb_job job = a.jobs[job_id];
@@ -91,6 +100,15 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   if (n <= 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.net.n_layers, n_in = a.n_in, n_out = a.n_out;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  long long t_mark = 0;
+  if (tracing) {
+    for (int i = 0; i < 2 * GB_MAX_LAYERS + 4; ++i) s_phase[i] = 0;
+    t_mark = clock64();
+  }
+  auto stamp = [&](int phase) {  // called by everyone right after a barrier; one thread books the cycles since the previous stamp
+    if (tracing) { const long long now = clock64(); s_phase[phase] += now - t_mark; t_mark = now; }
+  };
   const int B = a.hp.batch_size;
   float* P = a.params + (long)job.slot * a.pstride;
   float* Mg = a.adam_m + (long)job.slot * a.sstride;
@@ -128,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
     float* xs = smem + a.xofs[buf];
     float* ys = smem + a.yofs[buf];
     for (int r = warp; r < nb; r += NWARPS) {
-      const int src = row_index(e, s * B + c * BR + r);
+      const int src = s_idx[buf][r];
       const float* xr = xbase + (long)src * n_in;
       const float* yr = ybase + (long)src * n_out;
       if ((n_in & 3) == 0) {
@@ -148,7 +166,29 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   const float omb1 = 1.f - a.hp.beta1, omb2 = 1.f - a.hp.beta2, eps = a.hp.eps;
   int t_step = a.hp.step0;
   int cur = 0;
+  // the visiting order is resolved one chunk ahead of its gather by the last warp (a row per lane): the keyed permutation costs a
+  // few hundred instructions per row, which every warp would otherwise repeat in front of its cp.async
+  auto advance = [&](int& e, int& s, int& c) -> bool {  // next chunk in visiting order; false past the last epoch
+    const int nch = (min(B, n - s * B) + BR - 1) / BR;
+    if (++c == nch) { c = 0; if (++s == steps) { s = 0; ++e; } }
+    return e < a.hp.epochs;
+  };
+  auto stage_indices = [&](int buf, int e, int s, int c) {
+    const int nb = min(BR, min(B, n - s * B) - c * BR);
+    if (lane < nb) s_idx[buf][lane] = row_index(e, s * B + c * BR + lane);
+  };
+  auto adam_alpha = [&](int t_int) -> float {  // lr * sqrt(1 - b2^t) / (1 - b1^t)
+    const double t = (double)t_int;
+    return (float)((double)a.hp.lr * sqrt(1.0 - pow((double)a.hp.beta2, t)) / (1.0 - pow((double)a.hp.beta1, t)));
+  };
+  if (tid == 0) s_alpha[(t_step + 1) & 1] = adam_alpha(t_step + 1);
+  if (warp == NWARPS - 1) {
+    int e1 = 0, s1 = 0, c1 = 0;
+    stage_indices(0, 0, 0, 0);
+    if (advance(e1, s1, c1)) stage_indices(1, e1, s1, c1);
+  }
   __syncthreads();
+  stamp(2 * L + 2);  // set-up
   gather(0, 0, 0, 0);
   float* Gacc = Mg + a.wfloats;  // gradient sums of a multi-chunk mini-batch (same padded layout as the weights)
 
@@ -158,21 +198,20 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
       const int nbt = min(B, n - s * B);          // rows of this mini-batch
       const int nchunks = (nbt + BR - 1) / BR;
       ++t_step;
-      if (tid == 0) {
-        const double t = (double)t_step;
-        s_alpha = (float)((double)a.hp.lr * sqrt(1.0 - pow((double)a.hp.beta2, t)) / (1.0 - pow((double)a.hp.beta1, t)));
-      }
      for (int c = 0; c < nchunks; ++c) {
       const int nb = min(BR, nbt - c * BR);        // rows of this chunk
       const bool first_chunk = c == 0, last_chunk = c + 1 == nchunks;
       // ---- prefetch the next chunk, then wait for the current one ------------------------
-      int ne = e, ns = s, nc = c + 1;
-      if (nc == nchunks) { nc = 0; ++ns; }
-      if (ns == steps) { ns = 0; ++ne; }
-      const bool more = ne < a.hp.epochs;
+      int ne = e, ns = s, nc = c;
+      const bool more = advance(ne, ns, nc);
       if (more) gather(cur ^ 1, ne, ns, nc);
       if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
       __syncthreads();
+      stamp(0);
+      if (warp == NWARPS - 1) {  // the warp with the least work in the first layers prepares the next step
+        if (more && advance(ne, ns, nc)) stage_indices(cur, ne, ns, nc);  // read by the gather at the top of the next chunk
+        if (first_chunk && lane == 0) s_alpha[(t_step + 1) & 1] = adam_alpha(t_step + 1);  // read after the loss barrier of step t+1
+      }
 
       // ---- forward ---------------------------------------------------------------------------
       for (int l = 0; l < L; ++l) {
@@ -208,162 +247,169 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
           if (l1c != 0.f && lane < nb) acc_reg += l1c * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(o.w));
         }
         __syncthreads();
+        stamp(1 + l);
       }
 
-      // ---- loss, dL/dyhat, accuracy -------------------------------------------------------------
+      // ---- loss, accuracy, dz of the output layer: dz = (dL/dyhat + l1*sign(a)) * act'(a) ---------------
       {
         const float* yh = smem + a.aofs[L];
         const int yp = a.apitch[L];
         const float* yt = smem + a.yofs[cur];
         float* G = smem + a.dofs[0];
-        const int NpL = a.im.np[L - 1];
+        const int NpL = a.im.np[L - 1], actL = a.net.act[L - 1];
+        const float cL = a.net.l1[L - 1] / (a.hp.l1_div_batch ? (float)nbt : 1.f);
         const float gscale = 2.f / ((float)nbt * (float)n_out);
         for (int r = warp; r < BR; r += NWARPS) {
+          // keras "accuracy" on 2-D float targets: argmax match (binary if width 1); first maximum wins, as np.argmax.  The
+          // values are compared as order-preserving integer keys so that the warp-wide maximum is one REDUX.
+          unsigned kp = 0u, kt = 0u;
+          int bp = 0x7fffffff, bt = 0x7fffffff;
           for (int j = lane; j < NpL; j += 32) {
             float g = 0.f;
             if (r < nb && j < n_out) {
-              const float d = yh[r * yp + j] - yt[r * a.ypitch + j];
+              const float ao = yh[r * yp + j], t = yt[r * a.ypitch + j];
+              const float d = ao - t;
               acc_sq += d * d;
               g = gscale * d;
+              if (cL != 0.f) g += cL * ((ao > 0.f) ? 1.f : ((ao < 0.f) ? -1.f : 0.f));
+              g *= gb::act_grad_from_output(actL, ao);
+              const unsigned ka = order_key(ao), kb = order_key(t);
+              if (ka > kp) { kp = ka; bp = j; }
+              if (kb > kt) { kt = kb; bt = j; }
+              if (n_out == 1) acc_hit += ((ao > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
             }
             G[r * a.dpitch + j] = g;
           }
-        }
-        if (warp == NWARPS - 1 && lane < nb) {  // keras "accuracy" on 2-D float targets: argmax match (binary if width 1)
-          if (n_out == 1) {
-            acc_hit += ((yh[lane * yp] > 0.5f ? 1.f : 0.f) == yt[lane * a.ypitch]) ? 1.f : 0.f;
-          } else {
-            int bp = 0, bt = 0;
-            float vp = yh[lane * yp], vt = yt[lane * a.ypitch];
-            for (int j = 1; j < n_out; ++j) {
-              const float p = yh[lane * yp + j], q = yt[lane * a.ypitch + j];
-              if (p > vp) { vp = p; bp = j; }
-              if (q > vt) { vt = q; bt = j; }
-            }
-            acc_hit += (bp == bt) ? 1.f : 0.f;
+          if (n_out > 1 && r < nb) {
+            const unsigned mp = __reduce_max_sync(0xffffffffu, kp), mt = __reduce_max_sync(0xffffffffu, kt);
+            const int ip = __reduce_min_sync(0xffffffffu, kp == mp ? bp : 0x7fffffff);
+            const int it = __reduce_min_sync(0xffffffffu, kt == mt ? bt : 0x7fffffff);
+            if (lane == 0) acc_hit += (ip == it) ? 1.f : 0.f;
           }
         }
       }
       __syncthreads();
-      const float alpha = s_alpha;
+      stamp(L + 1);
+      const float alpha = s_alpha[t_step & 1];
 
-      // ---- backward + Adam --------------------------------------------------------------------------
-      int dcur = 0;
-      for (int l = L - 1; l >= 0; --l) {
-        const int Kp = a.im.kp[l], Np = a.im.np[l], N = a.net.dims[l + 1], act = a.net.act[l];
-        float* D = smem + a.dofs[dcur];
-        float* Dn = smem + a.dofs[dcur ^ 1];
-        const float* aout = smem + a.aofs[l + 1];
-        const int op = a.apitch[l + 1];
+      // ---- backward + Adam, pipelined over the layers ------------------------------------------------------
+      // dz of layer l lives in D buffer (L-1-l) % 3.  Phase p (one barrier each) runs, on disjoint data,
+      //   B(p):   dz_{p-1} = (dz_p . W_p^T + l1*sign(a)) * act'(a)      warps from the top, one 4-column task each
+      //   C(p+1): dW = a_in^T . dz, db, Adam in place                    all threads, one 4x2 block of W each
+      // B(p) reads W_p while C(p+1) writes W_{p+1}; the third buffer keeps dz_{p+1} alive while B(p) writes dz_{p-1}.
+      auto input_grad = [&](int l) {  // B(l), l >= 1
+        const int Kp = a.im.kp[l], Np = a.im.np[l], K = a.net.dims[l], actp = a.net.act[l - 1];
+        const float* D = smem + a.dofs[(L - 1 - l) % 3];
+        float* Dn = smem + a.dofs[(L - l) % 3];
+        const float* Wl = sW + a.im.wofs[l];
+        const float* aprev = smem + a.aofs[l] + lane * a.apitch[l];  // output of layer l-1
+        const float cp = a.net.l1[l - 1] / (a.hp.l1_div_batch ? (float)nbt : 1.f);
+        const bool live = lane < nb;
+        for (int task = NWARPS - 1 - warp; task < (Kp >> 2); task += NWARPS) {
+          const int k0 = task << 2;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* drow = D + lane * a.dpitch;
+          for (int nn = 0; nn < Np; nn += 4) {
+            const float4 d = *reinterpret_cast<const float4*>(drow + nn);
+            const float4 w0 = *reinterpret_cast<const float4*>(Wl + (k0 + 0) * Np + nn);
+            const float4 w1 = *reinterpret_cast<const float4*>(Wl + (k0 + 1) * Np + nn);
+            const float4 w2 = *reinterpret_cast<const float4*>(Wl + (k0 + 2) * Np + nn);
+            const float4 w3 = *reinterpret_cast<const float4*>(Wl + (k0 + 3) * Np + nn);
+            acc.x = fmaf(d.x, w0.x, acc.x); acc.x = fmaf(d.y, w0.y, acc.x); acc.x = fmaf(d.z, w0.z, acc.x); acc.x = fmaf(d.w, w0.w, acc.x);
+            acc.y = fmaf(d.x, w1.x, acc.y); acc.y = fmaf(d.y, w1.y, acc.y); acc.y = fmaf(d.z, w1.z, acc.y); acc.y = fmaf(d.w, w1.w, acc.y);
+            acc.z = fmaf(d.x, w2.x, acc.z); acc.z = fmaf(d.y, w2.y, acc.z); acc.z = fmaf(d.z, w2.z, acc.z); acc.z = fmaf(d.w, w2.w, acc.z);
+            acc.w = fmaf(d.x, w3.x, acc.w); acc.w = fmaf(d.y, w3.y, acc.w); acc.w = fmaf(d.z, w3.z, acc.w); acc.w = fmaf(d.w, w3.w, acc.w);
+          }
+          const float4 ao = *reinterpret_cast<const float4*>(aprev + k0);
+          auto dz = [&](float g, float o, int j) -> float {
+            if (!live || j >= K) return 0.f;
+            if (cp != 0.f) g += cp * ((o > 0.f) ? 1.f : ((o < 0.f) ? -1.f : 0.f));
+            return g * gb::act_grad_from_output(actp, o);
+          };
+          float4 o;
+          o.x = dz(acc.x, ao.x, k0 + 0); o.y = dz(acc.y, ao.y, k0 + 1); o.z = dz(acc.z, ao.z, k0 + 2); o.w = dz(acc.w, ao.w, k0 + 3);
+          *reinterpret_cast<float4*>(Dn + lane * a.dpitch + k0) = o;
+        }
+      };
+      auto weight_step = [&](int l) {  // C(l)
+        const int Kp = a.im.kp[l], Np = a.im.np[l];
+        const float* D = smem + a.dofs[(L - 1 - l) % 3];
         const float* ain = (l == 0) ? smem + a.xofs[cur] : smem + a.aofs[l];
         const int ip = a.apitch[l];
         float* Wl = sW + a.im.wofs[l];
-        // A: dz = (G + l1*sign(a)) * act'(a)
-        {
-          const float c = a.net.l1[l] / (a.hp.l1_div_batch ? (float)nbt : 1.f);
-          for (int r = warp; r < BR; r += NWARPS) {
-            for (int j = lane; j < Np; j += 32) {
-              float dz = 0.f;
-              if (r < nb && j < N) {
-                const float ao = aout[r * op + j];
-                float g = D[r * a.dpitch + j];
-                if (c != 0.f) g += c * ((ao > 0.f) ? 1.f : ((ao < 0.f) ? -1.f : 0.f));
-                dz = g * gb::act_grad_from_output(act, ao);
-              }
-              D[r * a.dpitch + j] = dz;
-            }
-          }
-        }
-        __syncthreads();
-        // B: dL/da_in = dz . W^T
-        if (l > 0) {
-          for (int task = warp; task < (Kp >> 2); task += NWARPS) {
-            const int k0 = task << 2;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float* drow = D + lane * a.dpitch;
-            for (int nn = 0; nn < Np; nn += 4) {
-              const float4 d = *reinterpret_cast<const float4*>(drow + nn);
-              const float4 w0 = *reinterpret_cast<const float4*>(Wl + (k0 + 0) * Np + nn);
-              const float4 w1 = *reinterpret_cast<const float4*>(Wl + (k0 + 1) * Np + nn);
-              const float4 w2 = *reinterpret_cast<const float4*>(Wl + (k0 + 2) * Np + nn);
-              const float4 w3 = *reinterpret_cast<const float4*>(Wl + (k0 + 3) * Np + nn);
-              acc.x = fmaf(d.x, w0.x, acc.x); acc.x = fmaf(d.y, w0.y, acc.x); acc.x = fmaf(d.z, w0.z, acc.x); acc.x = fmaf(d.w, w0.w, acc.x);
-              acc.y = fmaf(d.x, w1.x, acc.y); acc.y = fmaf(d.y, w1.y, acc.y); acc.y = fmaf(d.z, w1.z, acc.y); acc.y = fmaf(d.w, w1.w, acc.y);
-              acc.z = fmaf(d.x, w2.x, acc.z); acc.z = fmaf(d.y, w2.y, acc.z); acc.z = fmaf(d.z, w2.z, acc.z); acc.z = fmaf(d.w, w2.w, acc.z);
-              acc.w = fmaf(d.x, w3.x, acc.w); acc.w = fmaf(d.y, w3.y, acc.w); acc.w = fmaf(d.z, w3.z, acc.w); acc.w = fmaf(d.w, w3.w, acc.w);
-            }
-            *reinterpret_cast<float4*>(Dn + lane * a.dpitch + k0) = acc;
-          }
-        }
-        __syncthreads();
-        // C: dW = a_in^T . dz (4x4 block per thread), db, Adam -- weights updated in place in smem
-        {
-          const int kblocks = Kp >> 2, nblocks = kblocks * (Np >> 2);
-          float* Ml = Mg + a.im.wofs[l];
-          float* Vl = Vg + a.im.wofs[l];
-          for (int bid = tid; bid < nblocks; bid += THREADS) {
-            const int kb = bid % kblocks, n0 = (bid / kblocks) << 2, k0 = kb << 2;
-            float4 mq[4], vq[4];  // Adam moments of this block: requested now, consumed after the reduction over the batch rows
+        float* Ml = Mg + a.im.wofs[l];
+        float* Vl = Vg + a.im.wofs[l];
+        float* Gl = Gacc + a.im.wofs[l];
+        const int nhalf = Np >> 1, nblocks = (Kp >> 2) * nhalf;
+        for (int bid = tid; bid < nblocks; bid += THREADS) {  // consecutive threads along n: the moments stream coalesced
+          const int kb = bid / nhalf, n0 = (bid - kb * nhalf) << 1, k0 = kb << 2;
+          const bool adam = nchunks == 1 || last_chunk;
+          float2 mq[4], vq[4];  // Adam moments of this block: requested now, consumed after the reduction over the batch rows
+          if (adam) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              mq[i] = *reinterpret_cast<const float4*>(Ml + (k0 + i) * Np + n0);
-              vq[i] = *reinterpret_cast<const float4*>(Vl + (k0 + i) * Np + n0);
+              mq[i] = *reinterpret_cast<const float2*>(Ml + (k0 + i) * Np + n0);
+              vq[i] = *reinterpret_cast<const float2*>(Vl + (k0 + i) * Np + n0);
             }
-            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
-#pragma unroll 4
-            for (int r = 0; r < BR; ++r) {
-              const float4 av = *reinterpret_cast<const float4*>(ain + r * ip + k0);
-              const float4 d = *reinterpret_cast<const float4*>(D + r * a.dpitch + n0);
-              g0.x = fmaf(av.x, d.x, g0.x); g0.y = fmaf(av.x, d.y, g0.y); g0.z = fmaf(av.x, d.z, g0.z); g0.w = fmaf(av.x, d.w, g0.w);
-              g1.x = fmaf(av.y, d.x, g1.x); g1.y = fmaf(av.y, d.y, g1.y); g1.z = fmaf(av.y, d.z, g1.z); g1.w = fmaf(av.y, d.w, g1.w);
-              g2.x = fmaf(av.z, d.x, g2.x); g2.y = fmaf(av.z, d.y, g2.y); g2.z = fmaf(av.z, d.z, g2.z); g2.w = fmaf(av.z, d.w, g2.w);
-              g3.x = fmaf(av.w, d.x, g3.x); g3.y = fmaf(av.w, d.y, g3.y); g3.z = fmaf(av.w, d.z, g3.z); g3.w = fmaf(av.w, d.w, g3.w);
-            }
-            float4 gs[4] = {g0, g1, g2, g3};
-            if (nchunks > 1) {  // multi-chunk mini-batch: sum the chunks' gradients in the L2 scratch image; Adam with the last chunk
-              float* Gl = Gacc + a.im.wofs[l];
+          }
+          float2 gs[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4* gp = reinterpret_cast<float4*>(Gl + (k0 + i) * Np + n0);
-                if (!first_chunk) {
-                  const float4 o = *gp;
-                  gs[i].x += o.x; gs[i].y += o.y; gs[i].z += o.z; gs[i].w += o.w;
-                }
-                if (!last_chunk) *gp = gs[i];
+          for (int i = 0; i < 4; ++i) gs[i] = make_float2(0.f, 0.f);
+#pragma unroll 4
+          for (int r = 0; r < BR; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(ain + r * ip + k0);
+            const float2 d = *reinterpret_cast<const float2*>(D + r * a.dpitch + n0);
+            gs[0].x = fmaf(av.x, d.x, gs[0].x); gs[0].y = fmaf(av.x, d.y, gs[0].y);
+            gs[1].x = fmaf(av.y, d.x, gs[1].x); gs[1].y = fmaf(av.y, d.y, gs[1].y);
+            gs[2].x = fmaf(av.z, d.x, gs[2].x); gs[2].y = fmaf(av.z, d.y, gs[2].y);
+            gs[3].x = fmaf(av.w, d.x, gs[3].x); gs[3].y = fmaf(av.w, d.y, gs[3].y);
+          }
+          if (nchunks > 1) {  // multi-chunk mini-batch: sum the chunks' gradients in the L2 scratch image; Adam with the last chunk
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2* gp = reinterpret_cast<float2*>(Gl + (k0 + i) * Np + n0);
+              if (!first_chunk) {
+                const float2 o = *gp;
+                gs[i].x += o.x; gs[i].y += o.y;
               }
-              if (!last_chunk) continue;
+              if (!last_chunk) *gp = gs[i];
             }
+          }
+          if (adam) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int off = (k0 + i) * Np + n0;
-              float4 w = *reinterpret_cast<float4*>(Wl + off);
-              float4 m = mq[i];
-              float4 v = vq[i];
+              float2 w = *reinterpret_cast<float2*>(Wl + off);
+              float2 m = mq[i];
+              float2 v = vq[i];
               adam_update(w.x, gs[i].x, m.x, v.x, alpha, omb1, omb2, eps);
               adam_update(w.y, gs[i].y, m.y, v.y, alpha, omb1, omb2, eps);
-              adam_update(w.z, gs[i].z, m.z, v.z, alpha, omb1, omb2, eps);
-              adam_update(w.w, gs[i].w, m.w, v.w, alpha, omb1, omb2, eps);
-              *reinterpret_cast<float4*>(Wl + off) = w;
-              *reinterpret_cast<float4*>(Ml + off) = m;
-              *reinterpret_cast<float4*>(Vl + off) = v;
+              *reinterpret_cast<float2*>(Wl + off) = w;
+              *reinterpret_cast<float2*>(Ml + off) = m;
+              *reinterpret_cast<float2*>(Vl + off) = v;
             }
-          }
-          for (int j = THREADS - 1 - tid; j < Np; j += THREADS) {
-            float g = 0.f;
-            for (int r = 0; r < BR; ++r) g += D[r * a.dpitch + j];
-            const int off = a.im.bofs[l] + j;
-            if (nchunks > 1) {
-              if (!first_chunk) g += Gacc[off];
-              if (!last_chunk) { Gacc[off] = g; continue; }
-            }
-            float w = sW[off], m = Mg[off], v = Vg[off];
-            adam_update(w, g, m, v, alpha, omb1, omb2, eps);
-            sW[off] = w; Mg[off] = m; Vg[off] = v;
           }
         }
-        dcur ^= 1;
+        for (int j = THREADS - 1 - tid; j < Np; j += THREADS) {
+          float g = 0.f;
+          for (int r = 0; r < BR; ++r) g += D[r * a.dpitch + j];
+          const int off = a.im.bofs[l] + j;
+          if (nchunks > 1) {
+            if (!first_chunk) g += Gacc[off];
+            if (!last_chunk) { Gacc[off] = g; continue; }
+          }
+          float w = sW[off], m = Mg[off], v = Vg[off];
+          adam_update(w, g, m, v, alpha, omb1, omb2, eps);
+          sW[off] = w; Mg[off] = m; Vg[off] = v;
+        }
+      };
+      for (int p = L - 1; p >= 0; --p) {
+        if (p > 0) input_grad(p);
+        if (p + 1 < L) weight_step(p + 1);
+        if (p == 0) weight_step(0);
+        __syncthreads();
+        stamp(L + 2 + (L - 1 - p));
       }
-      __syncthreads();
       cur ^= 1;
      }  // chunks
     }
@@ -396,7 +442,13 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
     }
     for (int nn = tid; nn < N; nn += THREADS) Wg[K * N + nn] = sW[a.im.bofs[l] + nn];
   }
+  if (tracing) {
+    stamp(2 * L + 3);  // epoch statistics + write-back
+    for (int i = 0; i < 2 * GB_MAX_LAYERS + 4; ++i) a.trace[i] = s_phase[i];
+  }
 }
+
+long long* g_fit_trace = nullptr;
 
 int odd_pitch(int width) {
   int p4 = (width + 3) / 4;
@@ -411,6 +463,13 @@ extern "C" {
 size_t gb_ffae_fit_state_stride(const gb_ffnet* net) {
   if (gb::validate_ffnet(net) != GB_OK) return 0;
   return 3 * (size_t)gb::round_up(gb::make_ff_image(net, 4).total, 4);  // moments + gradient scratch of multi-chunk mini-batches + weight image of wide stacks
+}
+
+// debug aid (not part of the public header): per-phase cycle sums of CTA 0 into a device buffer of 2*GB_MAX_LAYERS+4 int64
+// (0 gather wait, 1..L forward layers, L+1 loss, L+2.. backward phases, 2L+2 set-up, 2L+3 tail); NULL switches it off
+int gb_debug_set_fit_trace(void* dev_buf) {
+  g_fit_trace = static_cast<long long*>(dev_buf);
+  return GB_OK;
 }
 
 int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v, const gb_job* jobs, int32_t n_jobs,
@@ -454,7 +513,7 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
     a.ypitch = odd_pitch(gb::round_up(a.n_out, 4));
     for (int b = 0; b < 2; ++b) { a.yofs[b] = ofs; ofs += BR * a.ypitch; }
     a.dpitch = odd_pitch(a.im.max_np);
-    for (int b = 0; b < 2; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
+    for (int b = 0; b < 3; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
     a.smem_floats = ofs;
     smem = (size_t)ofs * sizeof(float);
     if (smem <= 227 * 1024) break;
@@ -463,6 +522,7 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
   GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory for the activations of one mini-batch chunk", smem);
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.jobs = jobs; a.x = x; a.y = y; a.perm = perm;
   a.out_loss = out_loss; a.out_acc = out_acc;
+  a.trace = g_fit_trace;
   if (w_global) {
     GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ffae_fit_kernel<true><<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
