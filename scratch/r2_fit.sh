@@ -2,7 +2,7 @@
 # fit kernel: parity tests, then the configs[2] share with the per-phase cycle trace of CTA 0
 cd "$(dirname "$0")/.."
 python gordo_components_b200/csrc/build.py > /dev/null || exit 1
-timeout 900 python -m pytest tests -q -m gpu -x -k "fit or build or cross or dropin or fleet or early" 2>&1 | tail -5
+timeout 900 python -m pytest tests -q -m gpu -x -k "fit or build or cross or dropin or fleet or early" 2>&1 | tail -${PYTAIL:-5}
 cat > /tmp/fit_run.py <<'PY'
 import torch, sys, os, ctypes, json
 sys.path.insert(0, os.getcwd())
