@@ -37,6 +37,16 @@ constexpr int STAGES = KC == 64 ? 2 : 4;
 constexpr int A_BOX = TILE * ROW_BYTES;    // bytes: 128 rows x KC FP16
 constexpr int B_BOX = NCOL * ROW_BYTES;    // bytes: 256 rows x KC FP16
 constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_BOX;
+#ifndef GB_LSTM_PAIR
+#define GB_LSTM_PAIR 1
+#endif
+// CTA pair (thread-block cluster of 2): the two CTAs work on neighbouring window tiles of the SAME job and unit block, so they need
+// the same weight box; each fetches half of it (128 of the 256 gate rows) and TMA multicasts the half into both CTAs' stages.  The wide
+// layers are bound by the L2 -> SM operand stream (64 KB of weights + 32 KB of state per 64 values of K and CTA); the pair reads the
+// weights from L2 once instead of twice.
+constexpr int PAIR = GB_LSTM_PAIR ? 2 : 1;
+constexpr int B_PART_ROWS = NCOL / PAIR;          // gate rows of the weight box one CTA fetches
+constexpr int B_PART = B_PART_ROWS * ROW_BYTES;   // bytes
 constexpr int EPI_WARPS = 16;        // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which UH of the 64 units
 constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread
 constexpr int SL = 4;                // units per software-pipeline slice (registers: 576 threads leave 112 each)
@@ -45,7 +55,7 @@ constexpr int NTHREADS = (EPI_WARPS + 2) * 32;  // + warp 8: TMA producer, warp 
 struct TcLayerArgs {
   int u, kc_below, kc_own;           // units; K chunks coming from the layer below / from this layer's own h
   int act, is_first;
-  int tiles_per_job, t, lookback, n_items;
+  int tiles_per_job, pairs_per_job, t, lookback, n_items;  // n_items counts (tile group of PAIR, unit block)
   const gb_job* jobs;
   const float* bias;                 // [n_slots][4u] reordered (layers >= 1; layer 0's bias lives in xk)
   const float* xk;                   // layer 0: input projection, row-blocked [x row / 128][4u reordered][128]
@@ -78,6 +88,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+// the same box into the same shared-memory offset of every CTA of the cluster named by mask; each destination's mbarrier (same offset)
+// receives the bytes
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], FP16 inputs, fp32 accumulate
 __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -90,6 +116,10 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t adesc, uint64_t 
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one arrival on the barrier at this offset in every CTA of the cluster named by mask, when the MMAs issued so far have completed
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 // K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); the K step inside the swizzle
 // row is taken by advancing the start address (32 bytes per K=16 FP16 step)
@@ -165,7 +195,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, PAIR);  // one tcgen05.commit per CTA of the pair: a stage is written by both CTAs' TMA
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_done + 8 * b, 1);
@@ -179,27 +209,38 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR > 1) cluster_sync_all();  // the partner's barriers are initialised before anything of ours can reach them
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   const int n_chunks = a.kc_below + a.kc_own;
   const int nub = u / UB;
+  const int rank = PAIR > 1 ? (int)cluster_rank() : 0;
+  const int first_item = PAIR > 1 ? (int)(blockIdx.x / PAIR) : (int)blockIdx.x, item_step = (int)(gridDim.x / PAIR);
   // work item -> (tile, ub): the unit blocks of one window tile are neighbours, so CTAs running side by side read the same A
   // operand and it comes from L2.  Items whose tile holds no real window are skipped by every role alike.
-  auto item_info = [&](int item, int& tile, int& ub, gb_job& job, int& tj) -> bool {
-    tile = item / nub;
-    ub = item - tile * nub;
-    const int job_id = tile / a.tiles_per_job;
-    tj = tile - job_id * a.tiles_per_job;
+  // An item is a group of PAIR neighbouring tiles of one job x one unit block; this CTA takes tile rank of the group.  `real`: the
+  // group holds windows (every CTA of the pair runs the item's pipeline then -- the partner needs this CTA's half of the weights and
+  // its release of the stages); `mine`: this CTA's own tile holds windows (otherwise it computes on the group's first tile and
+  // writes nothing).
+  auto item_info = [&](int item, int& tile, int& ub, gb_job& job, int& tj, bool& mine) -> bool {
+    const int grp = item / nub;
+    ub = item - grp * nub;
+    const int job_id = grp / a.pairs_per_job;
+    const int tj0 = (grp - job_id * a.pairs_per_job) * PAIR;
     job = a.jobs[job_id];
-    return tj * TILE < job.n_rows;
+    tj = tj0 + rank;
+    mine = tj < a.tiles_per_job && tj * TILE < job.n_rows;
+    if (!mine) tj = tj0;
+    tile = job_id * a.tiles_per_job + tj;
+    return tj0 * TILE < job.n_rows;
   };
   // The job record of an item is a global load (L2 latency) that every role needs before it can do anything for the item: each
   // role fetches the record of its NEXT item while it works on the current one (ncu: the exposed load was ~20 % of the stall
   // samples of the narrow layers).
-  struct Item { int tile, ub, tj; gb_job job; bool real; };
+  struct Item { int tile, ub, tj; gb_job job; bool real, mine; };
   auto fetch_item = [&](int item) -> Item {
     Item it{};
-    if (item < a.n_items) it.real = item_info(item, it.tile, it.ub, it.job, it.tj);
+    if (item < a.n_items) it.real = item_info(item, it.tile, it.ub, it.job, it.tj, it.mine);
     return it;
   };
 
@@ -207,10 +248,10 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     // ============================== TMA producer
     if (elect_one()) {
       int cc = 0;  // chunks issued so far (ring position)
-      Item nxt = fetch_item(blockIdx.x);
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      Item nxt = fetch_item(first_item);
+      for (int item = first_item; item < a.n_items; item += item_step) {
         const Item cur = nxt;
-        nxt = fetch_item(item + gridDim.x);
+        nxt = fetch_item(item + item_step);
         if (!cur.real) continue;
         const int tile = cur.tile, ub = cur.ub;
         const gb_job job = cur.job;
@@ -224,8 +265,14 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
           const int acol = (below ? c : c - a.kc_below) * KC;
           tma_load_2d(st, below ? &m_below_hi : &m_own_hi, acol, row0, bar_full + 8 * s);
           tma_load_2d(st + A_BOX, below ? &m_below_lo : &m_own_lo, acol, row0, bar_full + 8 * s);
-          tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0, bar_full + 8 * s);
-          tma_load_2d(st + 2 * A_BOX + B_BOX, &m_w_lo, c * KC, wrow0, bar_full + 8 * s);
+          if (PAIR > 1) {  // this CTA's part of the weight box, into both CTAs
+            const uint16_t both = (uint16_t)((1u << PAIR) - 1u);
+            tma_load_2d_mc(st + 2 * A_BOX + rank * B_PART, &m_w_hi, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s, both);
+            tma_load_2d_mc(st + 2 * A_BOX + B_BOX + rank * B_PART, &m_w_lo, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s, both);
+          } else {
+            tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0, bar_full + 8 * s);
+            tma_load_2d(st + 2 * A_BOX + B_BOX, &m_w_lo, c * KC, wrow0, bar_full + 8 * s);
+          }
         }
       }
     }
@@ -233,10 +280,10 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     // ============================== MMA issuer
     const uint32_t idesc = make_idesc_f16(NCOL);
     int cc = 0, n = 0;  // chunks consumed, items started
-    Item nxt = fetch_item(blockIdx.x);
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    Item nxt = fetch_item(first_item);
+    for (int item = first_item; item < a.n_items; item += item_step) {
       const Item cur = nxt;
-      nxt = fetch_item(item + gridDim.x);
+      nxt = fetch_item(item + item_step);
       if (!cur.real) continue;
       const int buf = n & 1;
       if (n >= 2) mbar_wait(bar_free + 8 * buf, ((n >> 1) - 1) & 1);  // the epilogue has drained this accumulator
@@ -257,7 +304,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
             mma_f16_ss(dcol, a_hi + adv, b_lo + adv, idesc, 1u);
             mma_f16_ss(dcol, a_hi + adv, b_hi + adv, idesc, 1u);
           }
-          mma_commit(bar_empty + 8 * s);
+          if (PAIR > 1) mma_commit_mc(bar_empty + 8 * s, (uint16_t)((1u << PAIR) - 1u)); else mma_commit(bar_empty + 8 * s);
           if (c + 1 == n_chunks) mma_commit(bar_done + 8 * buf);
         }
         __syncwarp();
@@ -271,13 +318,13 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     // current one is evaluated: per-thread row accesses have no coalescing to hide their latency behind.
     int n = 0;
     bool bias_staged = false;  // the previous item already put this item's bias into s_bias[buf]
-    Item nxt = fetch_item(blockIdx.x);
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-      const Item cur = nxt;
-      nxt = fetch_item(item + gridDim.x);
-      if (!cur.real) continue;
-      const int tile = cur.tile, ub = cur.ub, tj = cur.tj;
-      const gb_job job = cur.job;
+    Item nxt = fetch_item(first_item);
+    for (int item = first_item; item < a.n_items; item += item_step) {
+      const Item cur_item = nxt;
+      nxt = fetch_item(item + item_step);
+      if (!cur_item.real) continue;
+      const int tile = cur_item.tile, ub = cur_item.ub, tj = cur_item.tj;
+      const gb_job job = cur_item.job;
       const int buf = n & 1;
       const int r = tid & (TILE - 1), uh = warp >> 2;      // window row 0..127; which UH of the 64 units this warp evaluates
       const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
@@ -345,8 +392,10 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
           cn[i] = fmaf(fg, cp[j0 + i], ig * gg);
           hv[i] = og * cell_act<TANH>(a.act, cn[i]);
         }
+        if (cur_item.mine) {
 #pragma unroll
-        for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
+          for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
+        }
 #pragma unroll
         for (int i = 0; i < SL / 2; ++i) {  // FP16 pair h = h1 + h2, packed in registers: a thread's UH units are one full 32-byte sector per image
           const __half2 p1 = __floats2half2_rn(hv[2 * i], hv[2 * i + 1]);  // low half = even unit
@@ -356,10 +405,12 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
           hp2[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p2);
         }
       }
+      if (cur_item.mine) {  // a CTA without a tile of its own ran the item for its partner's sake (weights, stage release) on the group's first tile
 #pragma unroll
-      for (int i = 0; i < UH / 8; ++i) {
-        *reinterpret_cast<uint4*>(hh + 8 * i) = make_uint4(hp1[4 * i], hp1[4 * i + 1], hp1[4 * i + 2], hp1[4 * i + 3]);
-        *reinterpret_cast<uint4*>(hl + 8 * i) = make_uint4(hp2[4 * i], hp2[4 * i + 1], hp2[4 * i + 2], hp2[4 * i + 3]);
+        for (int i = 0; i < UH / 8; ++i) {
+          *reinterpret_cast<uint4*>(hh + 8 * i) = make_uint4(hp1[4 * i], hp1[4 * i + 1], hp1[4 * i + 2], hp1[4 * i + 3]);
+          *reinterpret_cast<uint4*>(hl + 8 * i) = make_uint4(hp2[4 * i], hp2[4 * i + 1], hp2[4 * i + 2], hp2[4 * i + 3]);
+        }
       }
       if (!FIRST && bias_staged && tid < NCOL) s_bias[buf ^ 1][tid] = bias_next;
       ++n;
@@ -367,6 +418,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR > 1) cluster_sync_all();  // nothing of the partner's (multicast bytes, barrier arrivals) may still be on its way into this CTA
   if (warp == EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
 }
 
@@ -594,8 +646,8 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
       if ((rc = make_map_f16(&m_h[l][b][0], ws + p.h_hi[l][b], rows_pad, p.u[l], TILE)) != GB_OK) return rc;
       if ((rc = make_map_f16(&m_h[l][b][1], ws + p.h_lo[l][b], rows_pad, p.u[l], TILE)) != GB_OK) return rc;
     }
-    if ((rc = make_map_f16(&m_w[l][0], ws + p.w_hi[l], (long)n_slots * 4 * p.u[l], p.kp[l], NCOL)) != GB_OK) return rc;
-    if ((rc = make_map_f16(&m_w[l][1], ws + p.w_lo[l], (long)n_slots * 4 * p.u[l], p.kp[l], NCOL)) != GB_OK) return rc;
+    if ((rc = make_map_f16(&m_w[l][0], ws + p.w_hi[l], (long)n_slots * 4 * p.u[l], p.kp[l], B_PART_ROWS)) != GB_OK) return rc;
+    if ((rc = make_map_f16(&m_w[l][1], ws + p.w_lo[l], (long)n_slots * 4 * p.u[l], p.kp[l], B_PART_ROWS)) != GB_OK) return rc;
   }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   int dev = 0, sms = 148;
@@ -620,9 +672,21 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
       a.h_out_hi = reinterpret_cast<__half*>(ws + p.h_hi[l][wr]);
       a.h_out_lo = reinterpret_cast<__half*>(ws + p.h_lo[l][wr]);
       const int lb = l > 0 ? l - 1 : 0;
-      a.n_items = n_jobs * tiles_per_job * (p.u[l] / UB);
-      const int grid = a.n_items < sms ? a.n_items : sms;
-      kernels[l == 0][net->act[l] == GB_ACT_TANH]<<<grid, NTHREADS, smem, st>>>(a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1], m_w[l][0], m_w[l][1]);
+      a.pairs_per_job = (tiles_per_job + PAIR - 1) / PAIR;
+      a.n_items = n_jobs * a.pairs_per_job * (p.u[l] / UB);
+      const int groups = a.n_items < sms / PAIR ? a.n_items : sms / PAIR;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(groups * PAIR);
+      cfg.blockDim = dim3(NTHREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = PAIR; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      GB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernels[l == 0][net->act[l] == GB_ACT_TANH], a, m_h[lb][wr][0], m_h[lb][wr][1], m_h[l][rd][0], m_h[l][rd][1],
+                                       m_w[l][0], m_w[l][1]));
     }
   }
   const int top = p.nl - 1, fin = (p.L - 1) & 1;
