@@ -33,22 +33,32 @@ constexpr int NCOL = 4 * UB;         // gate columns per CTA (accumulator width 
 constexpr int KC = GB_LSTM_KC;
 static_assert(KC == 64 || KC == 32, "chunk = one 128- or 64-byte swizzle row");
 constexpr int ROW_BYTES = KC * 2;
-constexpr int STAGES = KC == 64 ? 2 : 4;
-constexpr int A_BOX = TILE * ROW_BYTES;    // bytes: 128 rows x KC FP16
-constexpr int B_BOX = NCOL * ROW_BYTES;    // bytes: 256 rows x KC FP16
-constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_BOX;
 #ifndef GB_LSTM_PAIR
-#define GB_LSTM_PAIR 1
+#define GB_LSTM_PAIR 2
 #endif
-// CTA pair (thread-block cluster of 2): the two CTAs work on neighbouring window tiles of the SAME job and unit block, so they need
-// the same weight box; each fetches half of it (128 of the 256 gate rows) and TMA multicasts the half into both CTAs' stages.  The wide
-// layers are bound by the L2 -> SM operand stream (64 KB of weights + 32 KB of state per 64 values of K and CTA); the pair reads the
-// weights from L2 once instead of twice.
-constexpr int PAIR = GB_LSTM_PAIR ? 2 : 1;
+// How the two CTAs of a thread-block cluster of 2 (neighbouring window tiles of the SAME job and unit block, hence the same weights)
+// cooperate.  The wide layers are bound by the operand stream: with a 96 KB stage only two stages fit, so the TMA of chunk c+2 cannot
+// start before the MMAs of chunk c have finished, and a 96 KB load (latency + transfer ~2.5 k cycles) is longer than the 1.6 k cycles
+// of MMAs of one chunk (ncu: tensor pipe 57-64 % on those layers).
+//   0  no pairing (one CTA = one tile, cta_group::1)
+//   1  each CTA fetches half of the weight box and TMA multicasts it into both CTAs' stages (L2 reads of the weights halved; the stage
+//      stays 96 KB and the ring two deep: +3.5 %)
+//   2  tcgen05 pair MMA (cta_group::2, M = 256): each CTA keeps only ITS half of the weight box (128 of the 256 gate rows) and its own
+//      128 windows of the state; the leader CTA issues the MMAs for both, the accumulator of a CTA's windows lands in its own TMEM.
+//      A stage is 64 KB and the ring three deep.
+constexpr int PAIR_MODE = GB_LSTM_PAIR;
+constexpr int PAIR = PAIR_MODE ? 2 : 1;
+constexpr bool TWO_SM = PAIR_MODE == 2;
 constexpr int B_PART_ROWS = NCOL / PAIR;          // gate rows of the weight box one CTA fetches
 constexpr int B_PART = B_PART_ROWS * ROW_BYTES;   // bytes
+constexpr int A_BOX = TILE * ROW_BYTES;           // bytes: 128 rows x KC FP16
+constexpr int B_BOX = NCOL * ROW_BYTES;           // bytes: 256 rows x KC FP16
+constexpr int B_STAGE = TWO_SM ? B_PART : B_BOX;  // bytes of one weight image (hi or lo) a CTA's stage holds
+constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_STAGE;
+constexpr int STAGES = (KC == 64 ? 2 : 4) * (TWO_SM ? 3 : 2) / 2;
 constexpr int EPI_WARPS = 16;        // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which UH of the 64 units
-constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread
+constexpr int EPI_GROUP = EPI_WARPS / 2 * 32;  // threads of one epilogue group (one accumulator each)
+constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread and pass (a thread covers 2 * UH units of its item in two passes)
 constexpr int SL = 4;                // units per software-pipeline slice (registers: 576 threads leave 112 each)
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;  // + warp 8: TMA producer, warp 9: MMA issuer
 
@@ -62,6 +72,8 @@ struct TcLayerArgs {
   long xk_rows;
   float* c;                          // [rows][u]
   __half *h_out_hi, *h_out_lo;       // [rows][u]
+  long long* trace;                  // debug (gb_debug_set_lstm_trace): timeline of CTA 0, three recorder threads; NULL in production
+  int trace_cap;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,6 +129,28 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t adesc, uint64_t 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// pair MMA (issued by the leader CTA of the pair only): M = 256 -- rows 0..127 are the leader's A tile, rows 128..255 the partner's (same
+// shared-memory offset in its CTA); the N = 256 columns of B are split, 128 from each CTA's stage; D rows land in the owning CTA's TMEM
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster.  What these arrivals order lives in tensor memory or is written by
+// the async proxy (TMA), ordered by tcgen05.fence / the barrier's own completion; a cluster-scope acquire on the waiting side makes ptxas
+// invalidate L1 (CCTL.IVALL, 13 % of the stall samples of the epilogue when it was tried), so the waits stay at the default scope.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 // one arrival on the barrier at this offset in every CTA of the cluster named by mask, when the MMAs issued so far have completed
 __device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
@@ -131,8 +165,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(KC == 64 ? 2 : 4) << 61;      // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
-__device__ __forceinline__ uint32_t make_idesc_f16(int n) {  // D fp32, A/B FP16, both K-major, M = 128
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {  // D fp32, A/B FP16, both K-major
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -148,28 +182,48 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
   if (N == 8) tmem_ld8(taddr, v); else tmem_ld4(taddr, v);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// sigmoid / tanh through ex2.approx + rcp.approx (~2e-7 absolute error, exact limits): the epilogue evaluates five of them per
-// (window, unit) and is otherwise the longest phase of a CTA
+// sigmoid through ex2.approx + rcp.approx (~2e-7 absolute error, exact limits); used by the cells whose activation is not tanh
 __device__ __forceinline__ float sigm(float z) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return r;
 }
-__device__ __forceinline__ float fast_tanh(float z) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(2.8853900817779268f * z));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-  return fmaf(-2.0f, r, 1.0f);
+// The tanh cell (every factory default) with the quotients merged: the epilogue is bound by the MUFU pipe (16 results per clock and SM;
+// trace: 6.6 k cycles of gate arithmetic per item against a floor of 5.1 k for ten MUFU per cell), so
+//   c' = f*c + i*g = [c*(1+ei)*(1+eg) + (eg-1)*(1+ef)] / [(1+ef)*(1+ei)*(1+eg)],   h = o*tanh(c') = (ec-1) / [(1+eo)*(1+ec)]
+// with ei = e^-zi, ef = e^-zf, eo = e^-zo, eg = e^2zg, ec = e^2c' costs five ex2 and two rcp instead of five and five.  The
+// exponentials are capped at 2^30 (sigmoid <= 1e-9 / tanh = 1 to fp32 there) so that the products stay finite; min.NaN keeps a NaN a NaN.
+__device__ __forceinline__ float ex2_capped(float t) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("min.NaN.ftz.f32 %0, %0, 0f4E800000;" : "+f"(e));  // 2^30
+  return e;
 }
-// TANH (every factory default): straight-line ex2/rcp code; otherwise the generic activation switch (libdevice calls)
-template <bool TANH>
-__device__ __forceinline__ float cell_act(int act, float z) { return TANH ? fast_tanh(z) : gb::apply_act(act, z); }
+__device__ __forceinline__ void tanh_cell(float zi, float zf, float zg, float zo, float c_prev, float& c_new, float& h) {
+  const float pi = 1.0f + ex2_capped(-1.4426950408889634f * zi), pf = 1.0f + ex2_capped(-1.4426950408889634f * zf);
+  const float eg = ex2_capped(2.8853900817779268f * zg), po = 1.0f + ex2_capped(-1.4426950408889634f * zo);
+  const float pig = pi * (eg + 1.0f);
+  float r1, r2;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(pig * pf));
+  c_new = fmaf(c_prev, pig, (eg - 1.0f) * pf) * r1;
+  const float ec = ex2_capped(2.8853900817779268f * c_new);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r2) : "f"(po * (ec + 1.0f)));
+  h = (ec - 1.0f) * r2;
+}
 // one lane of a converged warp (lets ptxas emit the tcgen05 / TMA issue as straight-line uniform code, see ffae_infer_tc.cu)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
+}
+
+// debug timeline: role r (0 producer, 1 MMA issuer, 2 epilogue thread 0) of CTA 0 appends (clock << 20 | item ordinal << 8 | chunk << 4 | code)
+// to its region of the buffer [3 counts][3][cap]
+__device__ __forceinline__ void trace_ev(const TcLayerArgs& a, int role, int& cnt, int code, int n, int c) {
+  if (a.trace == nullptr || blockIdx.x != 0 || cnt >= a.trace_cap) return;
+  a.trace[3 + (long)role * a.trace_cap + cnt] = (long long)(((unsigned long long)clock64() << 20) | ((unsigned long long)(n & 0xfff) << 8) | ((c & 0xf) << 4) | (code & 0xf));
+  a.trace[role] = ++cnt;
 }
 
 // ------------------------------------------------------------------------------------------------ one (layer, timestep) for all windows
@@ -185,27 +239,33 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
                     const __grid_constant__ CUtensorMap m_w_hi, const __grid_constant__ CUtensorMap m_w_lo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) unsigned long long s_bar[2 * STAGES + 4];
-  __shared__ __align__(16) float s_bias[2][NCOL];
+  __shared__ __align__(8) unsigned long long s_bar[3 * STAGES + 4];
+  __shared__ __align__(16) float s_bias[2][2][NCOL];  // [epilogue group][double buffer]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[STAGES]), bar_done = smem_u32(&s_bar[2 * STAGES]),
-                 bar_free = smem_u32(&s_bar[2 * STAGES + 2]);
+                 bar_free = smem_u32(&s_bar[2 * STAGES + 2]), bar_peer = smem_u32(&s_bar[2 * STAGES + 4]);  // bar_peer: the partner's stage s has landed (leader only)
   const int u = a.u;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, PAIR);  // one tcgen05.commit per CTA of the pair: a stage is written by both CTAs' TMA
+      mbar_init(bar_empty + 8 * s, PAIR_MODE == 1 ? 2 : 1);  // multicast mode: one tcgen05.commit per CTA of the pair, a stage is written by both CTAs' TMA
+      mbar_init(bar_peer + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_done + 8 * b, 1);
-      mbar_init(bar_free + 8 * b, EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(bar_free + 8 * b, TWO_SM ? EPI_WARPS : EPI_WARPS / 2);  // one arrival per warp of the group that drains it (pair MMA: of both CTAs, on the leader's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * NCOL) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO_SM) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * NCOL) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * NCOL) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -222,204 +282,294 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
   // group holds windows (every CTA of the pair runs the item's pipeline then -- the partner needs this CTA's half of the weights and
   // its release of the stages); `mine`: this CTA's own tile holds windows (otherwise it computes on the group's first tile and
   // writes nothing).
-  auto item_info = [&](int item, int& tile, int& ub, gb_job& job, int& tj, bool& mine) -> bool {
-    const int grp = item / nub;
-    ub = item - grp * nub;
-    const int job_id = grp / a.pairs_per_job;
-    const int tj0 = (grp - job_id * a.pairs_per_job) * PAIR;
-    job = a.jobs[job_id];
-    tj = tj0 + rank;
-    mine = tj < a.tiles_per_job && tj * TILE < job.n_rows;
-    if (!mine) tj = tj0;
-    tile = job_id * a.tiles_per_job + tj;
-    return tj0 * TILE < job.n_rows;
-  };
   // The job record of an item is a global load (L2 latency) that every role needs before it can do anything for the item: each
-  // role fetches the record of its NEXT item while it works on the current one (ncu: the exposed load was ~20 % of the stall
-  // samples of the narrow layers).
-  struct Item { int tile, ub, tj; gb_job job; bool real, mine; };
-  auto fetch_item = [&](int item) -> Item {
-    Item it{};
-    if (item < a.n_items) it.real = item_info(item, it.tile, it.ub, it.job, it.tj, it.mine);
+  // role requests the record of its NEXT item while it works on the current one and looks at it only when that item's turn comes
+  // (ncu: the exposed load was ~20 % of the stall samples of the narrow layers).
+  struct Item {
+    int item;                  // work item index (< 0: past the end); the rest of the coordinates are recomputed from it by resolve()
+    int slot, n_rows;          // the job record as loaded (the part this kernel uses)
+    long x_row;
+    int tile, ub, tj;          // filled in by resolve()
+    bool real, mine;
+    struct { int slot, n_rows; long x_row; } job;
+  };
+  auto fetch_item = [&](int item) -> Item {  // index arithmetic + the load; nothing here waits for the record
+    Item it;
+    it.item = -1;
+    it.slot = it.n_rows = 0;
+    it.x_row = 0;
+    if (item < a.n_items) {
+      const gb_job* jp = a.jobs + (item / nub) / a.pairs_per_job;
+      it.item = item;
+      const int2 sn = __ldg(reinterpret_cast<const int2*>(jp));  // slot, n_rows
+      it.slot = sn.x; it.n_rows = sn.y;
+      it.x_row = FIRST ? (long)__ldg(reinterpret_cast<const long long*>(&jp->x_row)) : 0;
+    }
     return it;
+  };
+  auto resolve = [&](Item& it) {
+    it.real = it.mine = false;
+    if (it.item < 0) return;
+    const int grp = it.item / nub;
+    it.ub = it.item - grp * nub;
+    const int job_id = grp / a.pairs_per_job, tj0 = (grp - job_id * a.pairs_per_job) * PAIR;
+    it.job.slot = it.slot; it.job.n_rows = it.n_rows; it.job.x_row = it.x_row;
+    it.tj = tj0 + rank;
+    it.mine = it.tj < a.tiles_per_job && it.tj * TILE < it.n_rows;
+    if (!it.mine) it.tj = tj0;
+    it.tile = job_id * a.tiles_per_job + it.tj;
+    it.real = tj0 * TILE < it.n_rows;
   };
 
   if (warp == EPI_WARPS) {
     // ============================== TMA producer
     if (elect_one()) {
       int cc = 0;  // chunks issued so far (ring position)
+      int tr = 0, tn = 0;
       Item nxt = fetch_item(first_item);
       for (int item = first_item; item < a.n_items; item += item_step) {
-        const Item cur = nxt;
+        Item cur = nxt;
+        resolve(cur);
         nxt = fetch_item(item + item_step);
         if (!cur.real) continue;
         const int tile = cur.tile, ub = cur.ub;
-        const gb_job job = cur.job;
-        const int row0 = tile * TILE, wrow0 = job.slot * 4 * u + ub * NCOL;
+        const int row0 = tile * TILE, wrow0 = cur.slot * 4 * u + ub * NCOL;
         for (int c = 0; c < n_chunks; ++c, ++cc) {
           const int s = cc % STAGES, round = cc / STAGES;
           if (round > 0) mbar_wait(bar_empty + 8 * s, (round - 1) & 1);
+          trace_ev(a, 0, tr, 1, tn, c);
           const uint32_t st = sbase + s * STAGE_BYTES;
           mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
           const bool below = c < a.kc_below;
           const int acol = (below ? c : c - a.kc_below) * KC;
           tma_load_2d(st, below ? &m_below_hi : &m_own_hi, acol, row0, bar_full + 8 * s);
           tma_load_2d(st + A_BOX, below ? &m_below_lo : &m_own_lo, acol, row0, bar_full + 8 * s);
-          if (PAIR > 1) {  // this CTA's part of the weight box, into both CTAs
-            const uint16_t both = (uint16_t)((1u << PAIR) - 1u);
-            tma_load_2d_mc(st + 2 * A_BOX + rank * B_PART, &m_w_hi, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s, both);
-            tma_load_2d_mc(st + 2 * A_BOX + B_BOX + rank * B_PART, &m_w_lo, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s, both);
+          if (TWO_SM) {  // this CTA's half of the weight box, into its own stage: the pair MMA reads 128 gate rows from each CTA
+            tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s);
+            tma_load_2d(st + 2 * A_BOX + B_STAGE, &m_w_lo, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s);
+          } else if (PAIR_MODE == 1) {  // this CTA's half of the weight box, into both CTAs
+            tma_load_2d_mc(st + 2 * A_BOX + rank * B_PART, &m_w_hi, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s, (uint16_t)3);
+            tma_load_2d_mc(st + 2 * A_BOX + B_BOX + rank * B_PART, &m_w_lo, c * KC, wrow0 + rank * B_PART_ROWS, bar_full + 8 * s, (uint16_t)3);
           } else {
             tma_load_2d(st + 2 * A_BOX, &m_w_hi, c * KC, wrow0, bar_full + 8 * s);
             tma_load_2d(st + 2 * A_BOX + B_BOX, &m_w_lo, c * KC, wrow0, bar_full + 8 * s);
           }
+          trace_ev(a, 0, tr, 2, tn, c);
         }
+        ++tn;
       }
     }
   } else if (warp == EPI_WARPS + 1) {
-    // ============================== MMA issuer
-    const uint32_t idesc = make_idesc_f16(NCOL);
+    // ============================== MMA issuer (pair MMA: the leader CTA issues for both; the partner's warp reports its stages)
+    const uint32_t idesc = make_idesc_f16(TWO_SM ? 2 * TILE : TILE, NCOL);
     int cc = 0, n = 0;  // chunks consumed, items started
+    int tr = 0;
     Item nxt = fetch_item(first_item);
     for (int item = first_item; item < a.n_items; item += item_step) {
-      const Item cur = nxt;
+      Item cur = nxt;
+      resolve(cur);
       nxt = fetch_item(item + item_step);
       if (!cur.real) continue;
       const int buf = n & 1;
-      if (n >= 2) mbar_wait(bar_free + 8 * buf, ((n >> 1) - 1) & 1);  // the epilogue has drained this accumulator
+      if (TWO_SM && rank != 0) {
+        // partner of the pair: when a stage of ours has landed, tell the leader (its MMAs read our shared memory)
+        for (int c = 0; c < n_chunks; ++c, ++cc) {
+          const int s = cc % STAGES, round = cc / STAGES;
+          mbar_wait(bar_full + 8 * s, round & 1);
+          if (elect_one()) mbar_arrive_remote(bar_peer + 8 * s, 0);
+          __syncwarp();
+        }
+        ++n;
+        continue;
+      }
+      if (n >= 2) mbar_wait(bar_free + 8 * buf, ((n >> 1) - 1) & 1);  // the epilogue has drained this accumulator (pair MMA: in both CTAs)
       tc_fence_after();
+      if (lane == 0) trace_ev(a, 1, tr, 3, n, 0);
       const uint32_t dcol = tmem + buf * NCOL;
       for (int c = 0; c < n_chunks; ++c, ++cc) {
         const int s = cc % STAGES, round = cc / STAGES;
         mbar_wait(bar_full + 8 * s, round & 1);
+        if (TWO_SM) mbar_wait(bar_peer + 8 * s, round & 1);
         tc_fence_after();
+        if (lane == 0) trace_ev(a, 1, tr, 4, n, c);
         if (elect_one()) {
           const uint32_t st = sbase + s * STAGE_BYTES;
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_BOX);
-          const uint64_t b_hi = make_desc_sw128(st + 2 * A_BOX), b_lo = make_desc_sw128(st + 2 * A_BOX + B_BOX);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * A_BOX), b_lo = make_desc_sw128(st + 2 * A_BOX + B_STAGE);
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K step, in 16-byte units of the address field
-            mma_f16_ss(dcol, a_lo + adv, b_hi + adv, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-            mma_f16_ss(dcol, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_f16_ss(dcol, a_hi + adv, b_hi + adv, idesc, 1u);
+            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+            if (TWO_SM) {
+              mma_f16_ss_2sm(dcol, a_lo + adv, b_hi + adv, idesc, acc);
+              mma_f16_ss_2sm(dcol, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma_f16_ss_2sm(dcol, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              mma_f16_ss(dcol, a_lo + adv, b_hi + adv, idesc, acc);
+              mma_f16_ss(dcol, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma_f16_ss(dcol, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
           }
-          if (PAIR > 1) mma_commit_mc(bar_empty + 8 * s, (uint16_t)((1u << PAIR) - 1u)); else mma_commit(bar_empty + 8 * s);
-          if (c + 1 == n_chunks) mma_commit(bar_done + 8 * buf);
+          if (TWO_SM) {  // the stage is free, and at the end of the item the accumulator ready, in BOTH CTAs
+            mma_commit_2sm(bar_empty + 8 * s, (uint16_t)3);
+            if (c + 1 == n_chunks) mma_commit_2sm(bar_done + 8 * buf, (uint16_t)3);
+          } else {
+            if (PAIR_MODE == 1) mma_commit_mc(bar_empty + 8 * s, (uint16_t)3); else mma_commit(bar_empty + 8 * s);
+            if (c + 1 == n_chunks) mma_commit(bar_done + 8 * buf);
+          }
         }
         __syncwarp();
+        if (lane == 0) trace_ev(a, 1, tr, 5, n, c);
       }
       ++n;
     }
   } else {
-    // ============================== epilogue: gates, cell, h (one thread = one window)
-    // Everything that does not depend on the accumulator is requested while the MMAs run (c_{t-1} of all 64 units, the
-    // first input-projection slice), and inside the loop the next slice's TMEM / global loads are in flight while the
-    // current one is evaluated: per-thread row accesses have no coalescing to hide their latency behind.
-    int n = 0;
-    bool bias_staged = false;  // the previous item already put this item's bias into s_bias[buf]
-    Item nxt = fetch_item(first_item);
+    // ============================== epilogue: gates, cell, h (one thread = one window x 32 units, in two passes of UH)
+    // Two groups of eight warps, group g drains accumulator g (items with an odd / even ordinal), so the groups run half an item
+    // apart: while one evaluates gates (MUFU bound) the other is in its requests / stores / waits.  With all sixteen warps on the same
+    // item the phases of an item ran one after the other (trace: 1.4 k prologue + 6.6 k gates + 2.5 k stores per 11.4 k item period).
+    // Everything that does not depend on the accumulator is requested while the MMAs run (c_{t-1}, the first input-projection
+    // slice), and inside the loop the next slice's TMEM / global loads are in flight while the current one is evaluated.
+    const int grp = warp >> 3, wg = warp & 7, tg = tid & (EPI_GROUP - 1);
+    const int r = tid & (TILE - 1), uhalf = wg >> 2;  // window row 0..127; which half of the 64 units this warp evaluates
+    int n = 0, m = 0, tr = 0;                          // items seen (real ones), items of this group done
+    bool bias_staged = false;  // the previous item of this group already put this item's bias into its buffer
+    Item q0 = fetch_item(first_item), q1 = fetch_item(first_item + item_step);  // two records ahead: a skipped item costs no load latency
     for (int item = first_item; item < a.n_items; item += item_step) {
-      const Item cur_item = nxt;
-      nxt = fetch_item(item + item_step);
+      Item cur_item = q0;
+      resolve(cur_item);
+      q0 = q1;
+      q1 = fetch_item(item + 2 * item_step);
       if (!cur_item.real) continue;
+      if ((n & 1) != grp) { ++n; continue; }
       const int tile = cur_item.tile, ub = cur_item.ub, tj = cur_item.tj;
-      const gb_job job = cur_item.job;
-      const int buf = n & 1;
-      const int r = tid & (TILE - 1), uh = warp >> 2;      // window row 0..127; which UH of the 64 units this warp evaluates
+      const auto job = cur_item.job;
+      const int buf = grp;
+      if (tid == 0) trace_ev(a, 2, tr, 6, n, 0);
       const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
       const long row = (long)tile * TILE + r;
-      const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + uh * UH;
-      const float* xk = nullptr;
-      float* sb = s_bias[buf];
-      if (FIRST) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
-        const long xr = min(job.x_row + min(w, job.n_rows - 1) + a.t, a.xk_rows - 1);
-        xk = a.xk + ((xr >> 7) * (long)(4 * u) + ub * NCOL + uh * UH) * TILE + (xr & (TILE - 1));
-      }
+      float* sbuf = s_bias[grp][m & 1];
       float bias_next = 0.f;
       if (!FIRST) {
-        // this buffer's previous user (item n-2) finished reading it before the epilogue-wide barrier of item n-1
-        if (!bias_staged && tid < NCOL) sb[tid] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + tid);
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        // the other buffer is free now (its readers, item n-1, are past the barrier): request the NEXT item's bias, store it when this
-        // item's arithmetic is done -- the load's latency is no longer in front of an item
-        bias_staged = nxt.real;
-        if (nxt.real && tid < NCOL) bias_next = __ldg(a.bias + (long)nxt.job.slot * 4 * u + nxt.ub * NCOL + tid);
+        // this buffer's previous readers (this group's item m-2) finished before the group barrier of item m-1
+        if (!bias_staged) sbuf[tg] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + tg);
+        if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUP) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(EPI_GROUP) : "memory");
+        // request the bias of this group's NEXT item (two items ahead) now, store it when this item's arithmetic is done.  Only when
+        // both following items hold windows (otherwise the next item of the group is not known yet: it loads its bias itself).
+        Item p0 = q0, p1 = q1;
+        resolve(p0);
+        resolve(p1);
+        bias_staged = p0.real && p1.real;
+        if (bias_staged)  // volatile: ptxas would otherwise sink the load to its use at the end of the item (trace: 1.8 k cycles there)
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(bias_next) : "l"(a.bias + (long)p1.job.slot * 4 * u + p1.ub * NCOL + tg));
       }
-      // c is stored tile-blocked, [tile][unit][128 windows]: consecutive threads (windows) touch consecutive floats and an item's
-      // slice is one contiguous 32 KB block (a row-major layout costs a 32-byte sector per thread and access)
-      float* ccol = a.c + ((long)tile * u + ub * UB + uh * UH) * TILE + r;  // unit j of this window: ccol[j * TILE]
-      __half* hh = a.h_out_hi + row * u + ub * UB + uh * UH;
-      __half* hl = a.h_out_lo + row * u + ub * UB + uh * UH;
-      sb += uh * UH;
-      float cp[UH];
+      bool waited = false;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int unit0 = uhalf * (2 * UH) + pass * UH;  // first of the UH units of this pass
+        const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + unit0;
+        const float* xk = nullptr;
+        if (FIRST) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
+          const long xr = min(job.x_row + min(w, job.n_rows - 1) + a.t, a.xk_rows - 1);
+          xk = a.xk + ((xr >> 7) * (long)(4 * u) + ub * NCOL + unit0) * TILE + (xr & (TILE - 1));
+        }
+        // c is stored tile-blocked, [tile][unit][128 windows]: consecutive threads (windows) touch consecutive floats and an item's
+        // slice is one contiguous 32 KB block (a row-major layout costs a 32-byte sector per thread and access)
+        float* ccol = a.c + ((long)tile * u + ub * UB + unit0) * TILE + r;  // unit j of this window: ccol[j * TILE]
+        __half* hh = a.h_out_hi + row * u + ub * UB + unit0;
+        __half* hl = a.h_out_lo + row * u + ub * UB + unit0;
+        const float* sb = sbuf + unit0;
+        float cp[UH];
 #pragma unroll
-      for (int i = 0; i < UH; ++i) cp[i] = a.t == 0 ? 0.f : ccol[i * TILE];
-      float ad[2][4][SL];  // [buffer][gate][unit]: the additive term (bias, or layer 0's input projection incl. bias)
-      auto load_add = [&](int b2, int j0) {
+        for (int i = 0; i < UH; ++i) cp[i] = a.t == 0 ? 0.f : ccol[i * TILE];
+        if (pass == 0 && a.t != 0) {  // the second pass's state: into L2/L1 now, its loads then hit
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+          for (int i = 0; i < UH; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ccol + (UH + i) * TILE));
+        }
+        float ad[2][4][SL];  // [buffer][gate][unit]: the additive term (bias, or layer 0's input projection incl. bias)
+        auto load_add = [&](int b2, int j0) {
 #pragma unroll
-          for (int i = 0; i < SL; ++i) ad[b2][g][i] = FIRST ? __ldg(xk + (g * UB + j0 + i) * TILE) : sb[g * UB + j0 + i];
-      };
-      load_add(0, 0);
-      mbar_wait(bar_done + 8 * buf, (n >> 1) & 1);
-      tc_fence_after();
-      float z[2][4][SL];
-      uint32_t hp1[UH / 2], hp2[UH / 2];
+          for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB, z[0][g]);
+            for (int i = 0; i < SL; ++i) ad[b2][g][i] = FIRST ? __ldg(xk + (g * UB + j0 + i) * TILE) : sb[g * UB + j0 + i];
+        };
+        load_add(0, 0);
+        if (!waited) {
+          if (tid == 0) trace_ev(a, 2, tr, 7, n, 0);
+          mbar_wait(bar_done + 8 * buf, m & 1);
+          tc_fence_after();
+          if (tid == 0) trace_ev(a, 2, tr, 8, n, 0);
+          waited = true;
+        }
+        float z[2][4][SL];
+        uint32_t hp1[UH / 2], hp2[UH / 2];
 #pragma unroll
-      for (int it = 0; it < UH / SL; ++it) {
-        const int j0 = it * SL, cur = it & 1;
-        tmem_wait_ld();
-        if (it + 1 < UH / SL) {
+        for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB, z[0][g]);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB + j0 + SL, z[cur ^ 1][g]);
-          load_add(cur ^ 1, j0 + SL);
-        } else {
-          tc_fence_before();  // last slice of the accumulator is in registers: hand the buffer back to the MMA warp
-          __syncwarp();
-          if (lane == 0) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * buf) : "memory");
+        for (int it = 0; it < UH / SL; ++it) {
+          const int j0 = it * SL, cur = it & 1;
+          tmem_wait_ld();
+          if (it + 1 < UH / SL) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB + j0 + SL, z[cur ^ 1][g]);
+            load_add(cur ^ 1, j0 + SL);
+          } else if (pass == 1) {
+            tc_fence_before();  // last slice of the accumulator is in registers: hand the buffer back to the MMA warp
+            __syncwarp();
+            if (lane == 0) {
+              if (TWO_SM && rank != 0) mbar_arrive_remote(bar_free + 8 * buf, 0);  // the leader issues the next MMAs into both CTAs' accumulators
+              else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * buf) : "memory");
+            }
+          }
+          float cn[SL], hv[SL];
+#pragma unroll
+          for (int i = 0; i < SL; ++i) {
+            if (TANH) {
+              tanh_cell(z[cur][0][i] + ad[cur][0][i], z[cur][1][i] + ad[cur][1][i], z[cur][2][i] + ad[cur][2][i], z[cur][3][i] + ad[cur][3][i],
+                        cp[j0 + i], cn[i], hv[i]);
+            } else {
+              const float ig = sigm(z[cur][0][i] + ad[cur][0][i]), fg = sigm(z[cur][1][i] + ad[cur][1][i]);
+              const float gg = gb::apply_act(a.act, z[cur][2][i] + ad[cur][2][i]), og = sigm(z[cur][3][i] + ad[cur][3][i]);
+              cn[i] = fmaf(fg, cp[j0 + i], ig * gg);
+              hv[i] = og * gb::apply_act(a.act, cn[i]);
+            }
+          }
+          if (cur_item.mine) {
+#pragma unroll
+            for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
+          }
+#pragma unroll
+          for (int i = 0; i < SL / 2; ++i) {  // FP16 pair h = h1 + h2, packed in registers: a pass's UH units are one full 32-byte sector per image
+            const __half2 p1 = __floats2half2_rn(hv[2 * i], hv[2 * i + 1]);  // low half = even unit
+            const float2 f1 = __half22float2(p1);
+            const __half2 p2 = __floats2half2_rn(hv[2 * i] - f1.x, hv[2 * i + 1] - f1.y);
+            hp1[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p1);
+            hp2[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p2);
           }
         }
-        float cn[SL], hv[SL];
+        if (cur_item.mine) {  // a CTA without a tile of its own ran the item for its partner's sake (weights, stage release) on the group's first tile
 #pragma unroll
-        for (int i = 0; i < SL; ++i) {
-          const float ig = sigm(z[cur][0][i] + ad[cur][0][i]), fg = sigm(z[cur][1][i] + ad[cur][1][i]);
-          const float gg = cell_act<TANH>(a.act, z[cur][2][i] + ad[cur][2][i]), og = sigm(z[cur][3][i] + ad[cur][3][i]);
-          cn[i] = fmaf(fg, cp[j0 + i], ig * gg);
-          hv[i] = og * cell_act<TANH>(a.act, cn[i]);
-        }
-        if (cur_item.mine) {
-#pragma unroll
-          for (int i = 0; i < SL; ++i) ccol[(j0 + i) * TILE] = cn[i];
-        }
-#pragma unroll
-        for (int i = 0; i < SL / 2; ++i) {  // FP16 pair h = h1 + h2, packed in registers: a thread's UH units are one full 32-byte sector per image
-          const __half2 p1 = __floats2half2_rn(hv[2 * i], hv[2 * i + 1]);  // low half = even unit
-          const float2 f1 = __half22float2(p1);
-          const __half2 p2 = __floats2half2_rn(hv[2 * i] - f1.x, hv[2 * i + 1] - f1.y);
-          hp1[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p1);
-          hp2[(j0 >> 1) + i] = *reinterpret_cast<const uint32_t*>(&p2);
+          for (int i = 0; i < UH / 8; ++i) {
+            *reinterpret_cast<uint4*>(hh + 8 * i) = make_uint4(hp1[4 * i], hp1[4 * i + 1], hp1[4 * i + 2], hp1[4 * i + 3]);
+            *reinterpret_cast<uint4*>(hl + 8 * i) = make_uint4(hp2[4 * i], hp2[4 * i + 1], hp2[4 * i + 2], hp2[4 * i + 3]);
+          }
         }
       }
-      if (cur_item.mine) {  // a CTA without a tile of its own ran the item for its partner's sake (weights, stage release) on the group's first tile
-#pragma unroll
-        for (int i = 0; i < UH / 8; ++i) {
-          *reinterpret_cast<uint4*>(hh + 8 * i) = make_uint4(hp1[4 * i], hp1[4 * i + 1], hp1[4 * i + 2], hp1[4 * i + 3]);
-          *reinterpret_cast<uint4*>(hl + 8 * i) = make_uint4(hp2[4 * i], hp2[4 * i + 1], hp2[4 * i + 2], hp2[4 * i + 3]);
-        }
-      }
-      if (!FIRST && bias_staged && tid < NCOL) s_bias[buf ^ 1][tid] = bias_next;
+      if (tid == 0) trace_ev(a, 2, tr, 9, n, 0);
+      if (!FIRST && bias_staged) s_bias[grp][(m & 1) ^ 1][tg] = bias_next;
+      if (tid == 0) trace_ev(a, 2, tr, 10, n, 0);
       ++n;
+      ++m;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (PAIR > 1) cluster_sync_all();  // nothing of the partner's (multicast bytes, barrier arrivals) may still be on its way into this CTA
-  if (warp == EPI_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
+  if (warp == EPI_WARPS + 1) {
+    if (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NCOL) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ preparation kernels (fp32 CUDA cores)
@@ -592,7 +742,19 @@ void make_plan(const gb_lstmnet* net, int n_slots, long rows_pad, long x_rows, P
   p->total = ofs;
 }
 
+long long* g_lstm_trace = nullptr;
+int g_lstm_trace_cap = 0, g_lstm_trace_layer = -1;
+
 }  // namespace
+
+// debug aid (not part of the public header): timeline of CTA 0 of the step kernel of `layer` at the last timestep into a device buffer of
+// 3 + 3 * capacity int64 (zeroed by the caller)
+extern "C" int gb_debug_set_lstm_trace(void* dev_buf, int capacity, int layer) {
+  g_lstm_trace = static_cast<long long*>(dev_buf);
+  g_lstm_trace_cap = capacity;
+  g_lstm_trace_layer = layer;
+  return GB_OK;
+}
 
 extern "C" int gb_lstm_tc_supported(const gb_lstmnet* net) {
   GB_REQUIRE(net != nullptr, GB_E_ARG, "net is NULL");
@@ -671,6 +833,8 @@ extern "C" int gb_lstm_infer_tc(const gb_lstmnet* net, const float* params, int3
       a.c = reinterpret_cast<float*>(ws + p.c[l]);
       a.h_out_hi = reinterpret_cast<__half*>(ws + p.h_hi[l][wr]);
       a.h_out_lo = reinterpret_cast<__half*>(ws + p.h_lo[l][wr]);
+      a.trace = (g_lstm_trace != nullptr && l == g_lstm_trace_layer && t == p.L - 1) ? g_lstm_trace : nullptr;
+      a.trace_cap = g_lstm_trace_cap;
       const int lb = l > 0 ? l - 1 : 0;
       a.pairs_per_job = (tiles_per_job + PAIR - 1) / PAIR;
       a.n_items = n_jobs * a.pairs_per_job * (p.u[l] / UB);
