@@ -26,15 +26,16 @@ for layer in layers:
             ev[(v & 0xf, (v >> 8) & 0xfff, (v >> 4) & 0xf)] = v >> 20
     items = sorted({n for (c, n, k) in ev if c == 6})
     nch = 1 + max(k for (c, n, k) in ev if c == 4)
-    # the recorder thread belongs to epilogue group 0, which takes every other item: its period spans TWO items
-    steady = [n for n in items[2:-1] if (6, n + 2, 0) in ev and (10, n, 0) in ev and (3, n, 0) in ev and (5, n, nch - 1) in ev]
+    # the recorder thread's epilogue group takes every item (layer 0) or every other item (two groups): its period spans `st` items
+    st = 2 if len(items) > 3 and all(n % 2 == 0 for n in items) else 1
+    steady = [n for n in items[3:-1] if (6, n + st, 0) in ev and (10, n, 0) in ev and (3, n, 0) in ev and (5, n, nch - 1) in ev]
     def mean(f):
         vals = [f(n) for n in steady]
         return float(np.mean(vals)) if vals else float('nan')
     print(f"layer {layer}: {len(items)} items on CTA 0, {nch} chunks per item, {len(steady)} in steady state; cycles per item (mean)")
-    print(f"  epilogue group 0 (every other item): period per item {mean(lambda n: (ev[(6, n + 2, 0)] - ev[(6, n, 0)]) / 2):8.0f}; of its own item: prologue (state / bias requests) {mean(lambda n: ev[(7, n, 0)] - ev[(6, n, 0)]):7.0f}"
+    print(f"  epilogue thread 0 ({st} group{'s' if st > 1 else ''}): period per item {mean(lambda n: (ev[(6, n + st, 0)] - ev[(6, n, 0)]) / st):8.0f}; of its own item: prologue (state / bias requests) {mean(lambda n: ev[(7, n, 0)] - ev[(6, n, 0)]):7.0f}"
           f" + wait for the accumulator {mean(lambda n: ev[(8, n, 0)] - ev[(7, n, 0)]):7.0f} + gates/cell {mean(lambda n: ev[(9, n, 0)] - ev[(8, n, 0)]):7.0f}"
-          f" + h stores {mean(lambda n: ev[(10, n, 0)] - ev[(9, n, 0)]):7.0f} + to its next item {mean(lambda n: ev[(6, n + 2, 0)] - ev[(10, n, 0)]):7.0f}")
+          f" + h stores {mean(lambda n: ev[(10, n, 0)] - ev[(9, n, 0)]):7.0f} + to its next item {mean(lambda n: ev[(6, n + st, 0)] - ev[(10, n, 0)]):7.0f}")
     print(f"  MMA issuer: wait for a free accumulator {mean(lambda n: ev[(3, n, 0)] - ev[(5, n - 1, nch - 1)] if (5, n - 1, nch - 1) in ev else 0):7.0f};"
           f" per chunk: wait for the stage {mean(lambda n: np.mean([ev[(4, n, k)] - (ev[(5, n, k - 1)] if k else ev[(3, n, 0)]) for k in range(nch)])):7.0f},"
           f" issue + commit {mean(lambda n: np.mean([ev[(5, n, k)] - ev[(4, n, k)] for k in range(nch)])):6.0f};"
