@@ -7,9 +7,10 @@
 // 335 MFLOP per 144 x 128 window is tensor-core work.  One launch advances EVERY window of EVERY job by one (layer,
 // timestep): a CTA owns a tile of 128 windows x 64 units and computes the four gate pre-activations
 //      z[128, 4 x 64] = [h_below,t | h_own,t-1] (128 x K)  .  [K; U]^T (K x 256)
-// as tcgen05.mma (M=128, N=256, K=16 per instruction) with both operands brought to shared memory by TMA (SWIZZLE_128B
-// K-major boxes, two-stage ring), accumulates in TMEM, and finishes the cell in the epilogue: gates, c_t, h_t, with h_t
-// written straight back as the next launches' A operand.  The recurrent state of all windows lives in HBM (h as an FP16
+// as tcgen05.mma with both operands brought to shared memory by TMA (SWIZZLE_128B K-major boxes), accumulates in TMEM, and
+// finishes the cell in the epilogue: gates, c_t, h_t, with h_t written straight back as the next launches' A operand.  By default
+// two CTAs on neighbouring window tiles form a pair (cluster of 2) and run ONE cta_group::2 MMA (M=256, N=256, K=16 per instruction):
+// each keeps its own 128 windows and half of the weight box, a stage is 64 KB and the ring three deep (GB_LSTM_PAIR below).  The recurrent state of all windows lives in HBM (h as an FP16
 // pair, c in fp32): per timestep that is a few GB of traffic against tens of TFLOP of contraction.
 //
 // Numerics (1e-4 parity): h in (-1, 1) and the weights are split into FP16 pairs (a = a1 + a2, 22 significant bits) and
@@ -28,8 +29,8 @@ constexpr int NCOL = 4 * UB;         // gate columns per CTA (accumulator width 
 #ifndef GB_LSTM_KC
 #define GB_LSTM_KC 64
 #endif
-// K elements per pipeline chunk = one swizzle row of FP16 (64: SWIZZLE_128B, two 96 KB stages; 32: SWIZZLE_64B, four 48 KB stages --
-// the same shared memory, but the TMA producer runs three chunks ahead of the MMAs instead of one)
+// K elements per pipeline chunk = one swizzle row of FP16 (64: SWIZZLE_128B; 32: SWIZZLE_64B, twice as many stages of half the size --
+// the same shared memory, the TMA producer further ahead of the MMAs; measured 2 % slower)
 constexpr int KC = GB_LSTM_KC;
 static_assert(KC == 64 || KC == 32, "chunk = one 128- or 64-byte swizzle row");
 constexpr int ROW_BYTES = KC * 2;
@@ -57,8 +58,7 @@ constexpr int B_STAGE = TWO_SM ? B_PART : B_BOX;  // bytes of one weight image (
 constexpr int STAGE_BYTES = 2 * A_BOX + 2 * B_STAGE;
 constexpr int STAGES = (KC == 64 ? 2 : 4) * (TWO_SM ? 3 : 2) / 2;
 constexpr int EPI_WARPS = 16;        // epilogue: warp % 4 = TMEM lane quadrant (32 windows), warp / 4 = which UH of the 64 units
-constexpr int EPI_GROUP = EPI_WARPS / 2 * 32;  // threads of one epilogue group (one accumulator each)
-constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread and pass (a thread covers 2 * UH units of its item in two passes)
+constexpr int UH = UB / (EPI_WARPS / 4);  // units per epilogue thread and pass (with NG epilogue groups a thread covers NG * UH units of its item in NG passes)
 constexpr int SL = 4;                // units per software-pipeline slice (registers: 576 threads leave 112 each)
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;  // + warp 8: TMA producer, warp 9: MMA issuer
 
@@ -211,6 +211,11 @@ __device__ __forceinline__ void tanh_cell(float zi, float zf, float zg, float zo
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r2) : "f"(po * (ec + 1.0f)));
   h = (ec - 1.0f) * r2;
 }
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {  // 32-byte aligned
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+               "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // one lane of a converged warp (lets ptxas emit the tcgen05 / TMA issue as straight-line uniform code, see ffae_infer_tc.cu)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -237,6 +242,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_below_hi, const __grid_constant__ CUtensorMap m_below_lo,
                     const __grid_constant__ CUtensorMap m_own_hi, const __grid_constant__ CUtensorMap m_own_lo,
                     const __grid_constant__ CUtensorMap m_w_hi, const __grid_constant__ CUtensorMap m_w_lo) {
+  // Epilogue groups: NG groups of 16 / NG warps, group g drains the items whose ordinal is g (mod NG).  Two groups run half an item apart,
+  // so one evaluates gates (MUFU bound) while the other is in its requests / stores / waits -- but a group then holds its accumulator
+  // twice as long, and the MMAs of the item after next wait for it.  Trace, cycles per item (one group / two groups): layer 0 (the input
+  // projection streams from HBM in the gate loop) 10.2 k / 11.5 k; the other layers 10.9 / 9.9 k (K = 384) and 9.0 / 8.4 k (K = 128).
+  constexpr int NG = FIRST ? 1 : 2;
+  constexpr int EPI_GROUP = EPI_WARPS / NG * 32;  // threads of one epilogue group
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) unsigned long long s_bar[3 * STAGES + 4];
@@ -254,7 +265,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_done + 8 * b, 1);
-      mbar_init(bar_free + 8 * b, TWO_SM ? EPI_WARPS : EPI_WARPS / 2);  // one arrival per warp of the group that drains it (pair MMA: of both CTAs, on the leader's barrier)
+      mbar_init(bar_free + 8 * b, (TWO_SM ? 2 : 1) * EPI_WARPS / NG);  // one arrival per warp of the group that drains it (pair MMA: of both CTAs, on the leader's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -424,15 +435,12 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       ++n;
     }
   } else {
-    // ============================== epilogue: gates, cell, h (one thread = one window x 32 units, in two passes of UH)
-    // Two groups of eight warps, group g drains accumulator g (items with an odd / even ordinal), so the groups run half an item
-    // apart: while one evaluates gates (MUFU bound) the other is in its requests / stores / waits.  With all sixteen warps on the same
-    // item the phases of an item ran one after the other (trace: 1.4 k prologue + 6.6 k gates + 2.5 k stores per 11.4 k item period).
+    // ============================== epilogue: gates, cell, h (one thread = one window x NG * UH units, in NG passes of UH)
     // Everything that does not depend on the accumulator is requested while the MMAs run (c_{t-1}, the first input-projection
     // slice), and inside the loop the next slice's TMEM / global loads are in flight while the current one is evaluated.
-    const int grp = warp >> 3, wg = warp & 7, tg = tid & (EPI_GROUP - 1);
-    const int r = tid & (TILE - 1), uhalf = wg >> 2;  // window row 0..127; which half of the 64 units this warp evaluates
-    int n = 0, m = 0, tr = 0;                          // items seen (real ones), items of this group done
+    const int grp = warp / (EPI_WARPS / NG), wg = warp % (EPI_WARPS / NG), tg = tid & (EPI_GROUP - 1);
+    const int r = tid & (TILE - 1), ublk = wg >> 2;  // window row 0..127; which block of NG * UH units this warp evaluates
+    int n = 0, tr = 0;                                 // items seen (real ones)
     bool bias_staged = false;  // the previous item of this group already put this item's bias into its buffer
     Item q0 = fetch_item(first_item), q1 = fetch_item(first_item + item_step);  // two records ahead: a skipped item costs no load latency
     for (int item = first_item; item < a.n_items; item += item_step) {
@@ -441,10 +449,10 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       q0 = q1;
       q1 = fetch_item(item + 2 * item_step);
       if (!cur_item.real) continue;
-      if ((n & 1) != grp) { ++n; continue; }
+      if (NG > 1 && (n % NG) != grp) { ++n; continue; }
       const int tile = cur_item.tile, ub = cur_item.ub, tj = cur_item.tj;
       const auto job = cur_item.job;
-      const int buf = grp;
+      const int buf = n & 1, m = n / NG;                   // accumulator; ordinal of the item inside this group
       if (tid == 0) trace_ev(a, 2, tr, 6, n, 0);
       const int w = tj * TILE + r;                         // window index inside the job (may exceed n_rows in the last tile)
       const long row = (long)tile * TILE + r;
@@ -452,22 +460,25 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
       float bias_next = 0.f;
       if (!FIRST) {
         // this buffer's previous readers (this group's item m-2) finished before the group barrier of item m-1
-        if (!bias_staged) sbuf[tg] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + tg);
+        if (!bias_staged) {
+          for (int i = tg; i < NCOL; i += EPI_GROUP) sbuf[i] = __ldg(a.bias + (long)job.slot * 4 * u + ub * NCOL + i);
+        }
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUP) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(EPI_GROUP) : "memory");
-        // request the bias of this group's NEXT item (two items ahead) now, store it when this item's arithmetic is done.  Only when
-        // both following items hold windows (otherwise the next item of the group is not known yet: it loads its bias itself).
+        // request the bias of this group's NEXT item (NG items ahead) now, store it when this item's arithmetic is done.  Only when
+        // the following NG items all hold windows (otherwise the next item of the group is not known yet: it loads its bias itself).
         Item p0 = q0, p1 = q1;
         resolve(p0);
         resolve(p1);
-        bias_staged = p0.real && p1.real;
-        if (bias_staged)  // volatile: ptxas would otherwise sink the load to its use at the end of the item (trace: 1.8 k cycles there)
-          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(bias_next) : "l"(a.bias + (long)p1.job.slot * 4 * u + p1.ub * NCOL + tg));
+        const Item& pn = NG == 1 ? p0 : p1;
+        bias_staged = p0.real && pn.real && tg < NCOL;
+        if (bias_staged)  // volatile: ptxas would otherwise sink the load to its use at the end of the item
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(bias_next) : "l"(a.bias + (long)pn.job.slot * 4 * u + pn.ub * NCOL + tg));
       }
       bool waited = false;
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const int unit0 = uhalf * (2 * UH) + pass * UH;  // first of the UH units of this pass
+      for (int pass = 0; pass < NG; ++pass) {
+        const int unit0 = ublk * (NG * UH) + pass * UH;  // first of the UH units of this pass
         const uint32_t lane_base = tmem + buf * NCOL + ((uint32_t)((warp & 3) * 32) << 16) + unit0;
         const float* xk = nullptr;
         if (FIRST) {  // xk is stored row-blocked, [row / 128][4u reordered][128]: windows (threads) run along the fastest axis
@@ -483,7 +494,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         float cp[UH];
 #pragma unroll
         for (int i = 0; i < UH; ++i) cp[i] = a.t == 0 ? 0.f : ccol[i * TILE];
-        if (pass == 0 && a.t != 0) {  // the second pass's state: into L2/L1 now, its loads then hit
+        if (NG > 1 && pass == 0 && a.t != 0) {  // the second pass's state: towards L2 now
 #pragma unroll
           for (int i = 0; i < UH; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ccol + (UH + i) * TILE));
         }
@@ -497,7 +508,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
         load_add(0, 0);
         if (!waited) {
           if (tid == 0) trace_ev(a, 2, tr, 7, n, 0);
-          mbar_wait(bar_done + 8 * buf, m & 1);
+          mbar_wait(bar_done + 8 * buf, (n >> 1) & 1);
           tc_fence_after();
           if (tid == 0) trace_ev(a, 2, tr, 8, n, 0);
           waited = true;
@@ -514,7 +525,7 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
 #pragma unroll
             for (int g = 0; g < 4; ++g) tmem_ldn<SL>(lane_base + g * UB + j0 + SL, z[cur ^ 1][g]);
             load_add(cur ^ 1, j0 + SL);
-          } else if (pass == 1) {
+          } else if (pass == NG - 1) {
             tc_fence_before();  // last slice of the accumulator is in registers: hand the buffer back to the MMA warp
             __syncwarp();
             if (lane == 0) {
@@ -549,18 +560,17 @@ lstm_tc_step_kernel(const TcLayerArgs a, const __grid_constant__ CUtensorMap m_b
           }
         }
         if (cur_item.mine) {  // a CTA without a tile of its own ran the item for its partner's sake (weights, stage release) on the group's first tile
-#pragma unroll
-          for (int i = 0; i < UH / 8; ++i) {
-            *reinterpret_cast<uint4*>(hh + 8 * i) = make_uint4(hp1[4 * i], hp1[4 * i + 1], hp1[4 * i + 2], hp1[4 * i + 3]);
-            *reinterpret_cast<uint4*>(hl + 8 * i) = make_uint4(hp2[4 * i], hp2[4 * i + 1], hp2[4 * i + 2], hp2[4 * i + 3]);
-          }
+          // one 256-bit store per image: a pass's UH units are exactly one 32-byte sector of the row (two 128-bit stores cost the LSU two
+          // half-filled sector transactions each; trace: 2.2 k cycles to issue an item's h stores when all warps reach them together)
+          static_assert(UH == 16, "a pass's units = one 32-byte sector of FP16");
+          st_global_256(hh, hp1);
+          st_global_256(hl, hp2);
         }
       }
       if (tid == 0) trace_ev(a, 2, tr, 9, n, 0);
       if (!FIRST && bias_staged) s_bias[grp][(m & 1) ^ 1][tg] = bias_next;
       if (tid == 0) trace_ev(a, 2, tr, 10, n, 0);
       ++n;
-      ++m;
     }
   }
   tc_fence_before();

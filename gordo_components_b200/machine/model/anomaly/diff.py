@@ -17,6 +17,8 @@ from __future__ import annotations
 from datetime import timedelta
 from typing import Dict, Optional, Sequence, Union
 
+import weakref
+
 import numpy as np
 import pandas as pd
 from sklearn.base import BaseEstimator, TransformerMixin
@@ -41,13 +43,30 @@ def _values(a) -> np.ndarray:
     return np.asarray(getattr(a, "values", a))
 
 
+_MULTIPLIERS = weakref.WeakKeyDictionary()  # scaler object -> (fitted-state key, slope): a request does not re-probe a fitted scaler
+
+
 def _scaler_multiplier(scaler, n_features: int) -> np.ndarray:
     """Per-feature slope (float64) of a fitted affine scaler; ValueError if the transform is not affine per feature."""
+    # a refit replaces the fitted arrays, so their identities stand for the fitted state (objects without such attributes are probed every time)
+    state = tuple(id(getattr(scaler, name)) for name in ("scale_", "min_", "mean_", "center_") if getattr(scaler, name, None) is not None)
+    key = (n_features, state)
+    try:
+        hit = _MULTIPLIERS.get(scaler) if state else None
+    except TypeError:  # unhashable / not weak-referenceable scaler object
+        hit = None
+    if hit is not None and hit[0] == key:
+        return hit[1]
     probe = np.vstack([np.zeros(n_features), np.ones(n_features), np.full(n_features, 2.0)])
     t = np.asarray(scaler.transform(probe), dtype=np.float64)
     slope = t[1] - t[0]
     if not np.allclose(t[2] - t[1], slope, rtol=1e-9, atol=1e-12):
         raise ValueError(f"scaler {scaler!r} is not a per-feature affine transform; the fused anomaly kernels cannot use it")
+    if state:
+        try:
+            _MULTIPLIERS[scaler] = (key, slope)
+        except TypeError:
+            pass
     return slope
 
 
