@@ -11,8 +11,10 @@
 // shared memory for the backward pass, the next mini-batch is gathered with cp.async while the current one is
 // processed, and the Adam moments (opaque state, same padded layout) stream through L2.  Machines (and CV folds,
 // which are just more jobs) are independent, so the grid is simply one CTA per job.
-// A mini-batch larger than 32 rows is processed as chunks of 32 (one row per lane): the chunks' weight gradients are summed in
+// A mini-batch larger than 32 rows is processed as chunks of 32: the chunks' weight gradients are summed in
 // an L2-resident scratch image (second half of the opaque Adam-m state) and the optimizer runs with the last chunk.
+// The two products with the batch rows as the outer dimension (a.W and dz.W^T) give a lane four rows and a quarter of the reduction
+// index (4x4 register tile, reduce-scatter over the four quarters); the weight gradient gives a thread a 4x2 block of W.
 #include <cuda_pipeline.h>
 #include "gb_common.cuh"
 
@@ -29,6 +31,7 @@ struct FitArgs {
   int apitch[GB_MAX_LAYERS + 1];  // pitch of activation buffer l (l = 0: x staging)
   int aofs[GB_MAX_LAYERS + 1];    // offset of activation buffer l (l >= 1) in smem floats
   int xofs[2], yofs[2], dofs[3];
+  int d_global;  // how many of the three dz buffers (from the last one) live in the slot's L2-resident state area instead of shared memory
   int ypitch, dpitch;
   int wfloats, smem_floats;
   int n_in, n_out, max_rows;
@@ -83,10 +86,31 @@ __device__ __forceinline__ void adam_update(float& w, float g, float& m, float& 
   w -= __fdividef(alpha * m, sq + eps);
 }
 
+// acc[j][c]: partial sums of rows p + 8 j (j = 0..3) x 4 columns held by lane (p = lane & 7, kq = lane >> 3), to be summed over the four kq.
+// Reduce-scatter in two rounds: the lanes 16 apart split rows {0,1} / {2,3}, then the lanes 8 apart split the remaining pair, so lane
+// (p, kq) ends with the complete sums of row p + 8 kq (12 shuffles instead of 32 for an all-reduce).
+__device__ __forceinline__ void quarter_reduce(const float (&acc)[4][4], int lane, float (&out)[4]) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  float h[2][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const float keep = hi16 ? acc[2 + jj][c] : acc[jj][c], send = hi16 ? acc[jj][c] : acc[2 + jj][c];
+      h[jj][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float keep = hi8 ? h[1][c] : h[0][c], send = hi8 ? h[0][c] : h[1][c];
+    out[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+}
+
 // WG = false: the slot's padded weight image lives in shared memory for the whole fit (every 64-tag stack).  WG = true: the image does
 // not fit beside the activations (e.g. the 128-tag hourglass, 245 KB) and lives in the slot's L2-resident state area instead; the
 // code is the same, the loads become global.
-template <bool WG>
+template <bool WG, bool DG>  // DG: some dz buffers live in global memory too (kept apart so that the usual case addresses them as shared memory)
 __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float s_red[3][NWARPS];
@@ -191,6 +215,12 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   stamp(2 * L + 2);  // set-up
   gather(0, 0, 0, 0);
   float* Gacc = Mg + a.wfloats;  // gradient sums of a multi-chunk mini-batch (same padded layout as the weights)
+  // dz buffer b: shared memory, or -- for stacks whose activations leave no room (256-wide encoders) -- the unused part of the slot's
+  // Adam-v state area (the second and third third of it), which stays in L2
+  auto dz_buf = [&](int b) -> float* {
+    if (!DG) return smem + a.dofs[b];
+    return b < 3 - a.d_global ? smem + a.dofs[b] : Vg + a.wfloats + (long)(b - (3 - a.d_global)) * BR * a.dpitch;
+  };
 
   for (int e = 0; e < a.hp.epochs; ++e) {
     float acc_sq = 0.f, acc_reg = 0.f, acc_hit = 0.f;
@@ -208,10 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
       if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
       __syncthreads();
       stamp(0);
-      if (warp == NWARPS - 1) {  // the warp with the least work in the first layers prepares the next step
-        if (more && advance(ne, ns, nc)) stage_indices(cur, ne, ns, nc);  // read by the gather at the top of the next chunk
-        if (first_chunk && lane == 0) s_alpha[(t_step + 1) & 1] = adam_alpha(t_step + 1);  // read after the loss barrier of step t+1
-      }
+      const bool more2 = more && advance(ne, ns, nc);  // (ne, ns, nc): the chunk after next
 
       // ---- forward ---------------------------------------------------------------------------
       for (int l = 0; l < L; ++l) {
@@ -222,29 +249,50 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
         const float* Wl = sW + a.im.wofs[l];
         const float* bl = sW + a.im.bofs[l];
         const float l1c = a.net.l1[l] * (a.hp.l1_div_batch ? 1.f : (float)nbt);
+        if (l == 0) {  // the last two warps have no tile in the first layer of a 64-tag hourglass (14 tiles): they prepare the next step
+          if (warp == NWARPS - 1 && more2) stage_indices(cur, ne, ns, nc);  // read by the gather at the top of the next chunk
+          if (warp == NWARPS - 2 && first_chunk && lane == 0) s_alpha[(t_step + 1) & 1] = adam_alpha(t_step + 1);  // read after the loss barrier of step t+1
+        }
+        // A warp owns 32 rows x 4 output columns; lane = (row group p, K quarter kq): rows p, p+8, p+16, p+24 against every fourth
+        // block of four k.  Per block a lane loads 4 + 4 float4 for 64 FMA (a row per lane with the whole K needs 1 + 4 for 16: the
+        // shared-memory return path, 128 B/clk, bounded these loops); the four K quarters are summed by a two-round reduce-scatter
+        // over the lanes that leaves lane (p, kq) with row p + 8 kq.
+        const int p8 = lane & 7, kq = lane >> 3, Kb = Kp >> 2;
         for (int task = warp; task < (Np >> 2); task += NWARPS) {
           const int n0 = task << 2;
-          float4 acc = *reinterpret_cast<const float4*>(bl + n0);
-          const float* arow = in + lane * ip;
+          float acc[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+          const float* arow = in + p8 * ip;
           const float* wcol = Wl + n0;
-          for (int k = 0; k < Kp; k += 4) {
-            const float4 av = *reinterpret_cast<const float4*>(arow + k);
-            const float4 w0 = *reinterpret_cast<const float4*>(wcol + (k + 0) * Np);
-            const float4 w1 = *reinterpret_cast<const float4*>(wcol + (k + 1) * Np);
-            const float4 w2 = *reinterpret_cast<const float4*>(wcol + (k + 2) * Np);
-            const float4 w3 = *reinterpret_cast<const float4*>(wcol + (k + 3) * Np);
-            acc.x = fmaf(av.x, w0.x, acc.x); acc.y = fmaf(av.x, w0.y, acc.y); acc.z = fmaf(av.x, w0.z, acc.z); acc.w = fmaf(av.x, w0.w, acc.w);
-            acc.x = fmaf(av.y, w1.x, acc.x); acc.y = fmaf(av.y, w1.y, acc.y); acc.z = fmaf(av.y, w1.z, acc.z); acc.w = fmaf(av.y, w1.w, acc.w);
-            acc.x = fmaf(av.z, w2.x, acc.x); acc.y = fmaf(av.z, w2.y, acc.y); acc.z = fmaf(av.z, w2.z, acc.z); acc.w = fmaf(av.z, w2.w, acc.w);
-            acc.x = fmaf(av.w, w3.x, acc.x); acc.y = fmaf(av.w, w3.y, acc.y); acc.z = fmaf(av.w, w3.z, acc.z); acc.w = fmaf(av.w, w3.w, acc.w);
+          for (int kb = kq; kb < Kb; kb += 4) {
+            const int k = kb << 2;
+            float4 av[4], wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const float4*>(arow + 8 * j * ip + k);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) wv[t] = *reinterpret_cast<const float4*>(wcol + (k + t) * Np);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j][0] = fmaf(av[j].x, wv[0].x, acc[j][0]); acc[j][1] = fmaf(av[j].x, wv[0].y, acc[j][1]); acc[j][2] = fmaf(av[j].x, wv[0].z, acc[j][2]); acc[j][3] = fmaf(av[j].x, wv[0].w, acc[j][3]);
+              acc[j][0] = fmaf(av[j].y, wv[1].x, acc[j][0]); acc[j][1] = fmaf(av[j].y, wv[1].y, acc[j][1]); acc[j][2] = fmaf(av[j].y, wv[1].z, acc[j][2]); acc[j][3] = fmaf(av[j].y, wv[1].w, acc[j][3]);
+              acc[j][0] = fmaf(av[j].z, wv[2].x, acc[j][0]); acc[j][1] = fmaf(av[j].z, wv[2].y, acc[j][1]); acc[j][2] = fmaf(av[j].z, wv[2].z, acc[j][2]); acc[j][3] = fmaf(av[j].z, wv[2].w, acc[j][3]);
+              acc[j][0] = fmaf(av[j].w, wv[3].x, acc[j][0]); acc[j][1] = fmaf(av[j].w, wv[3].y, acc[j][1]); acc[j][2] = fmaf(av[j].w, wv[3].z, acc[j][2]); acc[j][3] = fmaf(av[j].w, wv[3].w, acc[j][3]);
+            }
           }
+          float s4[4];
+          quarter_reduce(acc, lane, s4);
+          const int row = p8 + 8 * kq;
+          const float4 bv = *reinterpret_cast<const float4*>(bl + n0);
           float4 o;
-          o.x = (n0 + 0 < N) ? gb::apply_act(act, acc.x) : 0.f;
-          o.y = (n0 + 1 < N) ? gb::apply_act(act, acc.y) : 0.f;
-          o.z = (n0 + 2 < N) ? gb::apply_act(act, acc.z) : 0.f;
-          o.w = (n0 + 3 < N) ? gb::apply_act(act, acc.w) : 0.f;
-          *reinterpret_cast<float4*>(out + lane * op + n0) = o;
-          if (l1c != 0.f && lane < nb) acc_reg += l1c * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(o.w));
+          o.x = (n0 + 0 < N) ? gb::apply_act(act, s4[0] + bv.x) : 0.f;
+          o.y = (n0 + 1 < N) ? gb::apply_act(act, s4[1] + bv.y) : 0.f;
+          o.z = (n0 + 2 < N) ? gb::apply_act(act, s4[2] + bv.z) : 0.f;
+          o.w = (n0 + 3 < N) ? gb::apply_act(act, s4[3] + bv.w) : 0.f;
+          *reinterpret_cast<float4*>(out + row * op + n0) = o;
+          if (l1c != 0.f && row < nb) acc_reg += l1c * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(o.w));
         }
         __syncthreads();
         stamp(1 + l);
@@ -255,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
         const float* yh = smem + a.aofs[L];
         const int yp = a.apitch[L];
         const float* yt = smem + a.yofs[cur];
-        float* G = smem + a.dofs[0];
+        float* G = dz_buf(0);
         const int NpL = a.im.np[L - 1], actL = a.net.act[L - 1];
         const float cL = a.net.l1[L - 1] / (a.hp.l1_div_batch ? (float)nbt : 1.f);
         const float gscale = 2.f / ((float)nbt * (float)n_out);
@@ -299,41 +347,56 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
       // B(p) reads W_p while C(p+1) writes W_{p+1}; the third buffer keeps dz_{p+1} alive while B(p) writes dz_{p-1}.
       auto input_grad = [&](int l) {  // B(l), l >= 1
         const int Kp = a.im.kp[l], Np = a.im.np[l], K = a.net.dims[l], actp = a.net.act[l - 1];
-        const float* D = smem + a.dofs[(L - 1 - l) % 3];
-        float* Dn = smem + a.dofs[(L - l) % 3];
+        const float* D = dz_buf((L - 1 - l) % 3);
+        float* Dn = dz_buf((L - l) % 3);
         const float* Wl = sW + a.im.wofs[l];
-        const float* aprev = smem + a.aofs[l] + lane * a.apitch[l];  // output of layer l-1
+        const float* aprev = smem + a.aofs[l];  // output of layer l-1
         const float cp = a.net.l1[l - 1] / (a.hp.l1_div_batch ? (float)nbt : 1.f);
-        const bool live = lane < nb;
+        const int p8 = lane & 7, kq = lane >> 3, Nb = Np >> 2;  // lane = (row group, quarter of the n blocks): as in the forward pass
         for (int task = NWARPS - 1 - warp; task < (Kp >> 2); task += NWARPS) {
           const int k0 = task << 2;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float* drow = D + lane * a.dpitch;
-          for (int nn = 0; nn < Np; nn += 4) {
-            const float4 d = *reinterpret_cast<const float4*>(drow + nn);
-            const float4 w0 = *reinterpret_cast<const float4*>(Wl + (k0 + 0) * Np + nn);
-            const float4 w1 = *reinterpret_cast<const float4*>(Wl + (k0 + 1) * Np + nn);
-            const float4 w2 = *reinterpret_cast<const float4*>(Wl + (k0 + 2) * Np + nn);
-            const float4 w3 = *reinterpret_cast<const float4*>(Wl + (k0 + 3) * Np + nn);
-            acc.x = fmaf(d.x, w0.x, acc.x); acc.x = fmaf(d.y, w0.y, acc.x); acc.x = fmaf(d.z, w0.z, acc.x); acc.x = fmaf(d.w, w0.w, acc.x);
-            acc.y = fmaf(d.x, w1.x, acc.y); acc.y = fmaf(d.y, w1.y, acc.y); acc.y = fmaf(d.z, w1.z, acc.y); acc.y = fmaf(d.w, w1.w, acc.y);
-            acc.z = fmaf(d.x, w2.x, acc.z); acc.z = fmaf(d.y, w2.y, acc.z); acc.z = fmaf(d.z, w2.z, acc.z); acc.z = fmaf(d.w, w2.w, acc.z);
-            acc.w = fmaf(d.x, w3.x, acc.w); acc.w = fmaf(d.y, w3.y, acc.w); acc.w = fmaf(d.z, w3.z, acc.w); acc.w = fmaf(d.w, w3.w, acc.w);
+          float acc[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+          const float* drow = D + p8 * a.dpitch;
+          const float* wrow = Wl + k0 * Np;
+          for (int nb4 = kq; nb4 < Nb; nb4 += 4) {
+            const int nn = nb4 << 2;
+            float4 dv[4], wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dv[j] = *reinterpret_cast<const float4*>(drow + 8 * j * a.dpitch + nn);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(wrow + c * Np + nn);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                acc[j][c] = fmaf(dv[j].x, wv[c].x, acc[j][c]);
+                acc[j][c] = fmaf(dv[j].y, wv[c].y, acc[j][c]);
+                acc[j][c] = fmaf(dv[j].z, wv[c].z, acc[j][c]);
+                acc[j][c] = fmaf(dv[j].w, wv[c].w, acc[j][c]);
+              }
           }
-          const float4 ao = *reinterpret_cast<const float4*>(aprev + k0);
+          float s4[4];
+          quarter_reduce(acc, lane, s4);
+          const int row = p8 + 8 * kq;
+          const bool live = row < nb;
+          const float4 ao = *reinterpret_cast<const float4*>(aprev + row * a.apitch[l] + k0);
           auto dz = [&](float g, float o, int j) -> float {
             if (!live || j >= K) return 0.f;
             if (cp != 0.f) g += cp * ((o > 0.f) ? 1.f : ((o < 0.f) ? -1.f : 0.f));
             return g * gb::act_grad_from_output(actp, o);
           };
           float4 o;
-          o.x = dz(acc.x, ao.x, k0 + 0); o.y = dz(acc.y, ao.y, k0 + 1); o.z = dz(acc.z, ao.z, k0 + 2); o.w = dz(acc.w, ao.w, k0 + 3);
-          *reinterpret_cast<float4*>(Dn + lane * a.dpitch + k0) = o;
+          o.x = dz(s4[0], ao.x, k0 + 0); o.y = dz(s4[1], ao.y, k0 + 1); o.z = dz(s4[2], ao.z, k0 + 2); o.w = dz(s4[3], ao.w, k0 + 3);
+          *reinterpret_cast<float4*>(Dn + row * a.dpitch + k0) = o;
         }
       };
       auto weight_step = [&](int l) {  // C(l)
         const int Kp = a.im.kp[l], Np = a.im.np[l];
-        const float* D = smem + a.dofs[(L - 1 - l) % 3];
+        const float* D = dz_buf((L - 1 - l) % 3);
         const float* ain = (l == 0) ? smem + a.xofs[cur] : smem + a.aofs[l];
         const int ip = a.apitch[l];
         float* Wl = sW + a.im.wofs[l];
@@ -501,7 +564,10 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
   a.wfloats = gb::round_up(a.im.total, 4);
   size_t smem = 0;
   bool w_global = false;
-  for (int pass = 0; pass < 2; ++pass) {  // first with the weight image in shared memory; if that does not fit, with the image in L2
+  // first everything in shared memory; if that does not fit, the weight image in L2; then, one by one, the dz buffers in L2 as well
+  for (int pass = 0; pass < 5; ++pass) {
+    w_global = pass >= 1;
+    a.d_global = pass >= 2 ? pass - 1 : 0;
     int ofs = w_global ? 0 : a.wfloats;
     a.apitch[0] = odd_pitch(a.im.kp[0]);
     for (int l = 1; l <= L; ++l) {
@@ -513,23 +579,25 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
     a.ypitch = odd_pitch(gb::round_up(a.n_out, 4));
     for (int b = 0; b < 2; ++b) { a.yofs[b] = ofs; ofs += BR * a.ypitch; }
     a.dpitch = odd_pitch(a.im.max_np);
-    for (int b = 0; b < 3; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
+    for (int b = 0; b < 3 - a.d_global; ++b) { a.dofs[b] = ofs; ofs += BR * a.dpitch; }
     a.smem_floats = ofs;
     smem = (size_t)ofs * sizeof(float);
-    if (smem <= 227 * 1024) break;
-    w_global = true;
+    if (smem <= 227 * 1024 && (long)a.d_global * BR * a.dpitch <= 2L * a.wfloats) break;
   }
-  GB_REQUIRE(smem <= 227 * 1024, GB_E_SMEM, "architecture needs %zu bytes of shared memory for the activations of one mini-batch chunk", smem);
+  GB_REQUIRE(smem <= 227 * 1024 && (long)a.d_global * BR * a.dpitch <= 2L * a.wfloats, GB_E_SMEM,
+             "architecture needs %zu bytes of shared memory for the activations of one mini-batch chunk", smem);
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.jobs = jobs; a.x = x; a.y = y; a.perm = perm;
   a.out_loss = out_loss; a.out_acc = out_acc;
   a.trace = g_fit_trace;
-  if (w_global) {
-    GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ffae_fit_kernel<true><<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
-  } else {
-    GB_CUDA_CHECK(cudaFuncSetAttribute(ffae_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ffae_fit_kernel<false><<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
-  }
+  auto launch = [&](auto kernel) -> int {
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<n_jobs, THREADS, smem, (cudaStream_t)stream>>>(a);
+    return GB_OK;
+  };
+  if (a.d_global > 0) rc = launch(ffae_fit_kernel<true, true>);
+  else if (w_global) rc = launch(ffae_fit_kernel<true, false>);
+  else rc = launch(ffae_fit_kernel<false, false>);
+  if (rc != GB_OK) return rc;
   GB_CUDA_CHECK(cudaGetLastError());
   return GB_OK;
 }
