@@ -538,7 +538,8 @@ def test_lstm_infer_matches_oracle(engine, torch, F, units, lookback):
 @pytest.mark.parametrize("F,units,lookback,rows,scale", [(16, [64, 64], 5, [140, 300], 1.0), (128, [256, 128, 64, 64, 128, 256], 20, [57, 190], 1.0),
                                                           (7, [128], 9, [400], 1000.0), (5, [7, 9, 3], 4, [50, 133], 1.0),
                                                           (128, [107, 85, 64, 64, 85, 107], 12, [150], 1.0),  # widths padded to 64 internally
-                                                          (128, [256, 128, 64, 64, 128, 256], 144, [144 + 39, 144 + 130], 1.0)])  # BASELINE configs[3]: error growth over 144 steps
+                                                          (128, [256, 128, 64, 64, 128, 256], 144, [144 + 39, 144 + 130], 1.0),  # BASELINE configs[3]: error growth over 144 steps
+                                                          (4, [64, 64], 3, [19100, 18950], 1.0)])  # 149 + 148 tiles: every CTA pair walks several items (ring, accumulators, bias buffers wrap)
 def test_lstm_infer_tcgen05_matches_oracle(engine, torch, F, units, lookback, rows, scale):
     """gb_lstm_infer_tc: FP16-pair split operands on the tensor cores, state in HBM, one launch per (layer, timestep).
     Jobs of different lengths (tiles with padding rows), machines sharing the launch, raw inputs of large magnitude (the
