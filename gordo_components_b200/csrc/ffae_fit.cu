@@ -31,6 +31,7 @@ struct FitArgs {
   int apitch[GB_MAX_LAYERS + 1];  // pitch of activation buffer l (l = 0: x staging)
   int aofs[GB_MAX_LAYERS + 1];    // offset of activation buffer l (l >= 1) in smem floats
   int xofs[2], yofs[2], dofs[3];
+  int gather_layer, gather_layer2;  // the two forward layers with the fewest tiles (the same layer twice in a one-layer stack): their idle warps issue the cp.async gather of the next chunk
   int d_global;  // how many of the three dz buffers (from the last one) live in the slot's L2-resident state area instead of shared memory
   int ypitch, dpitch;
   int wfloats, smem_floats;
@@ -165,11 +166,12 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
     if (a.hp.shuffle == 2) return a.perm[((long)job_id * a.hp.epochs + e) * a.max_rows + i];
     return (int)permute_index((uint32_t)i, (uint32_t)n, mix32(key_base + (uint32_t)e * 0x9e3779b9U));
   };
-  auto gather = [&](int buf, int e, int s, int c) {  // chunk c (32 rows) of mini-batch s of epoch e
+  // rows [r_lo, r_hi) of chunk c (32 rows) of mini-batch s of epoch e, by n_warps warps
+  auto gather = [&](int buf, int e, int s, int c, int first_warp, int n_warps, int r_lo = 0, int r_hi = BR) {
     const int nb = min(BR, min(B, n - s * B) - c * BR);
     float* xs = smem + a.xofs[buf];
     float* ys = smem + a.yofs[buf];
-    for (int r = warp; r < nb; r += NWARPS) {
+    for (int r = r_lo + warp - first_warp; r < min(nb, r_hi); r += n_warps) {
       const int src = s_idx[buf][r];
       const float* xr = xbase + (long)src * n_in;
       const float* yr = ybase + (long)src * n_out;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
   }
   __syncthreads();
   stamp(2 * L + 2);  // set-up
-  gather(0, 0, 0, 0);
+  gather(0, 0, 0, 0, 0, NWARPS);
   float* Gacc = Mg + a.wfloats;  // gradient sums of a multi-chunk mini-batch (same padded layout as the weights)
   // dz buffer b: shared memory, or -- for stacks whose activations leave no room (256-wide encoders) -- the unused part of the slot's
   // Adam-v state area (the second and third third of it), which stays in L2
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
       // ---- prefetch the next chunk, then wait for the current one ------------------------
       int ne = e, ns = s, nc = c;
       const bool more = advance(ne, ns, nc);
-      if (more) gather(cur ^ 1, ne, ns, nc);
-      if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+      const int ne1 = ne, ns1 = ns, nc1 = nc;  // the next chunk: gathered below, by the warps without a tile in the narrowest layer
+      __pipeline_wait_prior(0);              // this chunk's rows (requested during the previous chunk) have landed
       __syncthreads();
       stamp(0);
       const bool more2 = more && advance(ne, ns, nc);  // (ne, ns, nc): the chunk after next
@@ -249,6 +251,13 @@ __global__ void __launch_bounds__(THREADS, 1) ffae_fit_kernel(const FitArgs a) {
         const float* Wl = sW + a.im.wofs[l];
         const float* bl = sW + a.im.bofs[l];
         const float l1c = a.net.l1[l] * (a.hp.l1_div_batch ? 1.f : (float)nbt);
+        // cp.async of the next chunk: off the step's critical path (at the head of a chunk it cost 2 k cycles), half of the rows in each of
+        // the two narrowest layers, by the warps without a tile there (a row costs its warp ~700 cycles of dependent address work)
+        if (more && (l == a.gather_layer || l == a.gather_layer2)) {
+          const int busy = min(Np >> 2, NWARPS), first = busy < NWARPS ? busy : 0;
+          const bool both = a.gather_layer == a.gather_layer2, second = l == a.gather_layer;
+          if (warp >= first) gather(cur ^ 1, ne1, ns1, nc1, first, NWARPS - first, (both || !second) ? 0 : BR / 2, (both || second) ? BR : BR / 2);
+        }
         if (l == 0) {  // the last two warps have no tile in the first layer of a 64-tag hourglass (14 tiles): they prepare the next step
           if (warp == NWARPS - 1 && more2) stage_indices(cur, ne, ns, nc);  // read by the gather at the top of the next chunk
           if (warp == NWARPS - 2 && first_chunk && lane == 0) s_alpha[(t_step + 1) & 1] = adam_alpha(t_step + 1);  // read after the loss barrier of step t+1
@@ -562,6 +571,12 @@ int gb_ffae_fit(const gb_ffnet* net, float* params, float* adam_m, float* adam_v
   a.pstride = (long)gb_ffnet_param_stride(net);
   a.sstride = (long)gb_ffae_fit_state_stride(net);
   a.wfloats = gb::round_up(a.im.total, 4);
+  a.gather_layer = 0;
+  for (int l = 1; l < L; ++l)
+    if (a.im.np[l] <= a.im.np[a.gather_layer]) a.gather_layer = l;  // the last of the narrowest layers
+  a.gather_layer2 = a.gather_layer;
+  for (int l = 0, best = 1 << 30; l < L; ++l)
+    if (l != a.gather_layer && a.im.np[l] < best) { best = a.im.np[l]; a.gather_layer2 = l; }  // the narrowest of the others
   size_t smem = 0;
   bool w_global = false;
   // first everything in shared memory; if that does not fit, the weight image in L2; then, one by one, the dz buffers in L2 as well
