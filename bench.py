@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 T = 64
 BYTES_PER_WINDOW = 4 * T + 4 * T + 4 * 4 * T + 12  # read x, y; write model-output, 2 tag-anomaly blocks, confidence; 3 row scalars
 # dram__bytes_read.sum + dram__bytes_write.sum per window from the committed `ncu --set full` captures (profiles/, file names below)
-NCU_DRAM_BYTES_PER_WINDOW = {"tcgen05": (1.568206e9 + 3.049132e9) / 3.0e6, "fma": (1.037003e9 + 2.019607e9) / 2.0e6}
+NCU_DRAM_BYTES_PER_WINDOW = {"tcgen05": (1.569383e9 + 3.048933e9) / 3.0e6, "fma": (1.037003e9 + 2.019607e9) / 2.0e6}
 NCU_SOURCE = {"tcgen05": "profiles/r02_ffae_tc_ncu.txt (300-machine capture)", "fma": "profiles/r01_ffae_infer_fma_ncu.txt (200-machine capture)"}
 METRIC = "anomaly windows/sec (64-tag feedforward_hourglass AE, 1k machines x 10k rows per GPU, fused predict+score)"
 
