@@ -282,6 +282,16 @@ def test_scaler_multiplier():
     np.testing.assert_allclose(_scaler_multiplier(RobustScaler().fit(y), 3), 1 / RobustScaler().fit(y).scale_, rtol=1e-6)
     with pytest.raises(ValueError):
         _scaler_multiplier(QuantileTransformer(n_quantiles=10).fit(y), 3)
+    # the slope of a fitted scaler is probed once per fitted state: a refit (new scale_ / min_ arrays) is seen, a repeat request is not re-probed
+    sc = MinMaxScaler().fit(y)
+    first = _scaler_multiplier(sc, 3)
+    calls = []
+    real_transform = sc.transform
+    sc.transform = lambda X: (calls.append(1), real_transform(X))[1]
+    assert _scaler_multiplier(sc, 3) is first and not calls
+    sc.fit(y * 2.0)
+    np.testing.assert_allclose(_scaler_multiplier(sc, 3), first / 2.0, rtol=1e-12)
+    assert len(calls) == 1
 
 
 # ---------------------------------------------------------------- frame assembly fast paths
