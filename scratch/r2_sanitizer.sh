@@ -10,3 +10,7 @@ K2="generic_architectures or quantile or thresholds_edge or smoothing or float64
 echo -e "\n## racecheck (shared-memory hazards; kernels without tcgen05/TMA async proxies): -k '$K2'" >> $out
 timeout -k 10 1200 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -q -p no:cacheprovider -k "$K2" 2>&1 | grep -E "COMPUTE-SANITIZER|passed|failed|RACECHECK SUMMARY|hazard" | head -20 >> $out
 cat $out
+K3="lstm_infer_tcgen05 or ffae_fit_matches or infer_score_matches"
+echo -e "\n## synccheck (barrier usage: named barriers of the LSTM epilogue groups, cluster barriers, training kernel): -k '$K3'" >> $out
+timeout -k 10 1200 compute-sanitizer --tool synccheck python -m pytest tests -m gpu -q -p no:cacheprovider -k "$K3" 2>&1 | grep -E "COMPUTE-SANITIZER|passed|failed|ERROR SUMMARY|Barrier|error" | head -20 >> $out
+tail -6 $out
