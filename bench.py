@@ -404,10 +404,15 @@ def main():
                         ("configs[4]", lambda: sec.server_shape(torch, engine, fleet))):
             if dist is not None:
                 dist.barrier()
+            side_clocks = ClockSampler(local_rank) if key == "configs[3]" else None  # the LSTM share is power bound: its clock belongs to its number
+            if side_clocks is not None:
+                side_clocks.start()
             try:
                 res = fn()
             except Exception as e:  # a failing side measurement must not take the headline line with it
                 res = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if side_clocks is not None:
+                res["clocks"] = side_clocks.stop()
             if dist is not None and "error" not in res:
                 if "ms" in res:  # device-timed shares: whole job = all ranks' units over the slowest rank's time
                     tm = torch.tensor([res["ms"]], device=dev, dtype=torch.float64)
